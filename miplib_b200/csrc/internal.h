@@ -1,0 +1,151 @@
+// internal.h - context layout and helpers shared by the translation units of libmiplib_cuda.so.
+// Nothing in here is part of the ABI (see include/mipcu.h for that).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/mipcu.h"
+#include "params.h"
+
+namespace mipcu {
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define MIPCU_CK(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      throw ::mipcu::Error(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" +        \
+                           __FILE__ + ":" + std::to_string(__LINE__) + ")");                   \
+  } while (0)
+
+#define MIPCU_REQUIRE(cond, msg)                                                               \
+  do {                                                                                         \
+    if (!(cond)) throw ::mipcu::Error(std::string(msg));                                       \
+  } while (0)
+
+constexpr int kThreads = 256;        // CTA size of every kernel in this library
+constexpr int kRowsPerCta = 256;     // rows (or columns) one CTA of a fused SpMV kernel owns
+
+// One sparse matrix in CSR layout on the device.  The context keeps two: K by rows ("rows")
+// and K' by rows, i.e. K by columns ("cols").  int32 indices: nnz < 2^31 is enforced at load.
+struct Csr {
+  int nrows = 0, ncols = 0;
+  int64_t nnz = 0;
+  int* ptr = nullptr;      // nrows + 1
+  int* idx = nullptr;      // nnz (+ padding)
+  double* val = nullptr;   // nnz (+ padding)
+  int tpr = 8;             // threads per row chosen for this matrix
+};
+
+// Quantities reduced per CTA on check iterations: partials[q * max_blocks + blockIdx.x].
+enum Quantity {
+  Q_DY2 = 0,     // sum (yhat - y)^2                      row step
+  Q_DY0,         // sum (yhat - y0)^2                     row step
+  Q_DOBJ_ROW,    // sum lo yhat+ - hi yhat-               row step
+  Q_PRES2,       // sum ((K xhat - proj)/d1)^2            kkt row pass
+  Q_DX2,         // sum (xhat - x)^2                      col step
+  Q_DXDATY,      // sum (xhat - x)(K'yhat - K'y)          col step
+  Q_DX0,         // sum (xhat - x0)^2                     col step
+  Q_DRES2,       // sum (reduced-cost violation / d2)^2   col step
+  Q_POBJ,        // sum c xhat                            col step
+  Q_DOBJ_COL,    // sum l r+ - u r-                       col step
+  Q_COUNT
+};
+
+// Device-resident control block.  The iteration kernels read it, the single-CTA controller
+// kernels write it, the host only ever copies it out (no host round trip inside a block).
+struct Scalars {
+  double tau, sigma, eta, w;
+  double eps;
+  double bnorm, cnorm;
+  double fp0, fp_prev, fp;
+  double rel_p, rel_d, rel_g, pobj, dobj;
+  long long k_base;     // iterations since the last restart, at the start of the current block
+  long long total;      // iterations done, at the start of the current block
+  int period;
+  int done;             // 0 running; 1 + MIPCU_* status once finished
+  int restart_flag;     // set by the controller, consumed by k_restart_apply
+  int restarts;
+  int nblk_row, nblk_col, max_blocks;
+  int pad_;
+};
+
+}  // namespace mipcu
+
+struct mipcu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  double params[MIPCU_PARAM_COUNT_];
+
+  // sharding (world == 1: plain single-GPU context)
+  int rank = 0, world = 1;
+  void* nccl_comm = nullptr;
+
+  // model as loaded (unscaled), device resident
+  int m = 0, n = 0;
+  int64_t nnz = 0;
+  bool loaded = false, maximize = false;
+  mipcu::Csr rows, cols;                 // scaled IN PLACE by prepare()
+  double *c = nullptr, *lb = nullptr, *ub = nullptr, *lo = nullptr, *hi = nullptr;
+  // scaled copies + diagonal scalings
+  double *cs = nullptr, *ls = nullptr, *us = nullptr, *los = nullptr, *his = nullptr;
+  double *d1 = nullptr, *d2 = nullptr;
+  bool prepared = false;        // matrix scaled, eta known
+  bool vectors_dirty = true;    // scaled vectors / norms must be refreshed (bounds or c changed)
+  double eta = 0, w0 = 1, bnorm = 0, cnorm = 0;
+  double setup_seconds = 0;
+
+  // iterate buffers (scaled space)
+  double *xbar = nullptr, *x0 = nullptr, *aty = nullptr, *aty0 = nullptr, *xhat_first = nullptr,
+         *xhat_chk = nullptr, *aty_cand = nullptr;             // n each
+  double *y = nullptr, *y0 = nullptr, *yhat = nullptr;         // m each
+  double *tmp_n = nullptr, *tmp_m = nullptr;                   // scratch
+  double *x_start = nullptr, *y_start = nullptr;               // warm start (unscaled) or null
+  double *x_sol = nullptr, *y_sol = nullptr;                   // last solution (unscaled)
+  bool has_solution = false;
+
+  double* partials = nullptr;
+  int max_blocks = 0;
+  mipcu::Scalars* d_sc = nullptr;
+  mipcu::Scalars* h_sc = nullptr;   // pinned, 2 slots
+
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_period = 0;
+  cudaEvent_t ev[12] = {};
+  void* flush_buf = nullptr;
+
+  int64_t launches = 0;   // kernels launched by the current call
+};
+
+namespace mipcu {
+
+// ---- setup.cu -------------------------------------------------------------------------------
+void free_model(mipcu_ctx* ctx);
+void load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr,
+             const int32_t* col_idx, const double* val, const double* c, const double* lb,
+             const double* ub, const double* row_lo, const double* row_hi, int maximize);
+void prepare(mipcu_ctx* ctx);           // scaling + step size (once per load)
+void refresh_vectors(mipcu_ctx* ctx);   // scaled c / bounds / norms / w0 (after bound changes)
+void spmv_plain(mipcu_ctx* ctx, const Csr& A, const double* v, double* out);
+double device_norm2(mipcu_ctx* ctx, const double* v, int64_t len);
+int choose_tpr(double avg_row_len, int override_tpr);
+void spmv_host(mipcu_ctx* ctx, int transpose, const double* v, double* out);
+
+// ---- solve.cu -------------------------------------------------------------------------------
+void solve_lp(mipcu_ctx* ctx, mipcu_stats* out);
+void debug_iterate(mipcu_ctx* ctx, int64_t iters, double* xbar_out, double* y_out);
+void time_kernel(mipcu_ctx* ctx, int which, int reps, int flush_l2, double* mean_us,
+                 int64_t* bytes);
+int64_t row_kernel_bytes(const mipcu_ctx* ctx);
+int64_t col_kernel_bytes(const mipcu_ctx* ctx);
+
+}  // namespace mipcu

@@ -1,0 +1,231 @@
+// kernels.cuh - the per-iteration kernels of the restarted reflected-Halpern PDHG method.
+//
+// One PDHG iteration is TWO kernel launches and nothing else:
+//   k_row_step : (K xbar)_i by a sub-warp per row, then - in the same CTA, coalesced over the
+//                CTA's 256 rows - the dual proximal step, the Halpern/reflection update of y and,
+//                on check iterations, the per-CTA partial sums the restart test needs;
+//   k_col_step : (K' yhat)_j by a sub-warp per column of the CSC copy, then the Halpern update of
+//                x and K'y, the projected primal step and the reflected point xbar that the next
+//                k_row_step gathers.
+// All scalars (tau, sigma, the Halpern weight) are read from the device-resident control block,
+// so a block of `period` iterations runs with no host involvement and can be graph-captured.
+//
+// The arithmetic is restated line for line in oracle/pdhg_ref.py (row_step / col_step /
+// kkt_scaled); tests/test_parity_gpu.py compares the two.
+#pragma once
+
+#include "internal.h"
+
+namespace mipcu {
+
+__device__ __forceinline__ double ld_stream(const double* p) {
+  // matrix values are touched once per launch: keep them out of L1
+  double v;
+  asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream(const int* p) {
+  int v;
+  asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ double clampd(double v, double lo, double hi) {
+  return fmin(fmax(v, lo), hi);
+}
+
+// Sum of A[row, :] * vec for the kRowsPerCta rows owned by this CTA, left in s_sum[0..kRowsPerCta).
+// TPR lanes cooperate on one row; a warp therefore streams 32/TPR consecutive rows, i.e. one
+// contiguous span of the val/idx arrays.  Two independent (val, idx, gather) chains per lane are
+// kept in flight to cover the L2 gather latency.
+template <int TPR>
+__device__ __forceinline__ void cta_row_sums(const int* __restrict__ ptr,
+                                             const int* __restrict__ idx,
+                                             const double* __restrict__ val,
+                                             const double* __restrict__ vec, int nrows,
+                                             double* s_sum) {
+  constexpr int SUBS = kThreads / TPR;        // rows in flight per pass
+  const int lane = threadIdx.x % TPR;
+  const int sub = threadIdx.x / TPR;
+  const int row0 = blockIdx.x * kRowsPerCta;
+#pragma unroll 2
+  for (int r = sub; r < kRowsPerCta; r += SUBS) {
+    const int row = row0 + r;
+    double acc0 = 0.0, acc1 = 0.0;
+    if (row < nrows) {
+      const int b = ptr[row], e = ptr[row + 1];
+      int k = b + lane;
+      for (; k + TPR < e; k += 2 * TPR) {
+        const double v0 = ld_stream(val + k);
+        const int c0 = ld_stream(idx + k);
+        const double v1 = ld_stream(val + k + TPR);
+        const int c1 = ld_stream(idx + k + TPR);
+        acc0 = fma(v0, __ldg(vec + c0), acc0);
+        acc1 = fma(v1, __ldg(vec + c1), acc1);
+      }
+      if (k < e) acc0 = fma(ld_stream(val + k), __ldg(vec + ld_stream(idx + k)), acc0);
+    }
+    double acc = acc0 + acc1;
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, TPR);
+    if (lane == 0) s_sum[r] = acc;
+  }
+  __syncthreads();
+}
+
+// Deterministic CTA reduction of NQ running sums; thread 0 stores them to
+// partials[(q0 + q) * max_blocks + blockIdx.x].
+template <int NQ>
+__device__ __forceinline__ void cta_reduce_store(double (&v)[NQ], const int (&q)[NQ],
+                                                 double* partials, int max_blocks) {
+  __shared__ double s_red[NQ][kThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    double a = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    if (lane == 0) s_red[i][warp] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < NQ) {
+    double a = 0.0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) a += s_red[threadIdx.x][w];
+    partials[(size_t)q[threadIdx.x] * max_blocks + blockIdx.x] = a;
+  }
+}
+
+struct RowStepArgs {
+  const int* ptr; const int* idx; const double* val;   // K by rows
+  const double* xbar;                                   // gathered
+  const double* lo; const double* hi; const double* y0;
+  double* y; double* yhat;
+  const Scalars* sc; double* partials;
+  int m; int iter_in_block;
+};
+
+template <int TPR, bool CHECK>
+__global__ void __launch_bounds__(kThreads)
+k_row_step(const RowStepArgs a) {
+  __shared__ double s_sum[kRowsPerCta];
+  const Scalars* sc = a.sc;
+  if (sc->done) return;
+  cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.xbar, a.m, s_sum);
+  const double sigma = sc->sigma;
+  const double k = (double)(sc->k_base + a.iter_in_block);
+  const double w_new = (k + 1.0) / (k + 2.0);
+  const int i = blockIdx.x * kRowsPerCta + threadIdx.x;
+  double red[3] = {0.0, 0.0, 0.0};
+  if (i < a.m) {
+    const double kx = s_sum[threadIdx.x];
+    const double yi = a.y[i], y0i = a.y0[i], lo = a.lo[i], hi = a.hi[i];
+    const double t = kx - yi / sigma;
+    const double yh = sigma * (clampd(t, lo, hi) - t);
+    a.yhat[i] = yh;
+    a.y[i] = w_new * (2.0 * yh - yi) + (1.0 - w_new) * y0i;
+    if (CHECK) {
+      const double dy = yh - yi, d0 = yh - y0i;
+      red[0] = dy * dy;
+      red[1] = d0 * d0;
+      const double yp = fmax(yh, 0.0), ym = fmax(-yh, 0.0);
+      red[2] = (isfinite(lo) ? lo * yp : 0.0) - (isfinite(hi) ? hi * ym : 0.0);
+    }
+  }
+  if (CHECK) {
+    const int q[3] = {Q_DY2, Q_DY0, Q_DOBJ_ROW};
+    cta_reduce_store<3>(red, q, a.partials, sc->max_blocks);
+  }
+}
+
+struct ColStepArgs {
+  const int* ptr; const int* idx; const double* val;   // K by columns (CSR of K')
+  const double* yhat;                                   // gathered
+  const double* x0; const double* aty0; const double* c; const double* l; const double* u;
+  const double* d2;
+  double* xbar; double* aty;
+  const double* xhat_in;     // CHECK: xhat of this iteration (stored by the previous col step)
+  double* xhat_out;          // STORE: xhat of the NEXT iteration
+  double* aty_cand;          // CHECK: K' yhat (restart candidate)
+  const Scalars* sc; double* partials;
+  int n; int iter_in_block;
+};
+
+template <int TPR, bool CHECK, bool STORE>
+__global__ void __launch_bounds__(kThreads)
+k_col_step(const ColStepArgs a) {
+  __shared__ double s_sum[kRowsPerCta];
+  const Scalars* sc = a.sc;
+  if (sc->done) return;
+  cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.yhat, a.n, s_sum);
+  const double tau = sc->tau;
+  const double k = (double)(sc->k_base + a.iter_in_block);
+  const double w_new = (k + 1.0) / (k + 2.0);
+  const int j = blockIdx.x * kRowsPerCta + threadIdx.x;
+  double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (j < a.n) {
+    const double atyh = s_sum[threadIdx.x];
+    const double xb = a.xbar[j], x0 = a.x0[j], at = a.aty[j], at0 = a.aty0[j];
+    const double cj = a.c[j], lj = a.l[j], uj = a.u[j];
+    if (CHECK) {
+      const double xh = a.xhat_in[j];
+      const double dx = xb - xh;            // = xhat_k - x_k  because xbar = 2 xhat - x
+      const double dat = atyh - at;
+      const double d0 = xh - x0;
+      red[0] = dx * dx;
+      red[1] = dx * dat;
+      red[2] = d0 * d0;
+      const double r = cj - atyh;
+      const double rp = fmax(r, 0.0), rm = fmax(-r, 0.0);
+      const double viol = ((isfinite(lj) ? 0.0 : rp) + (isfinite(uj) ? 0.0 : rm)) / a.d2[j];
+      red[3] = viol * viol;
+      red[4] = cj * xh;
+      red[5] = (isfinite(lj) ? lj * rp : 0.0) - (isfinite(uj) ? uj * rm : 0.0);
+      a.aty_cand[j] = atyh;
+    }
+    const double xn = w_new * xb + (1.0 - w_new) * x0;
+    const double atn = w_new * (2.0 * atyh - at) + (1.0 - w_new) * at0;
+    const double xh2 = clampd(xn - tau * (cj - atn), lj, uj);
+    a.xbar[j] = 2.0 * xh2 - xn;
+    a.aty[j] = atn;
+    if (STORE) a.xhat_out[j] = xh2;
+  }
+  if (CHECK) {
+    const int q[6] = {Q_DX2, Q_DXDATY, Q_DX0, Q_DRES2, Q_POBJ, Q_DOBJ_COL};
+    cta_reduce_store<6>(red, q, a.partials, sc->max_blocks);
+  }
+}
+
+// Primal residual of xhat on check iterations: sum ((K xhat - clamp(K xhat, lo, hi)) / d1)^2.
+template <int TPR>
+__global__ void __launch_bounds__(kThreads)
+k_kkt_row(const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
+          const double* __restrict__ xhat, const double* __restrict__ lo,
+          const double* __restrict__ hi, const double* __restrict__ d1, const Scalars* sc,
+          double* partials, int m) {
+  __shared__ double s_sum[kRowsPerCta];
+  if (sc->done) return;
+  cta_row_sums<TPR>(ptr, idx, val, xhat, m, s_sum);
+  const int i = blockIdx.x * kRowsPerCta + threadIdx.x;
+  double red[1] = {0.0};
+  if (i < m) {
+    const double kx = s_sum[threadIdx.x];
+    const double v = (kx - clampd(kx, lo[i], hi[i])) / d1[i];
+    red[0] = v * v;
+  }
+  const int q[1] = {Q_PRES2};
+  cta_reduce_store<1>(red, q, partials, sc->max_blocks);
+}
+
+// Plain out = A v through the same row-sum routine (setup, power iteration, test hook).
+template <int TPR>
+__global__ void __launch_bounds__(kThreads)
+k_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
+       const double* __restrict__ v, double* __restrict__ out, int nrows) {
+  __shared__ double s_sum[kRowsPerCta];
+  cta_row_sums<TPR>(ptr, idx, val, v, nrows, s_sum);
+  const int i = blockIdx.x * kRowsPerCta + threadIdx.x;
+  if (i < nrows) out[i] = s_sum[threadIdx.x];
+}
+
+}  // namespace mipcu

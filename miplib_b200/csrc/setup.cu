@@ -1,0 +1,525 @@
+// setup.cu - everything that happens once per model: upload, CSC (= CSR of K') construction,
+// Ruiz + Pock-Chambolle equilibration of both copies in place, step-size estimate.
+// Restated on the CPU by oracle/pdhg_ref.py: ruiz_pc_scale / spectral_norm / prepare.
+#include <cub/cub.cuh>
+
+#include <chrono>
+#include <cmath>
+
+#include "internal.h"
+#include "kernels.cuh"
+
+namespace mipcu {
+
+namespace {
+
+inline int grid_for(int64_t n, int per_block = kThreads) {
+  return (int)((n + per_block - 1) / per_block);
+}
+
+template <class T>
+T* dalloc(int64_t count) {
+  T* p = nullptr;
+  MIPCU_CK(cudaMalloc(&p, sizeof(T) * (size_t)(count > 0 ? count : 1)));
+  return p;
+}
+
+template <class T>
+void dfree(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+__global__ void k_narrow_ptr(const long long* __restrict__ in, int* __restrict__ out, int count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = (int)in[i];
+}
+
+// |v| >= INF_THRESHOLD (the MIPCU_INF sentinel, SCIP's 1e20, lp_solve's 1e30) -> IEEE infinity
+__global__ void k_sanitize_inf(double* v, int count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    double x = v[i];
+    if (x >= INF_THRESHOLD) v[i] = INFINITY;
+    else if (x <= -INF_THRESHOLD) v[i] = -INFINITY;
+  }
+}
+
+__global__ void k_expand_rows(const int* __restrict__ ptr, int* __restrict__ row_of, int nrows) {
+  // one warp per row (rows are short; long rows just loop)
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp < nrows)
+    for (int k = ptr[warp] + lane; k < ptr[warp + 1]; k += 32) row_of[k] = warp;
+}
+
+__global__ void k_iota(int* v, int64_t count) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) v[i] = (int)i;
+}
+
+__global__ void k_count(const int* __restrict__ keys, int* __restrict__ counts, int64_t count) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) atomicAdd(counts + keys[i], 1);
+}
+
+__global__ void k_permute(const int* __restrict__ perm, const int* __restrict__ row_of,
+                          const double* __restrict__ val, int* __restrict__ out_idx,
+                          double* __restrict__ out_val, int64_t count) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    int p = perm[i];
+    out_idx[i] = row_of[p];
+    out_val[i] = val[p];
+  }
+}
+
+__global__ void k_check_sorted(const int* __restrict__ ptr, const int* __restrict__ idx, int nrows,
+                               int ncols, int* bad) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp < nrows) {
+    int b = ptr[warp], e = ptr[warp + 1];
+    if (e < b) { *bad = 1; return; }
+    for (int k = b + lane; k < e; k += 32) {
+      int c = idx[k];
+      if (c < 0 || c >= ncols) *bad = 2;
+      if (k > b && idx[k - 1] >= c) *bad = 3;
+    }
+  }
+}
+
+// per-row max |a| (MODE 0) or sum |a| (MODE 1), one sub-warp of 8 lanes per row
+template <int MODE>
+__global__ void k_row_norm(const int* __restrict__ ptr, const double* __restrict__ val,
+                           double* __restrict__ out, int nrows) {
+  constexpr int TPR = 8;
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) / TPR, lane = threadIdx.x % TPR;
+  double a = 0.0;
+  if (row < nrows)
+    for (int k = ptr[row] + lane; k < ptr[row + 1]; k += TPR) {
+      double v = fabs(val[k]);
+      a = MODE == 0 ? fmax(a, v) : a + v;
+    }
+#pragma unroll
+  for (int o = TPR / 2; o > 0; o >>= 1) {
+    double b = __shfl_down_sync(0xffffffffu, a, o, TPR);
+    a = MODE == 0 ? fmax(a, b) : a + b;
+  }
+  if (row < nrows && lane == 0) out[row] = a;
+}
+
+// norm -> factor 1/sqrt(norm) (1 for empty rows); d *= factor
+__global__ void k_factor(double* __restrict__ norm_io, double* __restrict__ d, int count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    double nv = norm_io[i];
+    double f = nv > 0.0 ? 1.0 / sqrt(nv) : 1.0;
+    norm_io[i] = f;
+    d[i] *= f;
+  }
+}
+
+// val <- (val * rfac[row_of_entry]) * cfac[col_of_entry], the same expression on both copies.
+// OUTER_IS_ROW: this copy's outer index is the matrix row (CSR of K); else it is the column.
+template <bool OUTER_IS_ROW>
+__global__ void k_scale_matrix(const int* __restrict__ ptr, const int* __restrict__ idx,
+                               double* __restrict__ val, const double* __restrict__ rfac,
+                               const double* __restrict__ cfac, int nouter) {
+  constexpr int TPR = 8;
+  int o = (blockIdx.x * blockDim.x + threadIdx.x) / TPR, lane = threadIdx.x % TPR;
+  if (o < nouter) {
+    const double fo = OUTER_IS_ROW ? rfac[o] : cfac[o];
+    for (int k = ptr[o] + lane; k < ptr[o + 1]; k += TPR) {
+      const double fi = OUTER_IS_ROW ? cfac[idx[k]] : rfac[idx[k]];
+      val[k] = OUTER_IS_ROW ? (val[k] * fo) * fi : (val[k] * fi) * fo;
+    }
+  }
+}
+
+__global__ void k_fill(double* v, double a, int count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) v[i] = a;
+}
+
+__global__ void k_mul(const double* __restrict__ a, const double* __restrict__ b,
+                      double* __restrict__ out, int count, double s) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = s * a[i] * b[i];
+}
+
+__global__ void k_div(const double* __restrict__ a, const double* __restrict__ b,
+                      double* __restrict__ out, int count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = a[i] / b[i];
+}
+
+__global__ void k_scale_inplace(double* v, double s, int count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) v[i] *= s;
+}
+
+__global__ void k_hash_vector(double* v, int count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    unsigned long long h = ((unsigned long long)i * 2654435761ull) & 0xFFFFFFFFull;
+    v[i] = (double)h / 4294967296.0 + 0.5;
+  }
+}
+
+// MODE 0: sum v^2 ; MODE 1: sum max(|lo| finite, |hi| finite)^2 with b = second array
+template <int MODE>
+__global__ void k_sumsq_partial(const double* __restrict__ a, const double* __restrict__ b,
+                                double* __restrict__ partials, int64_t count) {
+  __shared__ double s[kThreads / 32];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double v;
+    if (MODE == 0) v = a[i];
+    else {
+      double lo = a[i], hi = b[i];
+      v = fmax(isfinite(lo) ? fabs(lo) : 0.0, isfinite(hi) ? fabs(hi) : 0.0);
+    }
+    acc += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) t += s[w];
+    partials[blockIdx.x] = t;
+  }
+}
+
+template <int MODE>
+double sumsq(mipcu_ctx* ctx, const double* a, const double* b, int64_t count) {
+  if (count <= 0) return 0.0;
+  int blocks = (int)std::min<int64_t>(grid_for(count), 1024);
+  k_sumsq_partial<MODE><<<blocks, kThreads, 0, ctx->stream>>>(a, b, ctx->partials, count);
+  ctx->launches++;
+  std::vector<double> h(blocks);
+  MIPCU_CK(cudaMemcpyAsync(h.data(), ctx->partials, sizeof(double) * blocks, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  MIPCU_CK(cudaStreamSynchronize(ctx->stream));
+  double t = 0.0;
+  for (double v : h) t += v;
+  return t;
+}
+
+template <int TPR>
+void launch_spmv(mipcu_ctx* ctx, const Csr& A, const double* v, double* out) {
+  if (A.nrows == 0) return;
+  k_spmv<TPR><<<grid_for(A.nrows, kRowsPerCta), kThreads, 0, ctx->stream>>>(A.ptr, A.idx, A.val, v,
+                                                                           out, A.nrows);
+  ctx->launches++;
+}
+
+// CSR of the transpose on the device: stable radix sort of (col, position) pairs, so the entries
+// of every column come out in increasing row order (deterministic summation order).
+void build_transpose(mipcu_ctx* ctx, const Csr& A, Csr& T) {
+  cudaStream_t st = ctx->stream;
+  T.nrows = A.ncols;
+  T.ncols = A.nrows;
+  T.nnz = A.nnz;
+  T.ptr = dalloc<int>(T.nrows + 1);
+  T.idx = dalloc<int>(T.nnz + 4);
+  T.val = dalloc<double>(T.nnz + 4);
+  MIPCU_CK(cudaMemsetAsync(T.ptr, 0, sizeof(int) * (T.nrows + 1), st));
+  MIPCU_CK(cudaMemsetAsync(T.idx + T.nnz, 0, sizeof(int) * 4, st));
+  MIPCU_CK(cudaMemsetAsync(T.val + T.nnz, 0, sizeof(double) * 4, st));
+  if (A.nnz == 0) return;
+  int* row_of = dalloc<int>(A.nnz);
+  int* pos = dalloc<int>(A.nnz);
+  int* keys_out = dalloc<int>(A.nnz);
+  int* perm = dalloc<int>(A.nnz);
+  int* counts = dalloc<int>(T.nrows + 1);
+  k_expand_rows<<<grid_for((int64_t)A.nrows * 32), kThreads, 0, st>>>(A.ptr, row_of, A.nrows);
+  k_iota<<<grid_for(A.nnz), kThreads, 0, st>>>(pos, A.nnz);
+  MIPCU_CK(cudaMemsetAsync(counts, 0, sizeof(int) * (T.nrows + 1), st));
+  k_count<<<grid_for(A.nnz), kThreads, 0, st>>>(A.idx, counts, A.nnz);
+  ctx->launches += 3;
+  int end_bit = 1;
+  while ((1ll << end_bit) < (long long)A.ncols && end_bit < 31) ++end_bit;
+  size_t tmp_bytes = 0, tmp2 = 0;
+  MIPCU_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, A.idx, keys_out, pos, perm,
+                                           (int)A.nnz, 0, end_bit, st));
+  MIPCU_CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, counts, T.ptr, T.nrows + 1, st));
+  void* tmp = nullptr;
+  MIPCU_CK(cudaMalloc(&tmp, std::max(tmp_bytes, tmp2) + 16));
+  MIPCU_CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, A.idx, keys_out, pos, perm, (int)A.nnz,
+                                           0, end_bit, st));
+  MIPCU_CK(cub::DeviceScan::ExclusiveSum(tmp, tmp2, counts, T.ptr, T.nrows + 1, st));
+  k_permute<<<grid_for(A.nnz), kThreads, 0, st>>>(perm, row_of, A.val, T.idx, T.val, A.nnz);
+  ctx->launches++;
+  MIPCU_CK(cudaStreamSynchronize(st));
+  cudaFree(tmp);
+  dfree(row_of); dfree(pos); dfree(keys_out); dfree(perm); dfree(counts);
+}
+
+void free_csr(Csr& A) {
+  dfree(A.ptr); dfree(A.idx); dfree(A.val);
+  A = Csr();
+}
+
+}  // namespace
+
+int choose_tpr(double avg, int override_tpr) {
+  if (override_tpr == 2 || override_tpr == 4 || override_tpr == 8 || override_tpr == 16 ||
+      override_tpr == 32)
+    return override_tpr;
+  if (avg <= 3.0) return 2;
+  if (avg <= 6.0) return 4;
+  if (avg <= 24.0) return 8;
+  if (avg <= 96.0) return 16;
+  return 32;
+}
+
+void spmv_plain(mipcu_ctx* ctx, const Csr& A, const double* v, double* out) {
+  switch (A.tpr) {
+    case 2: launch_spmv<2>(ctx, A, v, out); break;
+    case 4: launch_spmv<4>(ctx, A, v, out); break;
+    case 8: launch_spmv<8>(ctx, A, v, out); break;
+    case 16: launch_spmv<16>(ctx, A, v, out); break;
+    default: launch_spmv<32>(ctx, A, v, out); break;
+  }
+}
+
+double device_norm2(mipcu_ctx* ctx, const double* v, int64_t len) {
+  return std::sqrt(sumsq<0>(ctx, v, nullptr, len));
+}
+
+void free_model(mipcu_ctx* ctx) {
+  free_csr(ctx->rows);
+  free_csr(ctx->cols);
+  double** vecs[] = {&ctx->c, &ctx->lb, &ctx->ub, &ctx->lo, &ctx->hi, &ctx->cs, &ctx->ls, &ctx->us,
+                     &ctx->los, &ctx->his, &ctx->d1, &ctx->d2, &ctx->xbar, &ctx->x0, &ctx->aty,
+                     &ctx->aty0, &ctx->xhat_first, &ctx->xhat_chk, &ctx->aty_cand, &ctx->y,
+                     &ctx->y0, &ctx->yhat, &ctx->tmp_n, &ctx->tmp_m, &ctx->x_start, &ctx->y_start,
+                     &ctx->x_sol, &ctx->y_sol, &ctx->partials};
+  for (double** p : vecs) dfree(*p);
+  if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+  ctx->graph_period = 0;
+  ctx->loaded = ctx->prepared = ctx->has_solution = false;
+  ctx->vectors_dirty = true;
+}
+
+void load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr,
+             const int32_t* col_idx, const double* val, const double* c, const double* lb,
+             const double* ub, const double* row_lo, const double* row_hi, int maximize) {
+  MIPCU_REQUIRE(m >= 0 && n >= 0 && nnz >= 0, "mipcu_load_lp: negative dimension");
+  MIPCU_REQUIRE(m < (1ll << 31) - 1024 && n < (1ll << 31) - 1024 && nnz < (1ll << 31) - 1024,
+                "mipcu_load_lp: dimensions beyond int32 indexing are not supported");
+  MIPCU_REQUIRE(row_ptr && (nnz == 0 || (col_idx && val)), "mipcu_load_lp: null matrix array");
+  MIPCU_REQUIRE(n == 0 || (c && lb && ub), "mipcu_load_lp: null column array");
+  MIPCU_REQUIRE(m == 0 || (row_lo && row_hi), "mipcu_load_lp: null row array");
+  MIPCU_REQUIRE(row_ptr[0] == 0 && row_ptr[m] == nnz, "mipcu_load_lp: row_ptr[0] != 0 or row_ptr[m] != nnz");
+  MIPCU_CK(cudaSetDevice(ctx->device));
+  free_model(ctx);
+  cudaStream_t st = ctx->stream;
+  ctx->m = (int)m; ctx->n = (int)n; ctx->nnz = nnz; ctx->maximize = maximize != 0;
+
+  Csr& A = ctx->rows;
+  A.nrows = (int)m; A.ncols = (int)n; A.nnz = nnz;
+  A.ptr = dalloc<int>(m + 1);
+  A.idx = dalloc<int>(nnz + 4);
+  A.val = dalloc<double>(nnz + 4);
+  {
+    long long* tmp64 = dalloc<long long>(m + 1);
+    MIPCU_CK(cudaMemcpyAsync(tmp64, row_ptr, sizeof(int64_t) * (m + 1), cudaMemcpyHostToDevice, st));
+    k_narrow_ptr<<<grid_for(m + 1), kThreads, 0, st>>>(tmp64, A.ptr, (int)(m + 1));
+    ctx->launches++;
+    MIPCU_CK(cudaStreamSynchronize(st));
+    cudaFree(tmp64);
+  }
+  MIPCU_CK(cudaMemsetAsync(A.idx + nnz, 0, sizeof(int) * 4, st));
+  MIPCU_CK(cudaMemsetAsync(A.val + nnz, 0, sizeof(double) * 4, st));
+  if (nnz) {
+    MIPCU_CK(cudaMemcpyAsync(A.idx, col_idx, sizeof(int) * nnz, cudaMemcpyHostToDevice, st));
+    MIPCU_CK(cudaMemcpyAsync(A.val, val, sizeof(double) * nnz, cudaMemcpyHostToDevice, st));
+  }
+  // structural validation on the device (sorted, in range)
+  {
+    int* bad = dalloc<int>(1);
+    MIPCU_CK(cudaMemsetAsync(bad, 0, sizeof(int), st));
+    if (m) {
+      k_check_sorted<<<grid_for((int64_t)m * 32), kThreads, 0, st>>>(A.ptr, A.idx, (int)m, (int)n, bad);
+      ctx->launches++;
+    }
+    int hbad = 0;
+    MIPCU_CK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MIPCU_CK(cudaStreamSynchronize(st));
+    cudaFree(bad);
+    if (hbad) {
+      free_model(ctx);
+      throw Error(hbad == 1 ? "mipcu_load_lp: row_ptr is not non-decreasing"
+                  : hbad == 2 ? "mipcu_load_lp: column index out of range"
+                              : "mipcu_load_lp: column indices must be strictly increasing inside a row");
+    }
+  }
+  build_transpose(ctx, A, ctx->cols);
+  int tpr_override = (int)ctx->params[MIPCU_PARAM_THREADS_PER_ROW];
+  A.tpr = choose_tpr(m ? (double)nnz / (double)m : 0.0, tpr_override);
+  ctx->cols.tpr = choose_tpr(n ? (double)nnz / (double)n : 0.0, tpr_override);
+
+  auto upload = [&](double*& dst, const double* src, int64_t count, bool sanitize) {
+    dst = dalloc<double>(count);
+    if (count) {
+      MIPCU_CK(cudaMemcpyAsync(dst, src, sizeof(double) * count, cudaMemcpyHostToDevice, st));
+      if (sanitize) {
+        k_sanitize_inf<<<grid_for(count), kThreads, 0, st>>>(dst, (int)count);
+        ctx->launches++;
+      }
+    }
+  };
+  upload(ctx->c, c, n, false);
+  upload(ctx->lb, lb, n, true);
+  upload(ctx->ub, ub, n, true);
+  upload(ctx->lo, row_lo, m, true);
+  upload(ctx->hi, row_hi, m, true);
+
+  double** nvecs[] = {&ctx->cs, &ctx->ls, &ctx->us, &ctx->d2, &ctx->xbar, &ctx->x0, &ctx->aty,
+                      &ctx->aty0, &ctx->xhat_first, &ctx->xhat_chk, &ctx->aty_cand, &ctx->tmp_n,
+                      &ctx->x_sol};
+  for (double** p : nvecs) *p = dalloc<double>(n);
+  double** mvecs[] = {&ctx->los, &ctx->his, &ctx->d1, &ctx->y, &ctx->y0, &ctx->yhat, &ctx->tmp_m,
+                      &ctx->y_sol};
+  for (double** p : mvecs) *p = dalloc<double>(m);
+  ctx->max_blocks = std::max(1024, std::max(grid_for(m, kRowsPerCta), grid_for(n, kRowsPerCta)));
+  ctx->partials = dalloc<double>((int64_t)Q_COUNT * ctx->max_blocks);
+  MIPCU_CK(cudaMemsetAsync(ctx->partials, 0, sizeof(double) * Q_COUNT * ctx->max_blocks, st));
+  if (n) { k_fill<<<grid_for(n), kThreads, 0, st>>>(ctx->d2, 1.0, (int)n); ctx->launches++; }
+  if (m) { k_fill<<<grid_for(m), kThreads, 0, st>>>(ctx->d1, 1.0, (int)m); ctx->launches++; }
+  MIPCU_CK(cudaStreamSynchronize(st));
+  ctx->loaded = true;
+  ctx->prepared = false;
+  ctx->vectors_dirty = true;
+}
+
+// Ruiz x RUIZ_PASSES (row/col max-abs) then Pock-Chambolle alpha = 1 (row/col 1-norms), applied
+// in place to both copies; then eta = STEP_SAFETY / sigma_max(K) by power iteration.
+void prepare(mipcu_ctx* ctx) {
+  MIPCU_REQUIRE(ctx->loaded, "no model loaded");
+  if (ctx->prepared) return;
+  auto t0 = std::chrono::steady_clock::now();
+  cudaStream_t st = ctx->stream;
+  const int m = ctx->m, n = ctx->n;
+  Csr &R = ctx->rows, &C = ctx->cols;
+  const bool scaling = ctx->params[MIPCU_PARAM_SCALING] != 0.0;
+  if (scaling && ctx->nnz > 0) {
+    double* rf = ctx->tmp_m;
+    double* cf = ctx->tmp_n;
+    for (int sweep = 0; sweep < RUIZ_PASSES + 1; ++sweep) {
+      const int gr = grid_for((int64_t)m * 8), gc = grid_for((int64_t)n * 8);
+      if (sweep < RUIZ_PASSES) {
+        k_row_norm<0><<<gr, kThreads, 0, st>>>(R.ptr, R.val, rf, m);
+        k_row_norm<0><<<gc, kThreads, 0, st>>>(C.ptr, C.val, cf, n);
+      } else {
+        k_row_norm<1><<<gr, kThreads, 0, st>>>(R.ptr, R.val, rf, m);
+        k_row_norm<1><<<gc, kThreads, 0, st>>>(C.ptr, C.val, cf, n);
+      }
+      k_factor<<<grid_for(m), kThreads, 0, st>>>(rf, ctx->d1, m);
+      k_factor<<<grid_for(n), kThreads, 0, st>>>(cf, ctx->d2, n);
+      k_scale_matrix<true><<<gr, kThreads, 0, st>>>(R.ptr, R.idx, R.val, rf, cf, m);
+      k_scale_matrix<false><<<gc, kThreads, 0, st>>>(C.ptr, C.idx, C.val, rf, cf, n);
+      ctx->launches += 6;
+    }
+  }
+  // step size
+  double step = ctx->params[MIPCU_PARAM_STEP_SIZE];
+  if (step > 0.0) {
+    ctx->eta = step;
+  } else if (ctx->nnz == 0 || n == 0 || m == 0) {
+    ctx->eta = 1.0;
+  } else {
+    double* v = ctx->tmp_n;
+    double* u = ctx->tmp_m;
+    k_hash_vector<<<grid_for(n), kThreads, 0, st>>>(v, n);
+    ctx->launches++;
+    double nv = device_norm2(ctx, v, n);
+    k_scale_inplace<<<grid_for(n), kThreads, 0, st>>>(v, 1.0 / nv, n);
+    ctx->launches++;
+    double prev = 0.0, s = 0.0;
+    int it = 0;
+    bool zero = false;
+    while (it < POWER_MAX && !zero) {
+      double s2 = 0.0;
+      for (int b = 0; b < POWER_BATCH; ++b) {
+        spmv_plain(ctx, R, v, u);
+        spmv_plain(ctx, C, u, v);
+        s2 = device_norm2(ctx, v, n);
+        if (s2 == 0.0) { zero = true; break; }
+        k_scale_inplace<<<grid_for(n), kThreads, 0, st>>>(v, 1.0 / s2, n);
+        ctx->launches++;
+        ++it;
+      }
+      if (zero) break;
+      s = std::sqrt(s2);
+      if (std::fabs(s - prev) <= POWER_TOL * s) break;
+      prev = s;
+    }
+    ctx->eta = (!zero && s > 0.0) ? STEP_SAFETY / s : 1.0;
+  }
+  MIPCU_CK(cudaStreamSynchronize(st));
+  ctx->prepared = true;
+  ctx->vectors_dirty = true;
+  ctx->setup_seconds =
+      std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// scaled c / bounds / row sides, the norms of the termination test and the initial primal weight
+void refresh_vectors(mipcu_ctx* ctx) {
+  if (!ctx->vectors_dirty) return;
+  cudaStream_t st = ctx->stream;
+  const int m = ctx->m, n = ctx->n;
+  const double sgn = ctx->maximize ? -1.0 : 1.0;
+  if (n) {
+    k_mul<<<grid_for(n), kThreads, 0, st>>>(ctx->c, ctx->d2, ctx->cs, n, sgn);
+    k_div<<<grid_for(n), kThreads, 0, st>>>(ctx->lb, ctx->d2, ctx->ls, n);
+    k_div<<<grid_for(n), kThreads, 0, st>>>(ctx->ub, ctx->d2, ctx->us, n);
+    ctx->launches += 3;
+  }
+  if (m) {
+    k_mul<<<grid_for(m), kThreads, 0, st>>>(ctx->lo, ctx->d1, ctx->los, m, 1.0);
+    k_mul<<<grid_for(m), kThreads, 0, st>>>(ctx->hi, ctx->d1, ctx->his, m, 1.0);
+    ctx->launches += 2;
+  }
+  ctx->cnorm = std::sqrt(sumsq<0>(ctx, ctx->c, nullptr, n));
+  ctx->bnorm = std::sqrt(sumsq<1>(ctx, ctx->lo, ctx->hi, m));
+  double cs = std::sqrt(sumsq<0>(ctx, ctx->cs, nullptr, n));
+  double bs = std::sqrt(sumsq<1>(ctx, ctx->los, ctx->his, m));
+  ctx->w0 = (cs > 0.0 && bs > 0.0) ? cs / bs : 1.0;
+  ctx->vectors_dirty = false;
+}
+
+// test hook: out = A v (or A' v) on the matrix AS LOADED.  Once prepare() has equilibrated the
+// copies in place, A = D1^-1 K D2^-1, so the input is divided by one diagonal and the output by
+// the other around the same SpMV kernel.
+void spmv_host(mipcu_ctx* ctx, int transpose, const double* v, double* out) {
+  MIPCU_REQUIRE(ctx->loaded, "mipcu_spmv: no model loaded");
+  MIPCU_REQUIRE(v && out, "mipcu_spmv: null array");
+  MIPCU_CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int n_in = transpose ? ctx->m : ctx->n, n_out = transpose ? ctx->n : ctx->m;
+  double* d_in = transpose ? ctx->tmp_m : ctx->tmp_n;
+  double* d_out = transpose ? ctx->tmp_n : ctx->tmp_m;
+  const double* din_scale = transpose ? ctx->d1 : ctx->d2;
+  const double* dout_scale = transpose ? ctx->d2 : ctx->d1;
+  if (n_in) MIPCU_CK(cudaMemcpyAsync(d_in, v, sizeof(double) * n_in, cudaMemcpyHostToDevice, st));
+  if (ctx->prepared && n_in) {
+    k_div<<<grid_for(n_in), kThreads, 0, st>>>(d_in, din_scale, d_in, n_in);
+    ctx->launches++;
+  }
+  if (n_out) {
+    if (n_in && ctx->nnz) spmv_plain(ctx, transpose ? ctx->cols : ctx->rows, d_in, d_out);
+    else MIPCU_CK(cudaMemsetAsync(d_out, 0, sizeof(double) * n_out, st));
+    if (ctx->prepared) {
+      k_div<<<grid_for(n_out), kThreads, 0, st>>>(d_out, dout_scale, d_out, n_out);
+      ctx->launches++;
+    }
+    MIPCU_CK(cudaMemcpyAsync(out, d_out, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
+  }
+  MIPCU_CK(cudaStreamSynchronize(st));
+}
+
+}  // namespace mipcu
