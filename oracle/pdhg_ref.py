@@ -65,26 +65,38 @@ def _row_col_scale(K: sp.csr_matrix, r: np.ndarray, c: np.ndarray) -> sp.csr_mat
     return K
 
 
+def _segment_reduce(ufunc, values: np.ndarray, ptr: np.ndarray) -> np.ndarray:
+    """ufunc.reduceat over CSR segments, returning 0 for empty segments."""
+    nseg = ptr.size - 1
+    out = np.zeros(nseg)
+    nonempty = ptr[1:] > ptr[:-1]
+    if values.size and nonempty.any():
+        starts = ptr[:-1][nonempty]
+        out[nonempty] = ufunc.reduceat(values, starts)
+    return out
+
+
 def ruiz_pc_scale(A: sp.csr_matrix, ruiz_passes: int = RUIZ_PASSES, pock_chambolle: bool = True):
     """Ruiz (inf-norm, ``ruiz_passes`` sweeps) then Pock-Chambolle alpha=1 equilibration.
-    Returns (K, d1, d2) with K = diag(d1) A diag(d2)."""
+    Returns (K, d1, d2) with K = diag(d1) A diag(d2).  Row norms are reduced over the CSR
+    storage order, column norms over the CSC storage order (rows increasing inside a column),
+    like the two device copies."""
     K = A.tocsr().copy().astype(np.float64)
     K.sort_indices()
     m, n = K.shape
     d1 = np.ones(m)
     d2 = np.ones(n)
     rows = np.repeat(np.arange(m), np.diff(K.indptr))
+    perm = np.argsort(K.indices, kind="stable")            # CSR position -> CSC order
+    colptr = np.concatenate([[0], np.cumsum(np.bincount(K.indices, minlength=n))])
     for sweep in range(ruiz_passes + (1 if pock_chambolle else 0)):
         a = np.abs(K.data)
-        if sweep < ruiz_passes:
-            rn = np.zeros(m); np.maximum.at(rn, rows, a)
-            cn = np.zeros(n); np.maximum.at(cn, K.indices, a)
-        else:
-            rn = np.bincount(rows, weights=a, minlength=m)
-            cn = np.bincount(K.indices, weights=a, minlength=n)
+        uf = np.maximum if sweep < ruiz_passes else np.add
+        rn = _segment_reduce(uf, a, K.indptr)
+        cn = _segment_reduce(uf, a[perm], colptr)
         r = np.where(rn > 0, 1.0 / np.sqrt(np.where(rn > 0, rn, 1.0)), 1.0)
         c = np.where(cn > 0, 1.0 / np.sqrt(np.where(cn > 0, cn, 1.0)), 1.0)
-        K = _row_col_scale(K, r, c)
+        K.data = (K.data * r[rows]) * c[K.indices]
         d1 *= r
         d2 *= c
     return K, d1, d2

@@ -1,0 +1,111 @@
+"""CPU tests of the oracle itself: generators reproduce the golden recipes, the NumPy PDHG
+restatement converges to the exact-solver optimum, and the independent certificate verifier
+agrees with it.  (-m "not gpu")"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import gen, highs_ref, kkt_verify, pdhg_ref
+
+
+def rel(a, b):
+    return abs(a - b) / (1.0 + abs(b))
+
+
+def test_generator_c1_shape_and_golden(golden):
+    L = gen.config(1)
+    assert (L.m, L.n, L.nnz) == (1000, 2000, 16000)
+    assert np.all(np.diff(L.A.indptr) >= 1)
+    r = highs_ref.solve_lp(L, "highs-ipm")
+    assert r["status"] == 0
+    assert rel(r["obj"], golden["C1_lp"]["objective"]) < 1e-8
+    assert rel(r["obj"], -698.9207296656) < 1e-9
+
+
+def test_generators_mip_golden(golden):
+    S = gen.set_cover(200, 500, 8, 20264)
+    assert highs_ref.solve_mip(S)["obj"] == pytest.approx(382.0)
+    assert highs_ref.solve_lp(S)["obj"] == pytest.approx(380.625)
+    K = gen.mkp(5, 60, 4, 4, 20265)
+    assert highs_ref.solve_mip(K)["obj"] == pytest.approx(875.0)
+    assert K.maximize and K.A.shape == (5 + 4, 60 + 4)
+
+
+def test_oracle_pdhg_matches_exact_solver_c1(golden):
+    L = gen.config(1)
+    r = pdhg_ref.solve(L)
+    assert r["status"] == "optimal"
+    assert max(r["rel_pres"], r["rel_dres"], r["rel_gap"]) <= 1e-6
+    assert rel(r["obj"], golden["C1_lp"]["objective"]) < 1e-6
+    cert = kkt_verify.certificate(L, r["x"], r["y"])
+    assert cert["rel_primal_res"] <= 1.01e-6 and cert["rel_gap"] <= 1.01e-6
+    assert cert["rel_primal_res"] == pytest.approx(r["rel_pres"], rel=1e-6)
+    assert cert["rel_gap"] == pytest.approx(r["rel_gap"], rel=1e-5, abs=1e-12)
+    assert cert["max_bound_violation"] == 0.0
+
+
+@pytest.mark.parametrize("seed", [7, 8, 9])
+def test_oracle_pdhg_small_lps(golden, seed):
+    L = gen.lp(300, 500, 6, seed)
+    r = pdhg_ref.solve(L)
+    assert r["status"] == "optimal"
+    assert rel(r["obj"], golden[f"lp_300x500_s{seed}"]["objective"]) < 1e-6
+
+
+def test_oracle_pdhg_relaxations_of_mip_tier(golden):
+    S = gen.set_cover(400, 1000, 8, 20264)
+    r = pdhg_ref.solve(S)
+    assert r["status"] == "optimal"
+    assert rel(r["obj"], golden["setcover_400x1000_lp"]["objective"]) < 1e-6
+    K = gen.mkp(10, 100, 4, 5, 20265)                     # a maximisation model
+    r = pdhg_ref.solve(K)
+    assert r["status"] == "optimal"
+    assert rel(r["obj"], golden["mkp_10x100_lp"]["objective"]) < 1e-6
+    cert = kkt_verify.certificate(K, r["x"], r["y"])
+    assert max(cert["rel_primal_res"], cert["rel_dual_res"], cert["rel_gap"]) <= 1.01e-6
+
+
+def test_oracle_general_form_free_vars_and_ranges():
+    """Ranged rows, >= rows, free and half-bounded columns: the dual-residual branch."""
+    rng = np.random.default_rng(3)
+    m, n = 40, 30
+    A = sp.random(m, n, density=0.3, random_state=5, format="csr", data_rvs=lambda k: rng.uniform(-1, 1, k))
+    x0 = rng.uniform(-1, 1, n)
+    ax = A @ x0
+    lo = ax - rng.uniform(0, 1, m)
+    hi = ax + rng.uniform(0, 1, m)
+    lo[:10] = -np.inf
+    hi[10:20] = np.inf
+    lb = np.full(n, -np.inf); ub = np.full(n, np.inf)
+    lb[:10] = -2.0
+    ub[5:15] = 2.0
+    y0 = rng.uniform(-1, 1, m) * (np.isfinite(lo) | np.isfinite(hi))
+    y0 = np.where(~np.isfinite(lo), -np.abs(y0), y0)
+    y0 = np.where(~np.isfinite(hi), np.abs(y0), y0)
+    c = A.T @ y0                                         # dual feasible => bounded
+    L = gen.LP(A, c, lb, ub, lo, hi)
+    ref = highs_ref.solve_lp(L)
+    assert ref["status"] == 0
+    r = pdhg_ref.solve(L, max_iter=400000)
+    assert r["status"] == "optimal"
+    assert rel(r["obj"], ref["obj"]) < 1e-5
+    cert = kkt_verify.certificate(L, r["x"], r["y"])
+    assert max(cert["rel_primal_res"], cert["rel_dual_res"], cert["rel_gap"]) <= 1.01e-6
+
+
+def test_scaling_equilibrates():
+    L = gen.config(1)
+    K, d1, d2 = pdhg_ref.ruiz_pc_scale(L.A)
+    D = sp.diags(d1) @ L.A @ sp.diags(d2)
+    assert abs(D - K).max() < 1e-14
+    s, it = pdhg_ref.spectral_norm(K, K.T.tocsr())
+    assert 0.9 < s <= 1.0 + 1e-9                          # Pock-Chambolle alpha=1 bounds ||K||_2 by 1
+
+
+def test_golden_trace_reproduces():
+    from pathlib import Path
+    z = np.load(Path(__file__).parent / "golden" / "pdhg_trace_c1.npz")
+    L = gen.config(1)
+    r = pdhg_ref.solve(L, period=64, max_iter=64, trace_at=(10, 64))
+    assert np.allclose(r["trace"][10][0], z["xbar10"], rtol=0, atol=1e-13)
+    assert np.allclose(r["trace"][64][1], z["y64"], rtol=0, atol=1e-12)

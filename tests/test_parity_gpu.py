@@ -1,0 +1,326 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI of include/mipcu.h,
+against (i) the CPU oracle on the same seeded inputs, (ii) the committed golden fixtures
+(HiGHS optima - stand-in for the reference's SCIP / lp_solve backends; and the oracle's iterate
+trace), and (iii) at BASELINE.json's full sizes, the independent FP64 certificate verifier.
+
+Tolerances (BASELINE.json north_star): relative primal / dual feasibility <= 1e-6, relative
+objective gap <= 1e-6.  Kernel-level comparisons (SpMV, scaling, a few iterations) are FP64 with
+different summation order, so they are held to 1e-12 .. 1e-9, stated at each assert.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import gen, kkt_verify, pdhg_ref
+
+pytestmark = pytest.mark.gpu
+EPS = 1e-6
+
+
+def rel(a, b):
+    return abs(a - b) / (1.0 + abs(b))
+
+
+@pytest.fixture(scope="module")
+def engine(built):
+    from miplib_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def fresh(built):
+    from miplib_b200 import Engine
+    return Engine(0)
+
+
+def assert_optimal(stats):
+    assert stats.status == "optimal", stats
+    assert max(stats.rel_primal_res, stats.rel_dual_res, stats.rel_gap) <= EPS
+
+
+def assert_certificate(L, e, tol=1.05e-6):
+    cert = kkt_verify.certificate(L, e.x(), e.y())
+    assert cert["rel_primal_res"] <= tol, cert
+    assert cert["rel_dual_res"] <= tol, cert
+    assert cert["rel_gap"] <= tol, cert
+    assert cert["max_bound_violation"] <= 1e-12, cert
+    return cert
+
+
+# ---- kernel-level parity ---------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(1000, 2000, 8), (257, 513, 3), (64, 4000, 40), (3000, 50, 2)])
+def test_spmv_matches_scipy(engine, shape):
+    m, n, k = shape
+    L = gen.lp_fast(m, n, k, 11)
+    engine.load_lp(L)
+    rng = np.random.default_rng(1)
+    v, w = rng.standard_normal(n), rng.standard_normal(m)
+    for tpr in (0, 2, 4, 8, 16, 32):
+        engine.set_param("threads_per_row", tpr)
+        ax, aty = engine.spmv(v), engine.spmv(w, transpose=True)
+        # FP64, summation order differs from SciPy's: 1e-13 relative to the largest entry
+        assert np.abs(ax - L.A @ v).max() <= 1e-13 * max(1.0, np.abs(L.A @ v).max())
+        assert np.abs(aty - L.A.T @ w).max() <= 1e-13 * max(1.0, np.abs(L.A.T @ w).max())
+    engine.set_param("threads_per_row", 0)
+
+
+def test_spmv_long_rows_and_empty_rows(engine):
+    # config-5 shape: few very long rows, many short columns; plus empty rows / columns
+    rng = np.random.default_rng(2)
+    A = sp.random(37, 9000, density=0.2, random_state=3, format="lil")
+    A[5, :] = 0
+    A[:, 100:140] = 0
+    A = A.tocsr(); A.eliminate_zeros(); A.sort_indices()
+    L = gen.LP(A, np.zeros(9000), np.zeros(9000), np.ones(9000), np.full(37, -np.inf), np.ones(37))
+    engine.load_lp(L)
+    v, w = rng.standard_normal(9000), rng.standard_normal(37)
+    assert np.abs(engine.spmv(v) - A @ v).max() <= 1e-12
+    assert np.abs(engine.spmv(w, transpose=True) - A.T @ w).max() <= 1e-12
+
+
+def test_scaling_matches_oracle(engine):
+    L = gen.config(1)
+    engine.load_lp(L)
+    engine.prepare()
+    d1, d2 = engine.scaling()
+    K, o1, o2 = pdhg_ref.ruiz_pc_scale(L.A)
+    assert np.abs(d1 / o1 - 1).max() <= 1e-13
+    assert np.abs(d2 / o2 - 1).max() <= 1e-13
+    # the hook un-scales around the same kernel: still A v
+    v = np.random.default_rng(0).standard_normal(L.n)
+    assert np.abs(engine.spmv(v) - L.A @ v).max() <= 1e-12
+
+
+def test_iterates_match_golden_trace(engine):
+    """10 and 64 raw PDHG iterations from zero against the committed oracle trace."""
+    from pathlib import Path
+    z = np.load(Path(__file__).parent / "golden" / "pdhg_trace_c1.npz")
+    L = gen.config(1)
+    engine.load_lp(L)
+    xbar, y = engine.debug_iterate(10)
+    assert np.abs(xbar - z["xbar10"]).max() <= 1e-11
+    assert np.abs(y - z["y10"]).max() <= 1e-11
+    xbar, y = engine.debug_iterate(64)
+    assert np.abs(xbar - z["xbar64"]).max() <= 1e-10
+    assert np.abs(y - z["y64"]).max() <= 1e-10
+    st = engine.solve()
+    assert st.step_size == pytest.approx(float(z["eta"]), rel=1e-9)
+
+
+# ---- whole-solve parity ----------------------------------------------------------------------
+def test_c1_matches_oracle_and_exact_solver(engine, golden):
+    L = gen.config(1)
+    engine.load_lp(L)
+    st = engine.solve()
+    assert_optimal(st)
+    assert rel(st.primal_obj, golden["C1_lp"]["objective"]) <= EPS
+    ref = pdhg_ref.solve(L)
+    # same algorithm, same schedule: iteration counts agree to within a couple of check blocks
+    assert abs(st.iterations - ref["iters"]) <= 4 * 64
+    assert rel(st.primal_obj, ref["obj"]) <= EPS
+    assert_certificate(L, engine)
+
+
+@pytest.mark.parametrize("seed", [7, 8, 9])
+def test_small_lps_match_exact_solver(engine, golden, seed):
+    L = gen.lp(300, 500, 6, seed)
+    engine.load_lp(L)
+    st = engine.solve()
+    assert_optimal(st)
+    assert rel(st.primal_obj, golden[f"lp_300x500_s{seed}"]["objective"]) <= EPS
+    assert_certificate(L, engine)
+
+
+def test_mid_lp_matches_ipm_objective(engine, golden):
+    if "mid_lp" not in golden:
+        pytest.skip("10k x 20k golden not generated")
+    L = gen.lp(10000, 20000, 8, 1)
+    engine.load_lp(L)
+    st = engine.solve()
+    assert_optimal(st)
+    assert rel(st.primal_obj, golden["mid_lp"]["objective"]) <= EPS
+    assert rel(st.primal_obj, -7032.7239588228) <= EPS
+    assert_certificate(L, engine)
+
+
+def test_mip_tier_relaxations(engine, golden):
+    for key, L in [("setcover_200x500_lp", gen.set_cover(200, 500, 8, 20264)),
+                   ("setcover_400x1000_lp", gen.set_cover(400, 1000, 8, 20264)),
+                   ("mkp_5x60_lp", gen.mkp(5, 60, 4, 4, 20265)),
+                   ("mkp_10x100_lp", gen.mkp(10, 100, 4, 5, 20265))]:
+        engine.load_lp(L)
+        st = engine.solve()
+        assert_optimal(st)
+        assert rel(st.primal_obj, golden[key]["objective"]) <= EPS, key
+        assert_certificate(L, engine)
+
+
+def test_c2_full_size_certificate(engine):
+    """BASELINE config 2 (100k x 200k): no exact CPU solver finishes, so parity is the
+    independently verified optimality certificate."""
+    L = gen.config(2)
+    engine.load_lp(L)
+    st = engine.solve()
+    assert_optimal(st)
+    cert = assert_certificate(L, engine)
+    assert rel(st.primal_obj, cert["primal_obj"]) <= 1e-9
+    assert cert["dual_obj"] <= cert["primal_obj"] + 1e-6 * (1 + abs(cert["primal_obj"])) * 3
+
+
+def test_c3_full_size_certificate(engine):
+    """BASELINE config 3 (1M x 2M, 32M nonzeros) on one GPU."""
+    L = gen.config(3)
+    engine.load_lp(L)
+    st = engine.solve()
+    assert_optimal(st)
+    assert_certificate(L, engine)
+    # size-independent properties: linearity of the SpMV hook at full size
+    rng = np.random.default_rng(5)
+    a, b = rng.standard_normal(L.n), rng.standard_normal(L.n)
+    lhs = engine.spmv(2.0 * a - 3.0 * b)
+    rhs = 2.0 * engine.spmv(a) - 3.0 * engine.spmv(b)
+    assert np.abs(lhs - rhs).max() <= 1e-11 * np.abs(rhs).max()
+    # <A x, y> == <x, A'y>
+    w = rng.standard_normal(L.m)
+    assert abs(engine.spmv(a) @ w - a @ engine.spmv(w, transpose=True)) <= 1e-9 * L.nnz ** 0.5
+
+
+# ---- properties ------------------------------------------------------------------------------
+def test_objective_scaling_and_maximize_symmetry(engine):
+    L = gen.lp(300, 500, 6, 7)
+    engine.load_lp(L)
+    base = engine.solve().primal_obj
+    L2 = gen.LP(L.A, -3.0 * L.c, L.lb, L.ub, L.row_lo, L.row_hi, maximize=True)
+    engine.load_lp(L2)
+    st = engine.solve()
+    assert_optimal(st)
+    assert rel(st.primal_obj, -3.0 * base) <= 3e-6
+    assert_certificate(L2, engine)
+
+
+def test_row_permutation_invariance(engine):
+    L = gen.lp(300, 500, 6, 8)
+    p = np.random.default_rng(0).permutation(L.m)
+    Lp = gen.LP(L.A[p].tocsr(), L.c, L.lb, L.ub, L.row_lo[p], L.row_hi[p])
+    engine.load_lp(L); a = engine.solve().primal_obj
+    engine.load_lp(Lp); b = engine.solve().primal_obj
+    assert rel(a, b) <= 2e-6
+
+
+def test_resolve_is_deterministic(engine):
+    L = gen.lp(300, 500, 6, 9)
+    engine.load_lp(L)
+    s1 = engine.solve(); x1 = engine.x()
+    s2 = engine.solve(); x2 = engine.x()
+    assert s1.iterations == s2.iterations
+    assert np.array_equal(x1, x2)                       # bit-exact: no atomics on the data path
+    engine.set_param("use_graph", 0)
+    s3 = engine.solve(); x3 = engine.x()
+    engine.set_param("use_graph", -1)
+    assert s3.iterations == s1.iterations and np.array_equal(x1, x3)
+
+
+def test_warm_start_from_solution_converges_immediately(engine):
+    L = gen.lp(300, 500, 6, 7)
+    engine.load_lp(L)
+    s1 = engine.solve()
+    engine.warm_start(engine.x(), engine.y())
+    s2 = engine.solve()
+    assert_optimal(s2)
+    assert s2.iterations <= 64 * 3 and s2.iterations < s1.iterations
+    engine.warm_start(None, None)
+
+
+def test_set_bounds_matches_reload(engine, golden):
+    L = gen.set_cover(200, 500, 8, 20264)
+    engine.load_lp(L)
+    engine.solve()
+    cols = np.array([3, 17, 250])
+    engine.set_bounds(cols, [1.0, 0.0, 1.0], [1.0, 0.0, 1.0])        # a B&B node
+    a = engine.solve()
+    assert_optimal(a)
+    lb, ub = L.lb.copy(), L.ub.copy()
+    lb[cols] = [1, 0, 1]; ub[cols] = [1, 0, 1]
+    L2 = gen.LP(L.A, L.c, lb, ub, L.row_lo, L.row_hi)
+    with fresh(None) as e2:
+        e2.load_lp(L2)
+        b = e2.solve()
+    assert rel(a.primal_obj, b.primal_obj) <= 2e-6
+    from oracle import highs_ref
+    assert rel(a.primal_obj, highs_ref.solve_lp(L2)["obj"]) <= EPS
+
+
+# ---- edge cases ------------------------------------------------------------------------------
+def test_general_form_free_columns_ranged_rows_sentinel_infinities(engine):
+    rng = np.random.default_rng(3)
+    m, n = 40, 30
+    A = sp.random(m, n, density=0.3, random_state=5, format="csr", data_rvs=lambda k: rng.uniform(-1, 1, k))
+    x0 = rng.uniform(-1, 1, n)
+    ax = A @ x0
+    lo = ax - rng.uniform(0, 1, m); hi = ax + rng.uniform(0, 1, m)
+    lo[:10] = -np.inf; hi[10:20] = np.inf
+    lb = np.full(n, -np.inf); ub = np.full(n, np.inf)
+    lb[:10] = -2.0; ub[5:15] = 2.0
+    y0 = rng.uniform(-1, 1, m)
+    y0 = np.where(~np.isfinite(lo), -np.abs(y0), y0)
+    y0 = np.where(~np.isfinite(hi), np.abs(y0), y0)
+    c = A.T @ y0
+    L = gen.LP(A, c, lb, ub, lo, hi)
+    from oracle import highs_ref
+    ref = highs_ref.solve_lp(L)
+    # the adapter passes SCIP's 1e20 / lp_solve's 1e30 sentinels, not IEEE infinities
+    Ls = gen.LP(A, c, np.where(np.isfinite(lb), lb, -1e20), np.where(np.isfinite(ub), ub, 1e30),
+                np.where(np.isfinite(lo), lo, -1e20), np.where(np.isfinite(hi), hi, 1e20))
+    engine.load_lp(Ls)
+    engine.set_param("iter_limit", 400000)
+    st = engine.solve()
+    engine.set_param("iter_limit", 2e6)
+    assert_optimal(st)
+    assert rel(st.primal_obj, ref["obj"]) <= 1e-5
+    assert_certificate(L, engine)
+
+
+def test_degenerate_shapes(engine):
+    # no rows at all: the optimum sits at the bounds
+    n = 7
+    A = sp.csr_matrix((0, n))
+    c = np.array([1.0, -1.0, 2.0, 0.0, -3.0, 1.0, 1.0])
+    L = gen.LP(A, c, np.zeros(n), np.ones(n), np.zeros(0), np.zeros(0))
+    engine.load_lp(L)
+    st = engine.solve()
+    assert_optimal(st)
+    assert st.primal_obj == pytest.approx(-4.0, abs=1e-9)
+    assert np.allclose(engine.x(), [0, 1, 0, engine.x()[3], 1, 0, 0])
+    # rows present but all empty, trivially satisfied
+    A = sp.csr_matrix((3, n))
+    L = gen.LP(A, c, np.zeros(n), np.ones(n), np.full(3, -np.inf), np.ones(3))
+    engine.load_lp(L)
+    st = engine.solve()
+    assert_optimal(st)
+    assert st.primal_obj == pytest.approx(-4.0, abs=1e-9)
+    # a single entry
+    A = sp.csr_matrix(np.array([[2.0]]))
+    L = gen.LP(A, np.array([-1.0]), np.zeros(1), np.full(1, np.inf), np.full(1, -np.inf), np.array([3.0]))
+    engine.load_lp(L)
+    st = engine.solve()
+    assert_optimal(st)
+    assert st.primal_obj == pytest.approx(-1.5, abs=1e-5)
+
+
+def test_error_reporting(engine):
+    from miplib_b200 import MipcuError
+    with pytest.raises(MipcuError, match="strictly increasing"):
+        engine.load([0, 2], [1, 0], [1.0, 1.0], [0, 0], [0, 0], [1, 1], [0], [1])
+    with pytest.raises(MipcuError, match="out of range"):
+        engine.load([0, 1], [5], [1.0], [0, 0], [0, 0], [1, 1], [0], [1])
+    with pytest.raises(MipcuError, match="no model loaded"):
+        engine.solve()
+    L = gen.lp(300, 500, 6, 7)
+    engine.load_lp(L)
+    engine.set_param("iter_limit", 128)
+    st = engine.solve()
+    engine.set_param("iter_limit", 2e6)
+    assert st.status == "iteration_limit" and st.iterations == 128
+    with pytest.raises(MipcuError):
+        engine.set_param("check_period", 1)
