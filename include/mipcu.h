@@ -43,7 +43,8 @@ enum {
   MIPCU_UNBOUNDED = 3,
   MIPCU_ITERATION_LIMIT = 4,   /* -> Result::Interrupted */
   MIPCU_TIME_LIMIT = 5,        /* -> Result::Interrupted */
-  MIPCU_NUMERICAL_ERROR = 6    /* -> Result::Error */
+  MIPCU_NUMERICAL_ERROR = 6,   /* -> Result::Error */
+  MIPCU_CUTOFF = 7             /* dual bound crossed MIPCU_PARAM_OBJ_CUTOFF (B&B pruning) */
 };
 
 /* keys for mipcu_set_param / mipcu_get_param */
@@ -57,7 +58,9 @@ enum {
   MIPCU_PARAM_USE_GRAPH = 6,      /* -1 auto (graph for small problems), 0 never, 1 always */
   MIPCU_PARAM_SCALING = 7,        /* 1 (default): 10x Ruiz + Pock-Chambolle; 0: none */
   MIPCU_PARAM_THREADS_PER_ROW = 8,/* 0 auto; else 2,4,8,16,32 sub-warp width for both SpMVs */
-  MIPCU_PARAM_COUNT_ = 9
+  MIPCU_PARAM_OBJ_CUTOFF = 9,     /* stop with MIPCU_CUTOFF once the dual bound proves the optimum is no
+                                     better than this objective value (model's own sense); NaN = off */
+  MIPCU_PARAM_COUNT_ = 10
 };
 
 typedef struct mipcu_stats {

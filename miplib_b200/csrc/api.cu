@@ -1,6 +1,7 @@
 // api.cu - the extern "C" surface declared in include/mipcu.h.  Every entry point converts
 // C++ exceptions into rc = 1 + a message retrievable with mipcu_last_error(), the convention of
 // the reference's own C API (reference miplib/capi.cpp:7-28).
+#include <cmath>
 #include <cstring>
 #include <mutex>
 
@@ -49,6 +50,7 @@ void set_default_params(mipcu_ctx* ctx) {
   ctx->params[MIPCU_PARAM_USE_GRAPH] = -1;
   ctx->params[MIPCU_PARAM_SCALING] = 1;
   ctx->params[MIPCU_PARAM_THREADS_PER_ROW] = 0;
+  ctx->params[MIPCU_PARAM_OBJ_CUTOFF] = NAN;
 }
 
 mipcu_ctx* create_on(int device) {
@@ -157,23 +159,7 @@ int mipcu_load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64
 int mipcu_set_bounds(mipcu_ctx* ctx, int64_t n_changed, const int64_t* cols, const double* lb,
                      const double* ub) {
   if (!ctx) return 1;
-  return guarded(ctx, [&] {
-    MIPCU_REQUIRE(ctx->loaded, "mipcu_set_bounds: no model loaded");
-    MIPCU_REQUIRE(n_changed >= 0 && (n_changed == 0 || (cols && lb && ub)), "mipcu_set_bounds: null array");
-    MIPCU_CK(cudaSetDevice(ctx->device));
-    for (int64_t k = 0; k < n_changed; ++k) {
-      MIPCU_REQUIRE(cols[k] >= 0 && cols[k] < ctx->n, "mipcu_set_bounds: column out of range");
-      double l = lb[k], u = ub[k];
-      if (l <= -INF_THRESHOLD) l = -INFINITY;
-      if (l >= INF_THRESHOLD) l = INFINITY;
-      if (u >= INF_THRESHOLD) u = INFINITY;
-      if (u <= -INF_THRESHOLD) u = -INFINITY;
-      MIPCU_CK(cudaMemcpyAsync(ctx->lb + cols[k], &l, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-      MIPCU_CK(cudaMemcpyAsync(ctx->ub + cols[k], &u, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-      MIPCU_CK(cudaStreamSynchronize(ctx->stream));   // l, u are stack temporaries
-    }
-    ctx->vectors_dirty = true;
-  });
+  return guarded(ctx, [&] { set_bounds(ctx, n_changed, cols, lb, ub); });
 }
 
 int mipcu_set_objective(mipcu_ctx* ctx, const double* c, int maximize) {

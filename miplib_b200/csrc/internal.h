@@ -65,6 +65,7 @@ enum Quantity {
 struct Scalars {
   double tau, sigma, eta, w;
   double eps;
+  double cutoff;        // minimisation-sense objective cutoff for the dual bound (+inf: off)
   double bnorm, cnorm;
   double fp0, fp_prev, fp;
   double rel_p, rel_d, rel_g, pobj, dobj;
@@ -138,6 +139,8 @@ void refresh_vectors(mipcu_ctx* ctx);   // scaled c / bounds / norms / w0 (after
 void spmv_plain(mipcu_ctx* ctx, const Csr& A, const double* v, double* out);
 double device_norm2(mipcu_ctx* ctx, const double* v, int64_t len);
 int choose_tpr(double avg_row_len, int override_tpr);
+void set_bounds(mipcu_ctx* ctx, int64_t n_changed, const int64_t* cols, const double* lb,
+                const double* ub);
 void spmv_host(mipcu_ctx* ctx, int transpose, const double* v, double* out);
 
 // ---- solve.cu -------------------------------------------------------------------------------

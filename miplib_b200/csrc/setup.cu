@@ -135,6 +135,19 @@ __global__ void k_scale_matrix(const int* __restrict__ ptr, const int* __restric
   }
 }
 
+__global__ void k_scatter_bounds(const long long* __restrict__ cols, const double* __restrict__ lb,
+                                 const double* __restrict__ ub, double* __restrict__ dlb,
+                                 double* __restrict__ dub, int count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    double l = lb[i], u = ub[i];
+    if (l <= -INF_THRESHOLD) l = -INFINITY; else if (l >= INF_THRESHOLD) l = INFINITY;
+    if (u >= INF_THRESHOLD) u = INFINITY; else if (u <= -INF_THRESHOLD) u = -INFINITY;
+    dlb[cols[i]] = l;
+    dub[cols[i]] = u;
+  }
+}
+
 __global__ void k_fill(double* v, double a, int count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) v[i] = a;
@@ -490,6 +503,30 @@ void refresh_vectors(mipcu_ctx* ctx) {
   double bs = std::sqrt(sumsq<1>(ctx, ctx->los, ctx->his, m));
   ctx->w0 = (cs > 0.0 && bs > 0.0) ? cs / bs : 1.0;
   ctx->vectors_dirty = false;
+}
+
+// IVar::set_lb / set_ub and branch-and-bound: overwrite the bounds of a few columns
+void set_bounds(mipcu_ctx* ctx, int64_t n_changed, const int64_t* cols, const double* lb,
+                const double* ub) {
+  MIPCU_REQUIRE(ctx->loaded, "mipcu_set_bounds: no model loaded");
+  MIPCU_REQUIRE(n_changed >= 0 && (n_changed == 0 || (cols && lb && ub)), "mipcu_set_bounds: null array");
+  if (n_changed == 0) return;
+  for (int64_t k = 0; k < n_changed; ++k)
+    MIPCU_REQUIRE(cols[k] >= 0 && cols[k] < ctx->n, "mipcu_set_bounds: column out of range");
+  MIPCU_CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  long long* dcols = dalloc<long long>(n_changed);
+  double* dl = dalloc<double>(2 * n_changed);
+  double* du = dl + n_changed;
+  MIPCU_CK(cudaMemcpyAsync(dcols, cols, sizeof(int64_t) * n_changed, cudaMemcpyHostToDevice, st));
+  MIPCU_CK(cudaMemcpyAsync(dl, lb, sizeof(double) * n_changed, cudaMemcpyHostToDevice, st));
+  MIPCU_CK(cudaMemcpyAsync(du, ub, sizeof(double) * n_changed, cudaMemcpyHostToDevice, st));
+  k_scatter_bounds<<<grid_for(n_changed), kThreads, 0, st>>>(dcols, dl, du, ctx->lb, ctx->ub, (int)n_changed);
+  ctx->launches++;
+  MIPCU_CK(cudaStreamSynchronize(st));
+  cudaFree(dcols);
+  cudaFree(dl);
+  ctx->vectors_dirty = true;
 }
 
 // test hook: out = A v (or A' v) on the matrix AS LOADED.  Once prepare() has equilibrated the

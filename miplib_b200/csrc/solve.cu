@@ -81,6 +81,10 @@ __global__ void __launch_bounds__(kThreads) k_ctrl_check(Scalars* sc, const doub
     sc->done = 1 + MIPCU_OPTIMAL;
     return;
   }
+  if (sc->rel_d <= sc->eps && dobj >= sc->cutoff) {   // a dual-feasible y bounds the optimum
+    sc->done = 1 + MIPCU_CUTOFF;
+    return;
+  }
   const bool restart = fp <= BETA_SUFFICIENT * sc->fp0 ||
                        (fp <= BETA_NECESSARY * sc->fp0 && fp > sc->fp_prev) ||
                        (double)k >= BETA_ARTIFICIAL * (double)sc->total;
@@ -277,6 +281,10 @@ void init_iterate(mipcu_ctx* ctx, Scalars& h) {
   h.tau = h.eta / h.w;
   h.sigma = h.eta * h.w;
   h.eps = ctx->params[MIPCU_PARAM_EPS_REL];
+  {
+    const double cut = ctx->params[MIPCU_PARAM_OBJ_CUTOFF];
+    h.cutoff = (cut == cut) ? sgn * cut : INFINITY;
+  }
   h.bnorm = ctx->bnorm;
   h.cnorm = ctx->cnorm;
   h.period = (int)ctx->params[MIPCU_PARAM_CHECK_PERIOD];

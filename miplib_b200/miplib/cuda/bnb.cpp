@@ -1,0 +1,443 @@
+// miplib/cuda/bnb.cpp - see bnb.hpp.
+#include "bnb.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <deque>
+#include <iostream>
+#include <limits>
+#include <queue>
+#include <stdexcept>
+
+#include <mipcu.h>
+
+namespace miplib {
+
+namespace {
+
+constexpr double kInf = std::numeric_limits<double>::infinity();
+
+void check(mipcu_ctx* ctx, int rc)
+{
+  if (rc) throw std::logic_error(std::string("Cuda backend: ") + mipcu_last_error(ctx));
+}
+
+bool integral(double v) { return std::isfinite(v) && std::floor(v) == v; }
+
+}  // namespace
+
+CudaBranchAndBound::CudaBranchAndBound(CudaSolver& solver) : S(solver)
+{
+  n = S.m_columns.size();
+  sgn = S.m_sense == Solver::Sense::Maximize ? -1.0 : 1.0;
+  double const inf = S.infinity();
+  // alive rows, CSR
+  rptr.push_back(0);
+  for (std::size_t r = 0; r < S.m_row_alive.size(); ++r)
+  {
+    if (!S.m_row_alive[r]) continue;
+    for (std::int64_t k = S.m_row_start[r]; k < S.m_row_start[r + 1]; ++k)
+    {
+      ridx.push_back(S.m_row_idx[k]);
+      rval.push_back(S.m_row_val[k]);
+    }
+    rptr.push_back(static_cast<std::int64_t>(ridx.size()));
+    rlo.push_back(S.m_row_lo[r] <= -inf ? -kInf : S.m_row_lo[r]);
+    rhi.push_back(S.m_row_hi[r] >= inf ? kInf : S.m_row_hi[r]);
+  }
+  m = rlo.size();
+  // CSC (which rows to revisit when a column's box shrinks)
+  cptr.assign(n + 1, 0);
+  for (std::int32_t j : ridx) cptr[j + 1]++;
+  for (std::size_t j = 0; j < n; ++j) cptr[j + 1] += cptr[j];
+  cidx.resize(ridx.size());
+  cval.resize(ridx.size());
+  std::vector<std::int64_t> fill(cptr.begin(), cptr.end() - 1);
+  for (std::size_t r = 0; r < m; ++r)
+    for (std::int64_t k = rptr[r]; k < rptr[r + 1]; ++k)
+    {
+      cidx[fill[ridx[k]]] = static_cast<std::int32_t>(r);
+      cval[fill[ridx[k]]++] = rval[k];
+    }
+  cost.resize(n);
+  is_int.resize(n);
+  for (std::size_t j = 0; j < n; ++j)
+  {
+    cost[j] = sgn * (j < S.m_objective.size() ? S.m_objective[j] : 0.0);
+    is_int[j] = S.m_columns[j].type != Var::Type::Continuous;
+    if (!is_int[j]) pure_integer = false;
+    if (cost[j] != 0 && (!is_int[j] || !integral(cost[j]))) objective_integral = false;
+  }
+}
+
+double CudaBranchAndBound::objective(std::vector<double> const& x) const
+{
+  double v = 0;
+  for (std::size_t j = 0; j < n; ++j) v += cost[j] * x[j];
+  return v;
+}
+
+double CudaBranchAndBound::cutoff() const
+{
+  if (!have_incumbent) return kInf;
+  // an improving solution of an all-integer objective is better by at least 1
+  return objective_integral ? best - 1.0 + 1e-6 : best - 1e-9 * (1.0 + std::abs(best));
+}
+
+// Activity-based bound tightening to a fixpoint (bounded work).  Returns false when some row can
+// no longer be satisfied inside the box.
+bool CudaBranchAndBound::propagate(std::vector<double>& lb, std::vector<double>& ub) const
+{
+  std::deque<std::int32_t> work;
+  std::vector<char> queued(m, 1);
+  for (std::size_t r = 0; r < m; ++r) work.push_back(static_cast<std::int32_t>(r));
+  std::int64_t budget = 30 * static_cast<std::int64_t>(m) + 2000;
+  auto touch = [&](std::int32_t col) {
+    for (std::int64_t k = cptr[col]; k < cptr[col + 1]; ++k)
+      if (!queued[cidx[k]]) { queued[cidx[k]] = 1; work.push_back(cidx[k]); }
+  };
+  while (!work.empty() && budget-- > 0)
+  {
+    std::int32_t const r = work.front();
+    work.pop_front();
+    queued[r] = 0;
+    double amin = 0, amax = 0;
+    int min_inf = 0, max_inf = 0;
+    for (std::int64_t k = rptr[r]; k < rptr[r + 1]; ++k)
+    {
+      double const a = rval[k], l = lb[ridx[k]], u = ub[ridx[k]];
+      double const lo_side = a > 0 ? l : u, hi_side = a > 0 ? u : l;
+      if (std::isinf(lo_side)) ++min_inf; else amin += a * lo_side;
+      if (std::isinf(hi_side)) ++max_inf; else amax += a * hi_side;
+    }
+    double const tol_hi = 1e-7 * (1.0 + std::abs(std::isinf(rhi[r]) ? 0.0 : rhi[r]));
+    double const tol_lo = 1e-7 * (1.0 + std::abs(std::isinf(rlo[r]) ? 0.0 : rlo[r]));
+    if (min_inf == 0 && amin > rhi[r] + tol_hi) return false;
+    if (max_inf == 0 && amax < rlo[r] - tol_lo) return false;
+    for (std::int64_t k = rptr[r]; k < rptr[r + 1]; ++k)
+    {
+      std::int32_t const j = ridx[k];
+      double const a = rval[k], l = lb[j], u = ub[j];
+      double new_l = l, new_u = u;
+      // a x_j <= hi - (min activity of the other terms)
+      if (!std::isinf(rhi[r]))
+      {
+        double const mine = a > 0 ? l : u;
+        int const others_inf = min_inf - (std::isinf(mine) ? 1 : 0);
+        if (others_inf == 0)
+        {
+          double const rest = amin - (std::isinf(mine) ? 0.0 : a * mine);
+          double const bnd = (rhi[r] - rest) / a;
+          if (a > 0) new_u = std::min(new_u, bnd); else new_l = std::max(new_l, bnd);
+        }
+      }
+      // a x_j >= lo - (max activity of the other terms)
+      if (!std::isinf(rlo[r]))
+      {
+        double const mine = a > 0 ? u : l;
+        int const others_inf = max_inf - (std::isinf(mine) ? 1 : 0);
+        if (others_inf == 0)
+        {
+          double const rest = amax - (std::isinf(mine) ? 0.0 : a * mine);
+          double const bnd = (rlo[r] - rest) / a;
+          if (a > 0) new_l = std::max(new_l, bnd); else new_u = std::min(new_u, bnd);
+        }
+      }
+      if (is_int[j])
+      {
+        new_u = std::floor(new_u + 1e-6);
+        new_l = std::ceil(new_l - 1e-6);
+      }
+      double const span = std::max(1.0, std::max(std::abs(l), std::abs(u)));
+      bool changed = false;
+      // continuous boxes only move on a real improvement, so the loop cannot creep forever
+      double const min_step = is_int[j] ? 0.5 : 1e-4 * (std::isinf(u - l) ? span : std::max(u - l, 1e-9));
+      if (new_u < u - min_step || (std::isinf(u) && !std::isinf(new_u))) { ub[j] = new_u; changed = true; }
+      if (new_l > l + min_step || (std::isinf(l) && !std::isinf(new_l))) { lb[j] = new_l; changed = true; }
+      if (lb[j] > ub[j])
+      {
+        if (lb[j] - ub[j] > 1e-7 * span) return false;
+        lb[j] = ub[j] = 0.5 * (lb[j] + ub[j]);   // met within rounding: the column is fixed
+        if (is_int[j]) lb[j] = ub[j] = std::round(lb[j]);
+      }
+      if (changed) touch(j);
+    }
+  }
+  return true;
+}
+
+bool CudaBranchAndBound::row_feasible(std::vector<double> const& x, double tol_scale) const
+{
+  for (std::size_t r = 0; r < m; ++r)
+  {
+    double act = 0;
+    for (std::int64_t k = rptr[r]; k < rptr[r + 1]; ++k) act += rval[k] * x[ridx[k]];
+    if (act > rhi[r] + tol_scale * (1.0 + std::abs(std::isinf(rhi[r]) ? 0.0 : rhi[r]))) return false;
+    if (act < rlo[r] - tol_scale * (1.0 + std::abs(std::isinf(rlo[r]) ? 0.0 : rlo[r]))) return false;
+  }
+  return true;
+}
+
+bool CudaBranchAndBound::try_incumbent(std::vector<double> const& x)
+{
+  double const tol = pure_integer ? 1e-9 : std::max(10 * S.m_feas_tol, 1e-6);
+  if (!row_feasible(x, tol)) return false;
+  double const v = objective(x);
+  if (!have_incumbent || v < best - 1e-12 * (1 + std::abs(best)))
+  {
+    have_incumbent = true;
+    best = v;
+    best_x = x;
+  }
+  return true;
+}
+
+// nearest / up / down rounding of the integer columns of an LP point, clipped to the node box
+void CudaBranchAndBound::try_roundings(std::vector<double> const& x, std::vector<double> const& lb,
+                                       std::vector<double> const& ub)
+{
+  std::vector<double> cand(n);
+  for (int mode = 0; mode < 3; ++mode)
+  {
+    for (std::size_t j = 0; j < n; ++j)
+    {
+      double v = x[j];
+      if (is_int[j])
+      {
+        v = mode == 0 ? std::round(v) : mode == 1 ? std::ceil(v - 1e-6) : std::floor(v + 1e-6);
+        v = std::min(std::max(v, std::ceil(lb[j] - 1e-9)), std::floor(ub[j] + 1e-9));
+      }
+      cand[j] = v;
+    }
+    try_incumbent(cand);
+  }
+}
+
+void CudaBranchAndBound::push_device_bounds(std::vector<double> const& lb, std::vector<double> const& ub)
+{
+  double const inf = S.infinity();
+  std::vector<std::int64_t> cols;
+  std::vector<double> nl, nu;
+  for (std::size_t j = 0; j < n; ++j)
+    if (lb[j] != dev_lb[j] || ub[j] != dev_ub[j])
+    {
+      cols.push_back(static_cast<std::int64_t>(j));
+      nl.push_back(std::isinf(lb[j]) ? -inf : lb[j]);
+      nu.push_back(std::isinf(ub[j]) ? inf : ub[j]);
+      dev_lb[j] = lb[j];
+      dev_ub[j] = ub[j];
+    }
+  if (!cols.empty())
+    check(S.m_ctx, mipcu_set_bounds(S.m_ctx, static_cast<std::int64_t>(cols.size()), cols.data(),
+                                    nl.data(), nu.data()));
+}
+
+std::pair<Solver::Result, bool> CudaBranchAndBound::run()
+{
+  using R = Solver::Result;
+  auto const t0 = std::chrono::steady_clock::now();
+  auto elapsed = [&]() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  };
+  double const inf = S.infinity();
+  std::vector<double> root_lb(n), root_ub(n);
+  for (std::size_t j = 0; j < n; ++j)
+  {
+    root_lb[j] = S.m_columns[j].lb <= -inf ? -kInf : S.m_columns[j].lb;
+    root_ub[j] = S.m_columns[j].ub >= inf ? kInf : S.m_columns[j].ub;
+    if (is_int[j])
+    {
+      root_lb[j] = std::ceil(root_lb[j] - 1e-9);
+      root_ub[j] = std::floor(root_ub[j] + 1e-9);
+    }
+  }
+  if (!propagate(root_lb, root_ub)) return {R::Infeasible, false};
+
+  auto finish = [&](bool complete) -> std::pair<R, bool> {
+    S.m_info.proven_optimal = complete && have_incumbent;
+    if (have_incumbent)
+    {
+      S.m_solution = best_x;
+      S.m_has_solution = true;
+      double v = 0;
+      for (std::size_t j = 0; j < n; ++j) v += (j < S.m_objective.size() ? S.m_objective[j] : 0.0) * best_x[j];
+      S.m_objective_value = v;
+    }
+    if (complete) return have_incumbent ? std::make_pair(R::Optimal, true) : std::make_pair(R::Infeasible, false);
+    return {R::Interrupted, have_incumbent};
+  };
+
+  // a user start point that happens to be feasible is a free incumbent
+  if (S.m_start_x.size() == n)
+  {
+    std::vector<double> cand(S.m_start_x);
+    bool ok = true;
+    for (std::size_t j = 0; j < n && ok; ++j)
+    {
+      if (is_int[j]) cand[j] = std::round(cand[j]);
+      ok = cand[j] >= root_lb[j] - 1e-9 && cand[j] <= root_ub[j] + 1e-9;
+    }
+    if (ok) try_incumbent(cand);
+  }
+
+  auto all_fixed = [&](std::vector<double> const& lb, std::vector<double> const& ub) {
+    for (std::size_t j = 0; j < n; ++j)
+      if (lb[j] != ub[j]) return false;
+    return true;
+  };
+  if (all_fixed(root_lb, root_ub))
+  {
+    try_incumbent(root_lb);
+    return finish(true);
+  }
+
+  // device model at the root box
+  bool const user_verbose = S.m_verbose;
+  S.upload_model();
+  dev_lb.assign(n, 0);
+  dev_ub.assign(n, 0);
+  for (std::size_t j = 0; j < n; ++j)
+  {
+    dev_lb[j] = S.m_columns[j].lb <= -inf ? -kInf : S.m_columns[j].lb;
+    dev_ub[j] = S.m_columns[j].ub >= inf ? kInf : S.m_columns[j].ub;
+  }
+  mipcu_ctx* ctx = S.m_ctx;
+  check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_EPS_REL, S.m_feas_tol));
+  check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_VERBOSE, 0));
+  check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_ITER_LIMIT, 200000));
+
+  // no feasible point of the box can cost more than this: a dual bound above it proves the
+  // node LP infeasible (PDHG's dual iterate diverges on infeasible problems)
+  auto box_objective_max = [&](std::vector<double> const& lb, std::vector<double> const& ub) {
+    double v = 0;
+    for (std::size_t j = 0; j < n; ++j)
+    {
+      if (cost[j] == 0) continue;
+      double const side = cost[j] > 0 ? ub[j] : lb[j];
+      if (std::isinf(side)) return kInf;
+      v += cost[j] * side;
+    }
+    return v;
+  };
+
+  auto by_bound = [](Node const& a, Node const& b) {
+    return a.bound != b.bound ? a.bound > b.bound : a.depth < b.depth;
+  };
+  std::priority_queue<Node, std::vector<Node>, decltype(by_bound)> open(by_bound);
+  open.push(Node{{}, -kInf, 0, {}, {}});
+  bool complete = true;
+  std::int64_t const node_limit = 2000000;
+  bool const keep_warm = n + m <= 400000;
+
+  std::vector<double> lb, ub, x, y;
+  while (!open.empty())
+  {
+    if ((S.m_time_limit > 0 && elapsed() > S.m_time_limit) || S.m_info.nodes >= node_limit)
+    {
+      complete = false;
+      break;
+    }
+    Node node = open.top();
+    open.pop();
+    if (node.bound >= cutoff()) continue;          // best-first: everything left is no better
+    S.m_info.nodes += 1;
+
+    lb = root_lb;
+    ub = root_ub;
+    for (Change const& c : node.changes) { lb[c.col] = c.lb; ub[c.col] = c.ub; }
+    if (!propagate(lb, ub)) continue;
+    if (all_fixed(lb, ub))
+    {
+      try_incumbent(lb);
+      continue;
+    }
+
+    push_device_bounds(lb, ub);
+    double const umax = box_objective_max(lb, ub);
+    double cut = std::min(cutoff(), std::isinf(umax) ? kInf : umax + 1e-6 * (1.0 + std::abs(umax)));
+    check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_OBJ_CUTOFF, std::isinf(cut) ? std::nan("") : sgn * cut));
+    if (S.m_time_limit > 0)
+      check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_TIME_LIMIT, std::max(0.01, S.m_time_limit - elapsed())));
+    bool const warm = !node.x.empty();
+    if (warm)
+    {
+      // the parent's point, moved into the child's box
+      for (std::size_t j = 0; j < n; ++j) node.x[j] = std::min(std::max(node.x[j], lb[j]), ub[j]);
+      check(ctx, mipcu_warm_start(ctx, node.x.data(), node.y.empty() ? nullptr : node.y.data()));
+    }
+    else
+      check(ctx, mipcu_warm_start(ctx, nullptr, nullptr));
+    CudaSolver::LpOutcome const lp = S.solve_lp_on_device(&x, keep_warm ? &y : nullptr);
+    if (user_verbose)
+      std::cerr << "[miplib cuda b&b] node " << S.m_info.nodes << " depth " << node.depth << " open "
+                << open.size() << " lp status " << lp.status << " iters " << lp.iterations << " dual "
+                << lp.dual_obj << " incumbent " << (have_incumbent ? sgn * best : std::nan("")) << "\n";
+
+    if (lp.status == MIPCU_CUTOFF) continue;       // bound (or infeasibility) proven by the dual
+    if (lp.status == MIPCU_NUMERICAL_ERROR) { complete = false; continue; }
+    double node_bound = node.bound;
+    if (lp.status == MIPCU_OPTIMAL)
+    {
+      double const d = sgn * lp.dual_obj;
+      node_bound = std::max(node_bound, d - 1e-6 * (1.0 + std::abs(d)));
+      if (objective_integral) node_bound = std::ceil(node_bound - 1e-9);
+      try_roundings(x, lb, ub);
+      if (node_bound >= cutoff()) continue;
+    }
+    else if (lp.status == MIPCU_TIME_LIMIT)
+    {
+      complete = false;
+      break;
+    }
+    // branching column: the most fractional integer column of the LP point
+    std::int32_t pick = -1;
+    double worst = S.m_int_tol;
+    for (std::size_t j = 0; j < n; ++j)
+      if (is_int[j] && lb[j] < ub[j])
+      {
+        double const f = std::abs(x[j] - std::round(x[j]));
+        if (f > worst) { worst = f; pick = static_cast<std::int32_t>(j); }
+      }
+    if (pick < 0)
+    {
+      if (lp.status == MIPCU_OPTIMAL)
+      {
+        // integral LP optimum: round the integer columns exactly; the continuous ones keep their LP value
+        std::vector<double> cand(x);
+        for (std::size_t j = 0; j < n; ++j)
+          if (is_int[j]) cand[j] = std::min(std::max(std::round(cand[j]), lb[j]), ub[j]);
+        if (!try_incumbent(cand)) complete = false;   // an integral LP point that rounding broke
+      }
+      else
+        complete = false;                            // undecided node with nothing to branch on
+      continue;
+    }
+    double const split = std::floor(x[pick]);
+    for (int side = 0; side < 2; ++side)
+    {
+      Node child;
+      child.changes = node.changes;
+      // carry every bound propagation found, so the child starts from the tightened box
+      child.changes.clear();
+      for (std::size_t j = 0; j < n; ++j)
+        if (lb[j] != root_lb[j] || ub[j] != root_ub[j])
+          child.changes.push_back({static_cast<std::int32_t>(j), lb[j], ub[j]});
+      double cl = lb[pick], cu = ub[pick];
+      if (side == 0) cu = split; else cl = split + 1;
+      if (cl > cu) continue;
+      bool found = false;
+      for (Change& c : child.changes)
+        if (c.col == pick) { c.lb = cl; c.ub = cu; found = true; }
+      if (!found) child.changes.push_back({pick, cl, cu});
+      child.bound = node_bound;
+      child.depth = node.depth + 1;
+      if (keep_warm) { child.x = x; child.y = y; }
+      open.push(std::move(child));
+    }
+  }
+  S.m_info.best_bound = have_incumbent ? sgn * best : 0;
+  return finish(complete);
+}
+
+}  // namespace miplib

@@ -1,0 +1,58 @@
+// miplib/cuda/bnb.hpp - branch and bound around the device LP engine, for models with Binary /
+// Integer columns.  In the reference this lives inside the vendor call (SCIPsolve,
+// miplib/scip/solver.cpp:370; lp_solve's B&B behind ::solve, miplib/lpsolve/solver.cpp:156).
+//
+// Host side: best-first tree, activity-based bound propagation (decides most small models with
+// no LP at all and catches the structurally infeasible nodes PDHG cannot certify), rounding
+// heuristics, pruning by the DUAL objective of the node LP (a valid bound, unlike the primal value
+// of an inexact first-order solve).  Device side: one PDHG solve per node, warm started from the
+// parent, stopped early by MIPCU_PARAM_OBJ_CUTOFF as soon as its dual bound crosses the incumbent.
+#pragma once
+
+#include <cstdint>
+#include <utility>
+#include <vector>
+
+#include "solver.hpp"
+
+namespace miplib {
+
+struct CudaBranchAndBound
+{
+  explicit CudaBranchAndBound(CudaSolver& solver);
+  std::pair<Solver::Result, bool> run();
+
+  private:
+  struct Change { std::int32_t col; double lb, ub; };
+  struct Node
+  {
+    std::vector<Change> changes;   // bounds that differ from the root box
+    double bound;                  // lower bound on the (minimisation-sense) objective
+    int depth;
+    std::vector<double> x, y;      // parent LP solution: warm start
+  };
+
+  bool propagate(std::vector<double>& lb, std::vector<double>& ub) const;
+  bool row_feasible(std::vector<double> const& x, double tol_scale) const;
+  double objective(std::vector<double> const& x) const;
+  bool try_incumbent(std::vector<double> const& x);   // false: x violates a row
+  void try_roundings(std::vector<double> const& x, std::vector<double> const& lb,
+                     std::vector<double> const& ub);
+  void push_device_bounds(std::vector<double> const& lb, std::vector<double> const& ub);
+  double cutoff() const;           // nodes whose bound reaches this cannot improve the incumbent
+
+  CudaSolver& S;
+  std::size_t n = 0, m = 0;
+  double sgn = 1;                  // -1 when the model maximises: the tree minimises sgn * c'x
+  std::vector<std::int64_t> rptr, cptr;
+  std::vector<std::int32_t> ridx, cidx;
+  std::vector<double> rval, cval, rlo, rhi, cost;
+  std::vector<char> is_int;
+  bool pure_integer = true, objective_integral = true;
+  std::vector<double> dev_lb, dev_ub;
+  double best = 0;
+  bool have_incumbent = false;
+  std::vector<double> best_x;
+};
+
+}  // namespace miplib

@@ -1,0 +1,465 @@
+// miplib/cuda/solver.cpp - the Backend::Cuda adapter (see solver.hpp).
+//
+// Lowering rules, each pinned to what the reference's adapters do with the same front-end object:
+//   row  `sum a_j x_j + k <= 0`  ->  row_hi = -k, row_lo = -inf        (miplib/lpsolve/solver.cpp:115-130:
+//   row  `sum a_j x_j + k == 0`  ->  row_lo = row_hi = -k               type 1 / 3, rhs = -constant;
+//                                                                       miplib/scip/solver.cpp:117-118)
+//   posting the same Constr twice throws                                (miplib/lpsolve/solver.cpp:103-106)
+//   quadratic rows / objectives throw                                   (miplib/lpsolve/solver.cpp:78-81,109-110)
+//   Binary columns are [0,1] whatever bounds were passed                (miplib/lpsolve/var.cpp:112-123)
+//   missing bounds are -+infinity()                                     (miplib/lpsolve/var.cpp:37-48)
+//   the objective's constant term is dropped                            (miplib/lpsolve/solver.cpp:70-73,
+//                                                                        miplib/scip/solver.cpp:148-157)
+//   set_objective replaces the previous objective                       (lp_solve semantics, :73)
+#include "solver.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <numeric>
+#include <sstream>
+#include <stdexcept>
+
+#include <mipcu.h>
+
+#include "bnb.hpp"
+#include "constr.hpp"
+#include "var.hpp"
+
+namespace miplib {
+
+namespace {
+
+[[noreturn]] void fail(std::string const& what) { throw std::logic_error(what); }
+
+void check(mipcu_ctx* ctx, int rc)
+{
+  if (rc) fail(std::string("Cuda backend: ") + mipcu_last_error(ctx));
+}
+
+}  // namespace
+
+CudaSolver::CudaSolver(bool verbose) : m_verbose(verbose) {}
+
+CudaSolver::~CudaSolver()
+{
+  if (m_ctx) mipcu_destroy(m_ctx);
+}
+
+bool CudaSolver::is_available() { return mipcu_device_count() > 0; }
+
+std::string CudaSolver::backend_info()
+{
+  std::ostringstream s;
+  s << "miplib Cuda backend (restarted Halpern PDHG, sm_100a), " << mipcu_device_count()
+    << " usable device(s)";
+  return s.str();
+}
+
+// ---- model building (host only; works without a GPU) --------------------------------------------
+
+std::shared_ptr<detail::IVar> CudaSolver::create_var(
+  Solver const& solver, Var::Type const& type, std::optional<double> const& lb,
+  std::optional<double> const& ub, std::optional<std::string> const& name)
+{
+  Column col;
+  col.type = type;
+  col.name = name;
+  if (type == Var::Type::Binary)
+  {
+    col.lb = 0;
+    col.ub = 1;
+  }
+  else
+  {
+    col.lb = lb.value_or(-infinity());
+    col.ub = ub.value_or(infinity());
+  }
+  m_columns.push_back(col);
+  m_structure_dirty = true;
+  return std::make_shared<CudaVar>(solver, m_columns.size() - 1);
+}
+
+std::shared_ptr<detail::IConstr> CudaSolver::create_constr(
+  Constr::Type const& type, Expr const& e, std::optional<std::string> const& name)
+{
+  return std::make_shared<CudaConstr>(e, type, name);
+}
+
+std::shared_ptr<detail::IIndicatorConstr> CudaSolver::create_indicator_constr(
+  Constr const& implicant, Constr const& implicand, std::optional<std::string> const& name)
+{
+  return detail::create_reformulatable_indicator_constr(implicant, implicand, name);
+}
+
+std::size_t CudaSolver::column_of(Var const& v) const
+{
+  auto const* impl = dynamic_cast<CudaVar const*>(v.p_impl.get());
+  if (!impl || &impl->backend() != this)
+    fail("Cuda backend: expression uses a variable that belongs to another solver.");
+  return impl->m_column;
+}
+
+void CudaSolver::add(Constr const& constr)
+{
+  auto const& impl = static_cast<CudaConstr const&>(*constr.p_impl);
+  if (impl.m_row >= 0) fail("Attempt to post the same constraint twice.");
+  Expr const e = constr.expr();
+  if (e.is_quadratic()) fail("Cuda backend does not support quadratic constraints.");
+
+  std::vector<Var> const vars = e.linear_vars();
+  std::vector<double> const coefs = e.linear_coeffs();
+  // Expr hands the terms out in identity (pointer) order: sort by column so the CSR - and with
+  // it the FP64 summation order on the device - is reproducible from run to run
+  std::vector<std::pair<std::int32_t, double>> entries(vars.size());
+  for (std::size_t i = 0; i < vars.size(); ++i)
+    entries[i] = {static_cast<std::int32_t>(column_of(vars[i])), coefs[i]};
+  std::sort(entries.begin(), entries.end());
+  for (auto const& [col, coef] : entries)
+  {
+    m_row_idx.push_back(col);
+    m_row_val.push_back(coef);
+  }
+  m_row_start.push_back(static_cast<std::int64_t>(m_row_idx.size()));
+  double const rhs = -e.constant();
+  m_row_hi.push_back(rhs);
+  m_row_lo.push_back(constr.type() == Constr::Equal ? rhs : -infinity());
+  m_row_alive.push_back(1);
+  impl.m_row = static_cast<std::int64_t>(m_row_hi.size()) - 1;
+  m_structure_dirty = true;
+}
+
+void CudaSolver::add(IndicatorConstr const&)
+{
+  fail("Cuda backend does not support indicator constraints (they are reformulated by default).");
+}
+
+void CudaSolver::remove(Constr const& constr)
+{
+  auto const& impl = static_cast<CudaConstr const&>(*constr.p_impl);
+  if (impl.m_row < 0 || !m_row_alive[impl.m_row]) fail("Attempt to remove a constraint that was not posted.");
+  m_row_alive[impl.m_row] = 0;
+  impl.m_row = -1;
+  m_structure_dirty = true;
+}
+
+void CudaSolver::add_lazy_constr_handler(LazyConstrHandler const&, bool) { fail("Not implemented yet."); }
+
+void CudaSolver::set_objective(Solver::Sense const& sense, Expr const& e)
+{
+  if (e.is_quadratic()) fail("Cuda backend does not support quadratic objective functions.");
+  m_objective.assign(m_columns.size(), 0.0);
+  std::vector<Var> const vars = e.linear_vars();
+  std::vector<double> const coefs = e.linear_coeffs();
+  for (std::size_t i = 0; i < vars.size(); ++i) m_objective[column_of(vars[i])] = coefs[i];
+  m_sense = sense;
+  m_objective_dirty = true;
+}
+
+double CudaSolver::get_objective_value() const
+{
+  if (!m_has_solution) fail("Attempt to access the objective value before a solution was found.");
+  return m_objective_value;
+}
+
+void CudaSolver::set_nr_threads(std::size_t n)
+{
+  if (n == 0) fail("Cuda backend: the number of GPUs must be at least 1.");
+  m_nr_gpus = n;
+}
+
+void CudaSolver::column_bounds_changed(std::size_t column)
+{
+  m_dirty_columns.push_back(static_cast<std::int64_t>(column));
+}
+
+void CudaSolver::hint(std::size_t column, double value)
+{
+  if (m_start_x.size() < m_columns.size()) m_start_x.resize(m_columns.size(), 0.0);
+  m_start_x[column] = value;
+}
+
+void CudaSolver::set_warm_start(PartialSolution const& partial_solution)
+{
+  m_start_x.assign(m_columns.size(), 0.0);
+  for (auto const& [var, value] : partial_solution) m_start_x[column_of(var)] = value;
+}
+
+// ---- dump: free-format MPS or CPLEX-LP text of the lowered model ---------------------------------
+
+void CudaSolver::dump(std::string const& filename) const
+{
+  auto ends_with = [&](char const* ext) {
+    std::string e(ext);
+    if (filename.size() < e.size()) return false;
+    std::string tail = filename.substr(filename.size() - e.size());
+    std::transform(tail.begin(), tail.end(), tail.begin(), ::tolower);
+    return tail == e;
+  };
+  bool const as_mps = ends_with(".mps"), as_lp = ends_with(".lp");
+  if (!as_mps && !as_lp) fail("Dumping Cuda backend models to this file type is not supported (use .mps or .lp).");
+  std::ofstream out(filename);
+  if (!out) fail("Cuda backend: cannot open " + filename + " for writing.");
+  out << std::setprecision(17);
+  std::size_t const n = m_columns.size();
+  auto col_name = [&](std::size_t j) {
+    if (m_columns[j].name && m_columns[j].name->find(' ') == std::string::npos) return *m_columns[j].name;
+    return "x" + std::to_string(j);
+  };
+  std::vector<std::size_t> rows;
+  for (std::size_t r = 0; r < m_row_alive.size(); ++r)
+    if (m_row_alive[r]) rows.push_back(r);
+  double const inf = infinity();
+  auto obj = [&](std::size_t j) { return j < m_objective.size() ? m_objective[j] : 0.0; };
+
+  if (as_mps)
+  {
+    out << "NAME miplib_cuda\n";
+    if (m_sense == Solver::Sense::Maximize) out << "OBJSENSE\n    MAX\n";
+    out << "ROWS\n N obj\n";
+    for (std::size_t r : rows)
+      out << (m_row_lo[r] == m_row_hi[r] ? " E " : (m_row_hi[r] < inf ? " L " : " G ")) << "r" << r << "\n";
+    // column-major pass over the row store
+    std::vector<std::vector<std::pair<std::size_t, double>>> by_col(n);
+    for (std::size_t r : rows)
+      for (std::int64_t k = m_row_start[r]; k < m_row_start[r + 1]; ++k)
+        by_col[m_row_idx[k]].push_back({r, m_row_val[k]});
+    out << "COLUMNS\n";
+    bool in_int = false;
+    for (std::size_t j = 0; j < n; ++j)
+    {
+      bool const is_int = m_columns[j].type != Var::Type::Continuous;
+      if (is_int != in_int)
+      {
+        out << " MARKER MARKER " << (is_int ? "INTORG" : "INTEND") << "\n";
+        in_int = is_int;
+      }
+      out << " " << col_name(j) << " obj " << obj(j) << "\n";
+      for (auto const& [r, v] : by_col[j]) out << " " << col_name(j) << " r" << r << " " << v << "\n";
+    }
+    if (in_int) out << " MARKER MARKER INTEND\n";
+    out << "RHS\n";
+    for (std::size_t r : rows)
+    {
+      double const rhs = m_row_hi[r] < inf ? m_row_hi[r] : m_row_lo[r];
+      if (rhs != 0) out << " rhs r" << r << " " << rhs << "\n";
+    }
+    out << "BOUNDS\n";
+    for (std::size_t j = 0; j < n; ++j)
+    {
+      Column const& c = m_columns[j];
+      bool const lo_inf = c.lb <= -inf, hi_inf = c.ub >= inf;
+      if (lo_inf && hi_inf) out << " FR bnd " << col_name(j) << "\n";
+      else
+      {
+        if (lo_inf) out << " MI bnd " << col_name(j) << "\n";
+        else if (c.lb != 0 || c.type != Var::Type::Continuous) out << " LO bnd " << col_name(j) << " " << c.lb << "\n";
+        if (!hi_inf) out << " UP bnd " << col_name(j) << " " << c.ub << "\n";
+        else if (c.type != Var::Type::Continuous) out << " PL bnd " << col_name(j) << "\n";
+      }
+    }
+    out << "ENDATA\n";
+    return;
+  }
+
+  auto term = [&](double v, std::size_t j) {
+    out << (v < 0 ? " - " : " + ") << std::abs(v) << " " << col_name(j);
+  };
+  out << (m_sense == Solver::Sense::Maximize ? "Maximize\n obj:" : "Minimize\n obj:");
+  bool any = false;
+  for (std::size_t j = 0; j < n; ++j)
+    if (obj(j) != 0) { term(obj(j), j); any = true; }
+  if (!any && n) out << " 0 " << col_name(0);
+  out << "\nSubject To\n";
+  for (std::size_t r : rows)
+  {
+    auto body = [&]() {
+      for (std::int64_t k = m_row_start[r]; k < m_row_start[r + 1]; ++k) term(m_row_val[k], m_row_idx[k]);
+    };
+    if (m_row_lo[r] == m_row_hi[r]) { out << " r" << r << ":"; body(); out << " = " << m_row_hi[r] << "\n"; }
+    else
+    {
+      if (m_row_hi[r] < inf) { out << " r" << r << ":"; body(); out << " <= " << m_row_hi[r] << "\n"; }
+      if (m_row_lo[r] > -inf) { out << " r" << r << "_lo:"; body(); out << " >= " << m_row_lo[r] << "\n"; }
+    }
+  }
+  out << "Bounds\n";
+  for (std::size_t j = 0; j < n; ++j)
+  {
+    Column const& c = m_columns[j];
+    if (c.lb <= -inf && c.ub >= inf) out << " " << col_name(j) << " free\n";
+    else
+    {
+      out << " ";
+      if (c.lb <= -inf) out << "-inf"; else out << c.lb;
+      out << " <= " << col_name(j) << " <= ";
+      if (c.ub >= inf) out << "+inf"; else out << c.ub;
+      out << "\n";
+    }
+  }
+  bool header = false;
+  for (std::size_t j = 0; j < n; ++j)
+    if (m_columns[j].type != Var::Type::Continuous)
+    {
+      if (!header) { out << "General\n"; header = true; }
+      out << " " << col_name(j) << "\n";
+    }
+  out << "End\n";
+}
+
+// ---- device side ---------------------------------------------------------------------------------
+
+void CudaSolver::ensure_context()
+{
+  if (m_ctx) return;
+  if (mipcu_create(&m_ctx, 0)) fail(std::string("Cuda backend: ") + mipcu_last_error(nullptr));
+}
+
+void CudaSolver::upload_model()
+{
+  ensure_context();
+  std::size_t const n = m_columns.size();
+  m_objective.resize(n, 0.0);
+  bool const maximize = m_sense == Solver::Sense::Maximize;
+  if (m_structure_dirty)
+  {
+    std::vector<std::int64_t> ptr{0};
+    std::vector<std::int32_t> idx;
+    std::vector<double> val, lo, hi, lb(n), ub(n);
+    m_device_row_of.clear();
+    idx.reserve(m_row_idx.size());
+    val.reserve(m_row_val.size());
+    for (std::size_t r = 0; r < m_row_alive.size(); ++r)
+    {
+      if (!m_row_alive[r]) continue;
+      idx.insert(idx.end(), m_row_idx.begin() + m_row_start[r], m_row_idx.begin() + m_row_start[r + 1]);
+      val.insert(val.end(), m_row_val.begin() + m_row_start[r], m_row_val.begin() + m_row_start[r + 1]);
+      ptr.push_back(static_cast<std::int64_t>(idx.size()));
+      lo.push_back(m_row_lo[r]);
+      hi.push_back(m_row_hi[r]);
+      m_device_row_of.push_back(static_cast<std::int64_t>(r));
+    }
+    for (std::size_t j = 0; j < n; ++j)
+    {
+      lb[j] = m_columns[j].lb;
+      ub[j] = m_columns[j].ub;
+    }
+    check(m_ctx, mipcu_load_lp(m_ctx, static_cast<std::int64_t>(lo.size()), static_cast<std::int64_t>(n),
+                               static_cast<std::int64_t>(idx.size()), ptr.data(), idx.data(), val.data(),
+                               m_objective.data(), lb.data(), ub.data(), lo.data(), hi.data(), maximize));
+    m_structure_dirty = false;
+    m_objective_dirty = false;
+    m_dirty_columns.clear();
+    return;
+  }
+  if (m_objective_dirty)
+  {
+    check(m_ctx, mipcu_set_objective(m_ctx, m_objective.data(), maximize));
+    m_objective_dirty = false;
+  }
+  if (!m_dirty_columns.empty())
+  {
+    std::sort(m_dirty_columns.begin(), m_dirty_columns.end());
+    m_dirty_columns.erase(std::unique(m_dirty_columns.begin(), m_dirty_columns.end()), m_dirty_columns.end());
+    std::vector<double> lb, ub;
+    for (std::int64_t j : m_dirty_columns)
+    {
+      lb.push_back(m_columns[j].lb);
+      ub.push_back(m_columns[j].ub);
+    }
+    check(m_ctx, mipcu_set_bounds(m_ctx, static_cast<std::int64_t>(m_dirty_columns.size()),
+                                  m_dirty_columns.data(), lb.data(), ub.data()));
+    m_dirty_columns.clear();
+  }
+}
+
+CudaSolver::LpOutcome CudaSolver::solve_lp_on_device(std::vector<double>* x_out, std::vector<double>* y_out)
+{
+  mipcu_stats st{};
+  check(m_ctx, mipcu_solve_lp(m_ctx, &st));
+  m_info.lp_solves += 1;
+  m_info.lp_iterations += st.iterations;
+  m_info.kernel_launches += st.kernel_launches;
+  bool const has_point = st.status != MIPCU_NUMERICAL_ERROR;
+  if (x_out)
+  {
+    x_out->assign(m_columns.size(), 0.0);
+    if (has_point) check(m_ctx, mipcu_get_x(m_ctx, x_out->data()));
+  }
+  if (y_out && has_point)
+  {
+    y_out->resize(m_device_row_of.size());
+    check(m_ctx, mipcu_get_y(m_ctx, y_out->data()));
+  }
+  return {st.status, st.primal_obj, st.dual_obj, st.iterations};
+}
+
+std::pair<Solver::Result, bool> CudaSolver::solve()
+{
+  auto const t0 = std::chrono::steady_clock::now();
+  m_info = SolveInfo();
+  m_has_solution = false;
+  m_solution.clear();
+  m_objective.resize(m_columns.size(), 0.0);
+
+  for (Column const& c : m_columns)
+    if (c.lb > c.ub) return {Solver::Result::Infeasible, false};
+  // rows without variables are decided here (an empty model is trivially optimal)
+  for (std::size_t r = 0; r < m_row_alive.size(); ++r)
+    if (m_row_alive[r] && m_row_start[r] == m_row_start[r + 1] && (m_row_lo[r] > 0 || m_row_hi[r] < 0))
+      return {Solver::Result::Infeasible, false};
+  if (m_columns.empty())
+  {
+    m_has_solution = true;
+    m_objective_value = 0;
+    return {Solver::Result::Optimal, true};
+  }
+
+  bool const has_integers = std::any_of(m_columns.begin(), m_columns.end(), [](Column const& c) {
+    return c.type != Var::Type::Continuous;
+  });
+  auto result = has_integers ? solve_integer() : solve_continuous();
+  m_info.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return result;
+}
+
+std::pair<Solver::Result, bool> CudaSolver::solve_continuous()
+{
+  upload_model();
+  check(m_ctx, mipcu_set_param(m_ctx, MIPCU_PARAM_EPS_REL, m_feas_tol));
+  check(m_ctx, mipcu_set_param(m_ctx, MIPCU_PARAM_TIME_LIMIT, m_time_limit));
+  check(m_ctx, mipcu_set_param(m_ctx, MIPCU_PARAM_VERBOSE, m_verbose ? 1 : 0));
+  check(m_ctx, mipcu_set_param(m_ctx, MIPCU_PARAM_OBJ_CUTOFF, std::nan("")));
+  check(m_ctx, mipcu_warm_start(m_ctx, m_start_x.size() == m_columns.size() ? m_start_x.data() : nullptr, nullptr));
+  std::vector<double> x;
+  LpOutcome const lp = solve_lp_on_device(&x, nullptr);
+  using R = Solver::Result;
+  switch (lp.status)
+  {
+    case MIPCU_OPTIMAL:
+      m_solution = std::move(x);
+      m_has_solution = true;
+      m_objective_value = std::inner_product(m_solution.begin(), m_solution.end(), m_objective.begin(), 0.0);
+      m_info.best_bound = lp.dual_obj;
+      m_info.proven_optimal = true;
+      return {R::Optimal, true};
+    case MIPCU_INFEASIBLE: return {R::Infeasible, false};
+    case MIPCU_UNBOUNDED: return {R::Unbounded, false};
+    case MIPCU_INFEASIBLE_OR_UNBOUNDED: return {R::InfeasibleOrUnbounded, false};
+    case MIPCU_ITERATION_LIMIT:
+    case MIPCU_TIME_LIMIT: return {R::Interrupted, false};
+    case MIPCU_NUMERICAL_ERROR: return {R::Error, false};
+    default: return {R::Other, false};
+  }
+}
+
+std::pair<Solver::Result, bool> CudaSolver::solve_integer()
+{
+  CudaBranchAndBound bnb(*this);
+  return bnb.run();
+}
+
+}  // namespace miplib

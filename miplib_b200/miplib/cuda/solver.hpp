@@ -1,0 +1,137 @@
+// miplib/cuda/solver.hpp - Solver::Backend::Cuda: the adapter between the modelling front-end
+// and libmiplib_cuda.so (include/mipcu.h).
+//
+// It plays the role LpsolveSolver / ScipSolver play in the reference (miplib/lpsolve/solver.hpp,
+// miplib/scip/solver.hpp): create_var / create_constr hand out handles, add() lowers a row
+// immediately into host-side CSR triplets (the reference lowers into the vendor model,
+// miplib/lpsolve/solver.cpp:99-131, miplib/scip/solver.cpp:69-143), set_objective() keeps a
+// dense c, and solve() - the single vendor call in the reference (miplib/lpsolve/solver.cpp:156,
+// miplib/scip/solver.cpp:370) - uploads the model through the C ABI and runs the PDHG LP engine,
+// wrapped in a branch-and-bound when integer variables are present.
+//
+// Only the plugin seam is used (Expr::linear_vars/linear_coeffs/constant, Var::p_impl,
+// Constr::p_impl), so the same file drops into the reference tree.
+#pragma once
+
+#include <cstdint>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../solver.hpp"
+
+struct mipcu_ctx;
+
+namespace miplib {
+
+struct CudaSolver : detail::ISolver
+{
+  explicit CudaSolver(bool verbose);
+  ~CudaSolver() override;
+  CudaSolver(CudaSolver const&) = delete;
+  CudaSolver& operator=(CudaSolver const&) = delete;
+
+  std::shared_ptr<detail::IVar> create_var(Solver const& solver, Var::Type const& type,
+                                           std::optional<double> const& lb,
+                                           std::optional<double> const& ub,
+                                           std::optional<std::string> const& name) override;
+  std::shared_ptr<detail::IConstr> create_constr(Constr::Type const& type, Expr const& e,
+                                                 std::optional<std::string> const& name) override;
+  std::shared_ptr<detail::IIndicatorConstr> create_indicator_constr(
+    Constr const& implicant, Constr const& implicand, std::optional<std::string> const& name) override;
+
+  void set_objective(Solver::Sense const& sense, Expr const& e) override;
+  double get_objective_value() const override;
+  Solver::Sense get_objective_sense() const override { return m_sense; }
+
+  void add(Constr const& constr) override;
+  void add(IndicatorConstr const& constr) override;
+  void remove(Constr const& constr) override;
+  void add_lazy_constr_handler(LazyConstrHandler const&, bool) override;
+
+  std::pair<Solver::Result, bool> solve() override;
+
+  void set_non_convex_policy(Solver::NonConvexPolicy) override {}
+  void set_int_feasibility_tolerance(double value) override { m_int_tol = value; }
+  void set_feasibility_tolerance(double value) override { m_feas_tol = value; }
+  void set_epsilon(double value) override { m_epsilon = value; }
+  void set_nr_threads(std::size_t n) override;       // = number of GPUs to use
+  double get_int_feasibility_tolerance() const override { return m_int_tol; }
+  double get_feasibility_tolerance() const override { return m_feas_tol; }
+  double get_epsilon() const override { return m_epsilon; }
+
+  bool supports_indicator_constraint(IndicatorConstr const&) const override { return false; }
+  bool supports_quadratic_constraints() const override { return false; }
+  bool supports_quadratic_objective() const override { return false; }
+
+  double infinity() const override { return 1e20; }   // = MIPCU_INF = SCIP's sentinel
+  void set_time_limit(double secs) override { m_time_limit = secs; }
+  void dump(std::string const& filename) const override;
+  void set_warm_start(PartialSolution const& partial_solution) override;
+  void set_reoptimizing(bool) override {}
+  void setup_reoptimization() override {}
+
+  static std::string backend_info();
+  static bool is_available();
+
+  // ---- model store (host) --------------------------------------------------------------------
+  struct Column
+  {
+    Var::Type type;
+    double lb, ub;
+    std::optional<std::string> name;
+  };
+  std::vector<Column> m_columns;
+  // rows in posting order; row r owns entries [m_row_start[r], m_row_start[r+1]) sorted by column
+  std::vector<std::int64_t> m_row_start{0};
+  std::vector<std::int32_t> m_row_idx;
+  std::vector<double> m_row_val;
+  std::vector<double> m_row_lo, m_row_hi;
+  std::vector<char> m_row_alive;
+  std::vector<double> m_objective;              // dense, minimise/maximise per m_sense
+  Solver::Sense m_sense = Solver::Sense::Minimize;
+
+  // ---- results -------------------------------------------------------------------------------
+  std::vector<double> m_solution;
+  bool m_has_solution = false;
+  double m_objective_value = std::numeric_limits<double>::quiet_NaN();
+
+  // ---- statistics of the last solve (tests and bench read them) --------------------------------
+  struct SolveInfo
+  {
+    std::int64_t lp_solves = 0, lp_iterations = 0, nodes = 0, kernel_launches = 0;
+    double seconds = 0, best_bound = 0;
+    bool proven_optimal = false;
+  };
+  SolveInfo m_info;
+
+  void column_bounds_changed(std::size_t column);
+  void hint(std::size_t column, double value);   // IVar::set_hint: start value of one column
+
+  private:
+  friend struct CudaBranchAndBound;
+  void ensure_context();
+  void upload_model();
+  struct LpOutcome
+  {
+    int status;
+    double primal_obj, dual_obj;
+    std::int64_t iterations;
+  };
+  LpOutcome solve_lp_on_device(std::vector<double>* x_out, std::vector<double>* y_out);
+  std::pair<Solver::Result, bool> solve_continuous();
+  std::pair<Solver::Result, bool> solve_integer();
+  std::size_t column_of(Var const& v) const;
+
+  mipcu_ctx* m_ctx = nullptr;
+  bool m_verbose;
+  bool m_structure_dirty = true, m_objective_dirty = true;
+  std::vector<std::int64_t> m_dirty_columns;
+  std::vector<std::int64_t> m_device_row_of;     // device row -> host row (dead rows are skipped)
+  std::vector<double> m_start_x;                 // warm start (empty: none)
+  double m_feas_tol = 1e-6, m_int_tol = 1e-6, m_epsilon = 1e-9;
+  double m_time_limit = 0;
+  std::size_t m_nr_gpus = 1;
+};
+
+}  // namespace miplib

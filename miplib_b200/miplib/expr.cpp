@@ -1,0 +1,467 @@
+// miplib/expr.cpp - term-list engine behind Expr (see expr.hpp for the design).
+// Behaviour follows the reference's miplib/expr.cpp: cancellation erases terms (:53-119),
+// degree > 2 throws std::logic_error (:165-179), printing is sorted by variable id (:305-359),
+// interval bounds treat +-solver.infinity() as unbounded (:686-744).
+#include "expr.hpp"
+#include "solver.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <ostream>
+#include <sstream>
+#include <stdexcept>
+
+namespace miplib {
+namespace detail {
+
+namespace {
+
+inline IVar const* key(Var const& v) { return v.p_impl.get(); }
+
+template<class... Parts>
+[[noreturn]] void fail(Parts const&... parts)
+{
+  std::ostringstream msg;
+  (msg << ... << parts);
+  throw std::logic_error(msg.str());
+}
+
+}  // namespace
+
+void ExprImpl::canonicalize() const
+{
+  if (canonical) return;
+  std::less<IVar const*> before;
+
+  std::stable_sort(linear.begin(), linear.end(),
+                   [&](LinTerm const& a, LinTerm const& b) { return before(key(a.var), key(b.var)); });
+  std::size_t out = 0;
+  for (std::size_t i = 0; i < linear.size();)
+  {
+    std::size_t j = i;
+    double sum = 0;
+    while (j < linear.size() && key(linear[j].var) == key(linear[i].var)) sum += linear[j++].coef;
+    if (sum != 0)
+    {
+      if (out != i) linear[out] = linear[i];
+      linear[out++].coef = sum;
+    }
+    i = j;
+  }
+  linear.erase(linear.begin() + out, linear.end());
+
+  for (QuadTerm& t : quad)
+    if (before(key(t.second), key(t.first))) std::swap(t.first, t.second);
+  auto quad_before = [&](QuadTerm const& a, QuadTerm const& b) {
+    if (key(a.first) != key(b.first)) return before(key(a.first), key(b.first));
+    return before(key(a.second), key(b.second));
+  };
+  std::stable_sort(quad.begin(), quad.end(), quad_before);
+  out = 0;
+  for (std::size_t i = 0; i < quad.size();)
+  {
+    std::size_t j = i;
+    double sum = 0;
+    while (j < quad.size() && key(quad[j].first) == key(quad[i].first) &&
+           key(quad[j].second) == key(quad[i].second))
+      sum += quad[j++].coef;
+    if (sum != 0)
+    {
+      if (out != i) quad[out] = quad[i];
+      quad[out++].coef = sum;
+    }
+    i = j;
+  }
+  quad.erase(quad.begin() + out, quad.end());
+  canonical = true;
+}
+
+void ExprImpl::add_scaled(ExprImpl const& other, double factor)
+{
+  if (&other == this)
+  {
+    scale(1 + factor);
+    return;
+  }
+  constant += factor * other.constant;
+  if (factor == 0) return;
+  linear.reserve(linear.size() + other.linear.size());
+  for (LinTerm const& t : other.linear) linear.push_back({t.var, factor * t.coef});
+  for (QuadTerm const& t : other.quad) quad.push_back({t.first, t.second, factor * t.coef});
+  if (!other.linear.empty() || !other.quad.empty()) canonical = false;
+}
+
+void ExprImpl::scale(double factor)
+{
+  constant *= factor;
+  for (LinTerm& t : linear) t.coef *= factor;
+  for (QuadTerm& t : quad) t.coef *= factor;
+  if (factor == 0) canonical = false;   // zero terms must disappear
+}
+
+void ExprImpl::multiply(ExprImpl const& rhs)
+{
+  if (&rhs == this)
+  {
+    ExprImpl snapshot(*this);
+    multiply(snapshot);
+    return;
+  }
+  canonicalize();
+  rhs.canonicalize();
+  if (!quad.empty() && !rhs.quad.empty())
+    fail("Attempt to create quartic expression ", *this, " * ", rhs, ".");
+  if ((!quad.empty() && !rhs.linear.empty()) || (!linear.empty() && !rhs.quad.empty()))
+    fail("Attempt to create cubic expression ", *this, " * ", rhs, ".");
+
+  std::vector<QuadTerm> new_quad;
+  for (QuadTerm const& t : quad) new_quad.push_back({t.first, t.second, t.coef * rhs.constant});
+  for (QuadTerm const& t : rhs.quad) new_quad.push_back({t.first, t.second, t.coef * constant});
+  for (LinTerm const& a : linear)
+    for (LinTerm const& b : rhs.linear) new_quad.push_back({a.var, b.var, a.coef * b.coef});
+
+  std::vector<LinTerm> new_linear;
+  for (LinTerm const& t : linear) new_linear.push_back({t.var, t.coef * rhs.constant});
+  for (LinTerm const& t : rhs.linear) new_linear.push_back({t.var, t.coef * constant});
+
+  constant *= rhs.constant;
+  linear.swap(new_linear);
+  quad.swap(new_quad);
+  canonical = false;
+}
+
+void ExprImpl::divide_by_var(Var const& v)
+{
+  canonicalize();
+  auto fractional = [&]() { fail("Attempt to create fractional expression ", *this, " / ", v, "."); };
+  if (constant != 0 || linear.size() > 1) fractional();
+  double new_constant = 0;
+  if (linear.size() == 1)
+  {
+    if (!linear[0].var.is_same(v)) fractional();
+    new_constant = linear[0].coef;
+  }
+  std::vector<LinTerm> new_linear;
+  for (QuadTerm const& t : quad)
+  {
+    if (t.first.is_same(v)) new_linear.push_back({t.second, t.coef});
+    else if (t.second.is_same(v)) new_linear.push_back({t.first, t.coef});
+    else fractional();
+  }
+  constant = new_constant;
+  linear.swap(new_linear);
+  quad.clear();
+  canonical = false;
+}
+
+Solver const& ExprImpl::solver() const
+{
+  canonicalize();
+  if (!linear.empty()) return linear.front().var.solver();
+  if (!quad.empty()) return quad.front().first.solver();
+  fail("Attempt to access solver from constant expression ", *this, ".");
+}
+
+std::ostream& operator<<(std::ostream& os, ExprImpl const& e)
+{
+  e.canonicalize();
+  // printing order is by variable id (name), which - unlike identity order - is stable across runs
+  struct Item { std::string a, b; double coef; };
+  std::vector<Item> quads, lins;
+  for (QuadTerm const& t : e.quad)
+  {
+    std::string a = t.first.id(), b = t.second.id();
+    if (b < a) std::swap(a, b);
+    quads.push_back({a, b, t.coef});
+  }
+  for (LinTerm const& t : e.linear) lins.push_back({t.var.id(), "", t.coef});
+  auto by_id = [](Item const& x, Item const& y) { return x.a != y.a ? x.a < y.a : x.b < y.b; };
+  std::sort(quads.begin(), quads.end(), by_id);
+  std::sort(lins.begin(), lins.end(), by_id);
+
+  bool nothing_printed = true;
+  auto lead = [&](double c, bool is_constant) {
+    if (nothing_printed) { if (c < 0) os << "-"; }
+    else os << (c < 0 ? " - " : " + ");
+    double mag = std::abs(c);
+    if (is_constant) os << mag;
+    else if (mag != 1) os << mag << " ";
+    nothing_printed = false;
+  };
+  for (Item const& t : quads) { lead(t.coef, false); os << t.a << " " << t.b; }
+  for (Item const& t : lins) { lead(t.coef, false); os << t.a; }
+  if (e.constant != 0 || nothing_printed) lead(e.constant, true);
+  return os;
+}
+
+}  // namespace detail
+
+using detail::LinTerm;
+using detail::QuadTerm;
+
+std::ostream& operator<<(std::ostream& os, Expr const& e) { return os << *e.p_impl; }
+
+Expr Expr::copy() const
+{
+  Expr r;
+  r.p_impl = std::make_shared<detail::ExprImpl>(*p_impl);
+  return r;
+}
+
+bool Expr::is_constant() const
+{
+  p_impl->canonicalize();
+  return p_impl->linear.empty() && p_impl->quad.empty();
+}
+
+bool Expr::is_linear() const
+{
+  p_impl->canonicalize();
+  return p_impl->quad.empty();
+}
+
+bool Expr::is_quadratic() const { return !is_linear(); }
+
+bool Expr::must_be_binary() const
+{
+  if (is_constant()) return constant() == 0 || constant() == 1;
+  auto const& e = *p_impl;
+  if (e.linear.size() + e.quad.size() != 1) return false;
+  double coef;
+  if (e.quad.empty())
+  {
+    if (e.linear[0].var.type() != Var::Type::Binary) return false;
+    coef = e.linear[0].coef;
+  }
+  else
+  {
+    if (e.quad[0].first.type() != Var::Type::Binary || e.quad[0].second.type() != Var::Type::Binary)
+      return false;
+    coef = e.quad[0].coef;
+  }
+  // b, b1*b2, 1 - b or 1 - b1*b2
+  return (e.constant == 0 && coef == 1) || (e.constant == 1 && coef == -1);
+}
+
+bool Expr::must_be_integer() const
+{
+  auto integral = [](double c) { return std::isfinite(c) && std::trunc(c) == c; };
+  auto discrete = [](Var const& v) { return v.type() != Var::Type::Continuous; };
+  p_impl->canonicalize();
+  if (!integral(constant())) return false;
+  for (LinTerm const& t : p_impl->linear)
+    if (!integral(t.coef) || !discrete(t.var)) return false;
+  for (QuadTerm const& t : p_impl->quad)
+    if (!integral(t.coef) || !discrete(t.first) || !discrete(t.second)) return false;
+  return true;
+}
+
+std::vector<double> Expr::linear_coeffs() const
+{
+  p_impl->canonicalize();
+  std::vector<double> r;
+  r.reserve(p_impl->linear.size());
+  for (LinTerm const& t : p_impl->linear) r.push_back(t.coef);
+  return r;
+}
+
+std::vector<Var> Expr::linear_vars() const
+{
+  p_impl->canonicalize();
+  std::vector<Var> r;
+  r.reserve(p_impl->linear.size());
+  for (LinTerm const& t : p_impl->linear) r.push_back(t.var);
+  return r;
+}
+
+std::vector<double> Expr::quad_coeffs() const
+{
+  p_impl->canonicalize();
+  std::vector<double> r;
+  for (QuadTerm const& t : p_impl->quad) r.push_back(t.coef);
+  return r;
+}
+
+std::vector<Var> Expr::quad_vars_1() const
+{
+  p_impl->canonicalize();
+  std::vector<Var> r;
+  for (QuadTerm const& t : p_impl->quad) r.push_back(t.first);
+  return r;
+}
+
+std::vector<Var> Expr::quad_vars_2() const
+{
+  p_impl->canonicalize();
+  std::vector<Var> r;
+  for (QuadTerm const& t : p_impl->quad) r.push_back(t.second);
+  return r;
+}
+
+namespace {
+
+// [min, max] of coef * v over the variable's box, clipped to +-inf; with ignore_inf an
+// unbounded side counts as if the variable were 1 (so only the coefficient matters)
+std::pair<double, double> term_range(Var const& v, double coef, bool ignore_inf)
+{
+  double const inf = v.solver().infinity();
+  double lo = v.lb(), hi = v.ub();
+  if (ignore_inf)
+  {
+    if (lo == -inf) lo = 1;
+    if (hi == inf) hi = 1;
+  }
+  if (coef == 0) return {0.0, 0.0};
+  double a = coef * lo, b = coef * hi;
+  if (coef < 0) std::swap(a, b);
+  return {std::max(-inf, a), std::min(inf, b)};
+}
+
+}  // namespace
+
+std::pair<double, double> Expr::bounds() const
+{
+  if (!is_linear())
+  {
+    std::ostringstream msg;
+    msg << "Querying bounds of a nonlinear expression is not implemented yet: " << *this << ".";
+    throw std::logic_error(msg.str());
+  }
+  double lo = constant(), hi = constant();
+  if (is_constant()) return {lo, hi};
+  double const inf = solver().infinity();
+  for (LinTerm const& t : p_impl->linear)
+  {
+    auto [a, b] = term_range(t.var, t.coef, false);
+    lo += a;
+    hi += b;
+  }
+  return {std::max(-inf, lo), std::min(inf, hi)};
+}
+
+// (smallest, largest) over the terms of the term's maximum absolute value
+std::pair<double, double> Expr::numerical_range(bool ignore_inf_var_bounds) const
+{
+  double const inf = solver().infinity();
+  double smallest = std::abs(constant()) == 0 ? inf : std::abs(constant());
+  double largest = std::abs(constant());
+  p_impl->canonicalize();
+  for (LinTerm const& t : p_impl->linear)
+  {
+    auto [a, b] = term_range(t.var, t.coef, ignore_inf_var_bounds);
+    double mag = std::max(std::abs(a), std::abs(b));
+    smallest = std::min(smallest, mag);
+    largest = std::max(largest, mag);
+  }
+  return {smallest, largest};
+}
+
+Expr& Expr::operator+=(Var const& v)
+{
+  p_impl->linear.push_back({v, 1.0});
+  p_impl->canonical = false;
+  return *this;
+}
+
+Expr& Expr::operator-=(Var const& v)
+{
+  p_impl->linear.push_back({v, -1.0});
+  p_impl->canonical = false;
+  return *this;
+}
+
+Expr& Expr::operator+=(Expr const& e) { p_impl->add_scaled(*e.p_impl, 1.0); return *this; }
+Expr& Expr::operator-=(Expr const& e) { p_impl->add_scaled(*e.p_impl, -1.0); return *this; }
+Expr& Expr::operator*=(Expr const& e) { p_impl->multiply(*e.p_impl); return *this; }
+
+Expr Expr::operator-() const { Expr r(copy()); r *= -1.0; return r; }
+Expr Expr::operator+(double c) const { Expr r(copy()); r += c; return r; }
+Expr Expr::operator+(Var const& v) const { Expr r(copy()); r += v; return r; }
+Expr Expr::operator+(Expr const& e) const { Expr r(copy()); r += e; return r; }
+Expr Expr::operator-(Var const& v) const { Expr r(copy()); r -= v; return r; }
+Expr Expr::operator-(Expr const& e) const { Expr r(copy()); r -= e; return r; }
+Expr Expr::operator*(double c) const { Expr r(copy()); r *= c; return r; }
+Expr Expr::operator*(Var const& v) const { Expr r(copy()); r *= v; return r; }
+Expr Expr::operator*(Expr const& e) const { Expr r(copy()); r *= e; return r; }
+
+Expr Expr::operator/(Expr const& e) const
+{
+  if (!e.is_constant())
+  {
+    std::ostringstream msg;
+    msg << "Attempt to divide non-constant expression " << *this << " / " << e << ".";
+    throw std::logic_error(msg.str());
+  }
+  return *this / e.constant();
+}
+
+namespace {
+
+// extreme values of x*y for x in [l1,u1], y in [l2,u2]; a square never goes below 0
+double product_min(double l1, double u1, double l2, double u2, bool same_var)
+{
+  if (same_var) return (l1 <= 0 && u1 >= 0) ? 0.0 : std::min(l1 * l1, u1 * u1);
+  return std::min(std::min(l1 * l2, l1 * u2), std::min(u1 * l2, u1 * u2));
+}
+
+double product_max(double l1, double u1, double l2, double u2)
+{
+  return std::max(std::max(l1 * l2, l1 * u2), std::max(u1 * l2, u1 * u2));
+}
+
+}  // namespace
+
+double Expr::lb() const
+{
+  if (is_constant()) return constant();
+  double const inf = solver().infinity();
+  double total = constant();
+  for (LinTerm const& t : p_impl->linear)
+  {
+    // the side of the box that minimises coef * v
+    double side = t.coef > 0 ? t.var.lb() : t.var.ub();
+    if ((t.coef > 0 && side == -inf) || (t.coef < 0 && side == inf)) return -inf;
+    total += t.coef * side;
+  }
+  for (QuadTerm const& t : p_impl->quad)
+  {
+    double l1 = t.first.lb(), u1 = t.first.ub(), l2 = t.second.lb(), u2 = t.second.ub();
+    if (t.coef > 0)
+    {
+      double m = product_min(l1, u1, l2, u2, t.first.is_same(t.second));
+      if (m <= -inf) return -inf;
+      total += t.coef * m;
+    }
+    else
+    {
+      double m = product_max(l1, u1, l2, u2);
+      if (m >= inf) return -inf;
+      total += t.coef * m;
+    }
+  }
+  return total;
+}
+
+double Expr::ub() const { return -(-(*this)).lb(); }
+
+double Expr::value() const
+{
+  p_impl->canonicalize();
+  double total = constant();
+  for (LinTerm const& t : p_impl->linear) total += t.coef * t.var.value();
+  for (QuadTerm const& t : p_impl->quad) total += t.coef * t.first.value() * t.second.value();
+  return total;
+}
+
+std::vector<Var> Expr::vars() const
+{
+  p_impl->canonicalize();
+  std::vector<Var> all;
+  for (LinTerm const& t : p_impl->linear) all.push_back(t.var);
+  for (QuadTerm const& t : p_impl->quad) { all.push_back(t.first); all.push_back(t.second); }
+  std::sort(all.begin(), all.end(), std::less<Var>());
+  all.erase(std::unique(all.begin(), all.end(), std::equal_to<Var>()), all.end());
+  return all;
+}
+
+}  // namespace miplib
