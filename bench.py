@@ -196,16 +196,17 @@ def run_cuda(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
 
+    from miplib_b200 import sharding
     L = gen.config(args.config)
     A = L.A.tocsr()
     A.sort_indices()
     m, n = A.shape
-    # row block of this rank
-    r0, r1 = (m * rank) // world, (m * (rank + 1)) // world
-    Ab = A[r0:r1] if world > 1 else A
-    host = dict(indptr=pinned_like(Ab.indptr.astype(np.int64)), indices=pinned_like(Ab.indices.astype(np.int32)),
-                data=pinned_like(Ab.data), c=pinned_like(L.c), lb=pinned_like(L.lb), ub=pinned_like(L.ub),
-                row_lo=pinned_like(L.row_lo[r0:r1]), row_hi=pinned_like(L.row_hi[r0:r1]))
+    # row block of this rank (the whole matrix when world == 1)
+    r0, r1 = sharding.row_block(m, rank, world)
+    ptr, idx, val, lo, hi = sharding.shard_csr(A, L.row_lo, L.row_hi, rank, world)
+    host = dict(indptr=pinned_like(ptr), indices=pinned_like(idx), data=pinned_like(val),
+                c=pinned_like(L.c), lb=pinned_like(L.lb), ub=pinned_like(L.ub),
+                row_lo=pinned_like(lo), row_hi=pinned_like(hi))
     h2d = sum(v.nbytes for v in host.values())
     d2h = 8 * (n + (r1 - r0))
 

@@ -47,7 +47,7 @@ def build_cuda(force: bool = False) -> Path:
     srcs = cuda_sources()
     deps = srcs + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "mipcu.h"]
     if force or _stale(CUDA_LIB, deps):
-        _run([NVCC, *NVCC_FLAGS, "-o", CUDA_LIB, *srcs])
+        _run([NVCC, *NVCC_FLAGS, "-o", CUDA_LIB, *srcs, "-ldl"])
     return CUDA_LIB
 
 

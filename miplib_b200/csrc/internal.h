@@ -90,6 +90,8 @@ struct mipcu_ctx {
   // sharding (world == 1: plain single-GPU context)
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;
+  double* row_sums = nullptr;     // 8 doubles: all-reduced row-side scalars of check iterations
+  int64_t collectives = 0;        // NCCL calls issued by the current call
 
   // model as loaded (unscaled), device resident
   int m = 0, n = 0;
@@ -142,6 +144,10 @@ int choose_tpr(double avg_row_len, int override_tpr);
 void set_bounds(mipcu_ctx* ctx, int64_t n_changed, const int64_t* cols, const double* lb,
                 const double* ub);
 void spmv_host(mipcu_ctx* ctx, int transpose, const double* v, double* out);
+
+// ---- dist.cu --------------------------------------------------------------------------------
+void dist_allreduce(mipcu_ctx* ctx, double* buf, size_t count, bool max_instead_of_sum);
+double dist_sum_scalar(mipcu_ctx* ctx, double v);
 
 // ---- solve.cu -------------------------------------------------------------------------------
 void solve_lp(mipcu_ctx* ctx, mipcu_stats* out);

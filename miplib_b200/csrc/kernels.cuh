@@ -151,6 +151,38 @@ struct ColStepArgs {
   int n; int iter_in_block;
 };
 
+// The per-column part of the col step, given (K' yhat)_j: Halpern update of x and K'y, projected
+// primal step, reflected point; on CHECK iterations the six partial sums of the restart / KKT test.
+// Shared by the fused single-GPU kernel and by k_primal_step of the row-sharded path.
+template <bool CHECK, bool STORE>
+__device__ __forceinline__ void col_epilogue(const ColStepArgs& a, const int j, const double atyh,
+                                             const double tau, const double w_new, double (&red)[6]) {
+  const double xb = a.xbar[j], x0 = a.x0[j], at = a.aty[j], at0 = a.aty0[j];
+  const double cj = a.c[j], lj = a.l[j], uj = a.u[j];
+  if (CHECK) {
+    const double xh = a.xhat_in[j];
+    const double dx = xb - xh;            // = xhat_k - x_k  because xbar = 2 xhat - x
+    const double dat = atyh - at;
+    const double d0 = xh - x0;
+    red[0] = dx * dx;
+    red[1] = dx * dat;
+    red[2] = d0 * d0;
+    const double r = cj - atyh;
+    const double rp = fmax(r, 0.0), rm = fmax(-r, 0.0);
+    const double viol = ((isfinite(lj) ? 0.0 : rp) + (isfinite(uj) ? 0.0 : rm)) / a.d2[j];
+    red[3] = viol * viol;
+    red[4] = cj * xh;
+    red[5] = (isfinite(lj) ? lj * rp : 0.0) - (isfinite(uj) ? uj * rm : 0.0);
+    a.aty_cand[j] = atyh;
+  }
+  const double xn = w_new * xb + (1.0 - w_new) * x0;
+  const double atn = w_new * (2.0 * atyh - at) + (1.0 - w_new) * at0;
+  const double xh2 = clampd(xn - tau * (cj - atn), lj, uj);
+  a.xbar[j] = 2.0 * xh2 - xn;
+  a.aty[j] = atn;
+  if (STORE) a.xhat_out[j] = xh2;
+}
+
 template <int TPR, bool CHECK, bool STORE>
 __global__ void __launch_bounds__(kThreads)
 k_col_step(const ColStepArgs a) {
@@ -163,33 +195,27 @@ k_col_step(const ColStepArgs a) {
   const double w_new = (k + 1.0) / (k + 2.0);
   const int j = blockIdx.x * kRowsPerCta + threadIdx.x;
   double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  if (j < a.n) {
-    const double atyh = s_sum[threadIdx.x];
-    const double xb = a.xbar[j], x0 = a.x0[j], at = a.aty[j], at0 = a.aty0[j];
-    const double cj = a.c[j], lj = a.l[j], uj = a.u[j];
-    if (CHECK) {
-      const double xh = a.xhat_in[j];
-      const double dx = xb - xh;            // = xhat_k - x_k  because xbar = 2 xhat - x
-      const double dat = atyh - at;
-      const double d0 = xh - x0;
-      red[0] = dx * dx;
-      red[1] = dx * dat;
-      red[2] = d0 * d0;
-      const double r = cj - atyh;
-      const double rp = fmax(r, 0.0), rm = fmax(-r, 0.0);
-      const double viol = ((isfinite(lj) ? 0.0 : rp) + (isfinite(uj) ? 0.0 : rm)) / a.d2[j];
-      red[3] = viol * viol;
-      red[4] = cj * xh;
-      red[5] = (isfinite(lj) ? lj * rp : 0.0) - (isfinite(uj) ? uj * rm : 0.0);
-      a.aty_cand[j] = atyh;
-    }
-    const double xn = w_new * xb + (1.0 - w_new) * x0;
-    const double atn = w_new * (2.0 * atyh - at) + (1.0 - w_new) * at0;
-    const double xh2 = clampd(xn - tau * (cj - atn), lj, uj);
-    a.xbar[j] = 2.0 * xh2 - xn;
-    a.aty[j] = atn;
-    if (STORE) a.xhat_out[j] = xh2;
+  if (j < a.n) col_epilogue<CHECK, STORE>(a, j, s_sum[threadIdx.x], tau, w_new, red);
+  if (CHECK) {
+    const int q[6] = {Q_DX2, Q_DXDATY, Q_DX0, Q_DRES2, Q_POBJ, Q_DOBJ_COL};
+    cta_reduce_store<6>(red, q, a.partials, sc->max_blocks);
   }
+}
+
+// Row-sharded path: K' yhat arrives already summed over the ranks (NCCL all-reduce of the local
+// partial products), so the primal side is a plain elementwise kernel with the same arithmetic
+// and the same CTA-to-column mapping (hence the same partial sums) as the fused kernel.
+template <bool CHECK, bool STORE>
+__global__ void __launch_bounds__(kThreads)
+k_primal_step(const ColStepArgs a, const double* __restrict__ atyh) {
+  const Scalars* sc = a.sc;
+  if (sc->done) return;
+  const double tau = sc->tau;
+  const double k = (double)(sc->k_base + a.iter_in_block);
+  const double w_new = (k + 1.0) / (k + 2.0);
+  const int j = blockIdx.x * kRowsPerCta + threadIdx.x;
+  double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (j < a.n) col_epilogue<CHECK, STORE>(a, j, atyh[j], tau, w_new, red);
   if (CHECK) {
     const int q[6] = {Q_DX2, Q_DXDATY, Q_DX0, Q_DRES2, Q_POBJ, Q_DOBJ_COL};
     cta_reduce_store<6>(red, q, a.partials, sc->max_blocks);

@@ -419,7 +419,7 @@ void prepare(mipcu_ctx* ctx) {
   const int m = ctx->m, n = ctx->n;
   Csr &R = ctx->rows, &C = ctx->cols;
   const bool scaling = ctx->params[MIPCU_PARAM_SCALING] != 0.0;
-  if (scaling && ctx->nnz > 0) {
+  if (scaling && (ctx->nnz > 0 || ctx->world > 1)) {
     double* rf = ctx->tmp_m;
     double* cf = ctx->tmp_n;
     for (int sweep = 0; sweep < RUIZ_PASSES + 1; ++sweep) {
@@ -431,6 +431,8 @@ void prepare(mipcu_ctx* ctx) {
         k_row_norm<1><<<gr, kThreads, 0, st>>>(R.ptr, R.val, rf, m);
         k_row_norm<1><<<gc, kThreads, 0, st>>>(C.ptr, C.val, cf, n);
       }
+      // row-sharded: a column's norm spans all ranks (max for Ruiz, sum for Pock-Chambolle)
+      dist_allreduce(ctx, cf, (size_t)n, sweep < RUIZ_PASSES);
       k_factor<<<grid_for(m), kThreads, 0, st>>>(rf, ctx->d1, m);
       k_factor<<<grid_for(n), kThreads, 0, st>>>(cf, ctx->d2, n);
       k_scale_matrix<true><<<gr, kThreads, 0, st>>>(R.ptr, R.idx, R.val, rf, cf, m);
@@ -442,7 +444,7 @@ void prepare(mipcu_ctx* ctx) {
   double step = ctx->params[MIPCU_PARAM_STEP_SIZE];
   if (step > 0.0) {
     ctx->eta = step;
-  } else if (ctx->nnz == 0 || n == 0 || m == 0) {
+  } else if (ctx->world <= 1 && (ctx->nnz == 0 || n == 0 || m == 0)) {
     ctx->eta = 1.0;
   } else {
     double* v = ctx->tmp_n;
@@ -460,6 +462,7 @@ void prepare(mipcu_ctx* ctx) {
       for (int b = 0; b < POWER_BATCH; ++b) {
         spmv_plain(ctx, R, v, u);
         spmv_plain(ctx, C, u, v);
+        dist_allreduce(ctx, v, (size_t)n, false);
         s2 = device_norm2(ctx, v, n);
         if (s2 == 0.0) { zero = true; break; }
         k_scale_inplace<<<grid_for(n), kThreads, 0, st>>>(v, 1.0 / s2, n);
@@ -498,9 +501,9 @@ void refresh_vectors(mipcu_ctx* ctx) {
     ctx->launches += 2;
   }
   ctx->cnorm = std::sqrt(sumsq<0>(ctx, ctx->c, nullptr, n));
-  ctx->bnorm = std::sqrt(sumsq<1>(ctx, ctx->lo, ctx->hi, m));
+  ctx->bnorm = std::sqrt(dist_sum_scalar(ctx, sumsq<1>(ctx, ctx->lo, ctx->hi, m)));
   double cs = std::sqrt(sumsq<0>(ctx, ctx->cs, nullptr, n));
-  double bs = std::sqrt(sumsq<1>(ctx, ctx->los, ctx->his, m));
+  double bs = std::sqrt(dist_sum_scalar(ctx, sumsq<1>(ctx, ctx->los, ctx->his, m)));
   ctx->w0 = (cs > 0.0 && bs > 0.0) ? cs / bs : 1.0;
   ctx->vectors_dirty = false;
 }

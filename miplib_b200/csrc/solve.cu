@@ -38,10 +38,23 @@ __device__ double fixed_point_error(const Scalars* sc, double dx2, double dxdaty
 }
 
 // after the FIRST iteration of a block: records the fixed-point error right after a restart
-__global__ void __launch_bounds__(kThreads) k_ctrl_first(Scalars* sc, const double* partials) {
+// row-sharded: the row-side sums of this rank, to be all-reduced before the controllers read them
+__global__ void __launch_bounds__(kThreads) k_sum_row_partials(const Scalars* sc, const double* partials,
+                                                               double* row_sums) {
   if (sc->done) return;
   const int mb = sc->max_blocks;
-  double dy2 = cta_sum_partials(partials + (size_t)Q_DY2 * mb, sc->nblk_row);
+  const int q[4] = {Q_DY2, Q_DY0, Q_DOBJ_ROW, Q_PRES2};
+  for (int i = 0; i < 4; ++i) {
+    double v = cta_sum_partials(partials + (size_t)q[i] * mb, sc->nblk_row);
+    if (threadIdx.x == 0) row_sums[q[i]] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_ctrl_first(Scalars* sc, const double* partials,
+                                                         const double* row_sums) {
+  if (sc->done) return;
+  const int mb = sc->max_blocks;
+  double dy2 = row_sums ? row_sums[Q_DY2] : cta_sum_partials(partials + (size_t)Q_DY2 * mb, sc->nblk_row);
   double dx2 = cta_sum_partials(partials + (size_t)Q_DX2 * mb, sc->nblk_col);
   double dxd = cta_sum_partials(partials + (size_t)Q_DXDATY * mb, sc->nblk_col);
   if (threadIdx.x == 0 && sc->k_base == 0) {
@@ -52,13 +65,15 @@ __global__ void __launch_bounds__(kThreads) k_ctrl_first(Scalars* sc, const doub
 }
 
 // after the LAST iteration of a block: KKT test, restart test, primal-weight update
-__global__ void __launch_bounds__(kThreads) k_ctrl_check(Scalars* sc, const double* partials) {
+__global__ void __launch_bounds__(kThreads) k_ctrl_check(Scalars* sc, const double* partials,
+                                                         const double* row_sums) {
   if (sc->done) return;
   const int mb = sc->max_blocks;
   double q[Q_COUNT];
   for (int i = 0; i < Q_COUNT; ++i) {
     const bool is_row = (i == Q_DY2 || i == Q_DY0 || i == Q_DOBJ_ROW || i == Q_PRES2);
-    q[i] = cta_sum_partials(partials + (size_t)i * mb, is_row ? sc->nblk_row : sc->nblk_col);
+    if (is_row && row_sums) q[i] = row_sums[i];
+    else q[i] = cta_sum_partials(partials + (size_t)i * mb, is_row ? sc->nblk_row : sc->nblk_col);
   }
   if (threadIdx.x != 0) return;
   const double fp = fixed_point_error(sc, q[Q_DX2], q[Q_DXDATY], q[Q_DY2]);
@@ -215,8 +230,32 @@ void row_step(mipcu_ctx* ctx, int i, bool check) {
 void col_step(mipcu_ctx* ctx, int i, bool check, const double* xhat_in, double* xhat_out) {
   if (ctx->n == 0) return;
   ColStepArgs a = col_args(ctx, i, xhat_in, xhat_out);
+  if (ctx->world > 1) {
+    // row-sharded: local partial K_g' yhat_g -> all-reduce over NVLink -> elementwise primal step
+    // (replicated: every rank computes the same xbar from the same summed vector)
+    spmv_plain(ctx, ctx->cols, ctx->yhat, ctx->tmp_n);
+    dist_allreduce(ctx, ctx->tmp_n, (size_t)ctx->n, false);
+    const int g = grid_for(ctx->n, kRowsPerCta);
+    const bool store = xhat_out != nullptr;
+    cudaStream_t st = ctx->stream;
+    if (check && store) k_primal_step<true, true><<<g, kThreads, 0, st>>>(a, ctx->tmp_n);
+    else if (check) k_primal_step<true, false><<<g, kThreads, 0, st>>>(a, ctx->tmp_n);
+    else if (store) k_primal_step<false, true><<<g, kThreads, 0, st>>>(a, ctx->tmp_n);
+    else k_primal_step<false, false><<<g, kThreads, 0, st>>>(a, ctx->tmp_n);
+    ctx->launches++;
+    return;
+  }
   MIPCU_DISPATCH_TPR(ctx->cols.tpr, launch_col<T>(ctx, a, check, xhat_out != nullptr));
   ctx->launches++;
+}
+
+// row-sharded check iterations: make the row-side sums global before a controller runs
+const double* global_row_sums(mipcu_ctx* ctx) {
+  if (ctx->world <= 1) return nullptr;
+  k_sum_row_partials<<<1, kThreads, 0, ctx->stream>>>(ctx->d_sc, ctx->partials, ctx->row_sums);
+  ctx->launches++;
+  dist_allreduce(ctx, ctx->row_sums, 4, false);
+  return ctx->row_sums;
 }
 
 void kkt_row(mipcu_ctx* ctx) {
@@ -254,11 +293,11 @@ void enqueue_block(mipcu_ctx* ctx, int period, cudaEvent_t* time_events) {
     col_step(ctx, i, first || last, xin, xout);
     if (timed) MIPCU_CK(cudaEventRecord(time_events[2], st));
     if (first) {
-      k_ctrl_first<<<1, kThreads, 0, st>>>(ctx->d_sc, ctx->partials);
+      k_ctrl_first<<<1, kThreads, 0, st>>>(ctx->d_sc, ctx->partials, global_row_sums(ctx));
       ctx->launches++;
     }
   }
-  k_ctrl_check<<<1, kThreads, 0, st>>>(ctx->d_sc, ctx->partials);
+  k_ctrl_check<<<1, kThreads, 0, st>>>(ctx->d_sc, ctx->partials, global_row_sums(ctx));
   ctx->launches++;
   restart_apply(ctx);
 }
@@ -302,6 +341,7 @@ void init_iterate(mipcu_ctx* ctx, Scalars& h) {
   if (n) {
     if (m && ctx->nnz) spmv_plain(ctx, ctx->cols, ctx->yhat, ctx->aty_cand);
     else MIPCU_CK(cudaMemsetAsync(ctx->aty_cand, 0, sizeof(double) * n, st));
+    dist_allreduce(ctx, ctx->aty_cand, (size_t)n, false);
   }
   restart_apply(ctx);
   MIPCU_CK(cudaStreamSynchronize(st));   // h is a stack object: the H2D copy must be done
@@ -338,7 +378,12 @@ void solve_lp(mipcu_ctx* ctx, mipcu_stats* out) {
   const bool verbose = ctx->params[MIPCU_PARAM_VERBOSE] != 0.0;
   const int graph_mode = (int)ctx->params[MIPCU_PARAM_USE_GRAPH];
   // small problems are launch-bound: replay the block as a CUDA graph
-  const bool use_graph = graph_mode == 1 || (graph_mode < 0 && ctx->nnz < (int64_t)4 << 20);
+  // row-sharded solves enqueue directly (NCCL calls sit between the kernels)
+  const bool use_graph = ctx->world <= 1 &&
+                         (graph_mode == 1 || (graph_mode < 0 && ctx->nnz < (int64_t)4 << 20));
+  // a wall-clock limit would let ranks disagree on when to stop issuing collectives
+  MIPCU_REQUIRE(ctx->world <= 1 || time_limit <= 0.0,
+                "a time limit is not supported on row-sharded contexts (use the iteration limit)");
 
   Scalars h;
   init_iterate(ctx, h);
