@@ -120,9 +120,11 @@ int  mipcu_warm_start(mipcu_ctx* ctx, const double* x /* n or NULL */, const dou
 /* --- solve ---------------------------------------------------------------------------------- */
 int  mipcu_solve_lp(mipcu_ctx* ctx, mipcu_stats* out);
 /* B node LPs that share A, c and the row sides but differ in column bounds; bounds are
- * [B][n] row-major on the host.  x_out ([B][n]) may be NULL. */
+ * [B][n] row-major on the host.  cutoff ([B], model's own sense, NaN = none) may be NULL: then
+ * MIPCU_PARAM_OBJ_CUTOFF applies to every node.  x_out ([B][n]) may be NULL.  All nodes start
+ * from x = clamp(0), y = 0 and run to MIPCU_PARAM_EPS_REL / ITER_LIMIT / TIME_LIMIT. */
 int  mipcu_solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* ub,
-                          mipcu_stats* out /* [B] */, double* x_out);
+                          const double* cutoff, mipcu_stats* out /* [B] */, double* x_out);
 int  mipcu_get_x(mipcu_ctx* ctx, double* x /* n */);
 int  mipcu_get_y(mipcu_ctx* ctx, double* y /* m (local rows when sharded) */);
 

@@ -104,7 +104,7 @@ def load_library() -> C.CDLL:
         "mipcu_get_param": (C.c_int, [vp, C.c_int, P(dbl)]),
         "mipcu_warm_start": (C.c_int, [vp, vp, vp]),
         "mipcu_solve_lp": (C.c_int, [vp, P(_Stats)]),
-        "mipcu_solve_lp_batch": (C.c_int, [vp, i32, vp, vp, P(_Stats), vp]),
+        "mipcu_solve_lp_batch": (C.c_int, [vp, i32, vp, vp, vp, P(_Stats), vp]),
         "mipcu_get_x": (C.c_int, [vp, vp]),
         "mipcu_get_y": (C.c_int, [vp, vp]),
         "mipcu_spmv": (C.c_int, [vp, C.c_int, vp, vp]),
@@ -229,13 +229,14 @@ class Engine:
         self._check(self.lib.mipcu_solve_lp(self.h, C.byref(s)))
         return Stats.from_c(s)
 
-    def solve_batch(self, lb, ub, want_x=True):
+    def solve_batch(self, lb, ub, cutoff=None, want_x=True):
         lb = np.ascontiguousarray(lb, dtype=np.float64)
         ub = np.ascontiguousarray(ub, dtype=np.float64)
         B = lb.shape[0]
+        cutoff = None if cutoff is None else _f64(cutoff, B)
         stats = (_Stats * B)()
         x = np.empty((B, self.n)) if want_x else None
-        self._check(self.lib.mipcu_solve_lp_batch(self.h, B, _ptr(lb), _ptr(ub), stats, _ptr(x)))
+        self._check(self.lib.mipcu_solve_lp_batch(self.h, B, _ptr(lb), _ptr(ub), _ptr(cutoff), stats, _ptr(x)))
         return [Stats.from_c(s) for s in stats], x
 
     def x(self):

@@ -15,8 +15,8 @@ void dist_unique_id(void* out);
 void dist_init(mipcu_ctx* ctx, int rank, int world, const void* unique_id);
 void dist_destroy(mipcu_ctx* ctx);
 // batch.cu
-void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* ub, mipcu_stats* out,
-                    double* x_out);
+void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* ub, const double* cutoff,
+                    mipcu_stats* out, double* x_out);
 }  // namespace mipcu
 
 namespace {
@@ -223,9 +223,9 @@ int mipcu_solve_lp(mipcu_ctx* ctx, mipcu_stats* out) {
 }
 
 int mipcu_solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* ub,
-                         mipcu_stats* out, double* x_out) {
+                         const double* cutoff, mipcu_stats* out, double* x_out) {
   if (!ctx) return 1;
-  return guarded(ctx, [&] { solve_lp_batch(ctx, B, lb, ub, out, x_out); });
+  return guarded(ctx, [&] { solve_lp_batch(ctx, B, lb, ub, cutoff, out, x_out); });
 }
 
 int mipcu_get_x(mipcu_ctx* ctx, double* x) {

@@ -1,10 +1,477 @@
-// batch.cu - batched node-LP relaxations sharing one matrix.
+// batch.cu - B node-LP relaxations that share K, c and the row sides and differ only in their
+// column boxes (branch and bound), solved together (SURVEY.md section 2.2 "spmm_csr_batch +
+// batched step kernels", section 8e).
+//
+// Layout: every iterate vector is stored [n][BP] / [m][BP] with the batch index fastest
+// (BP = B rounded up to 32).  A warp owns one matrix row and its 32 lanes are 32 LPs: the
+// (val, idx) pair of a nonzero is loaded once (warp-uniform) and used by 32 problems, and the
+// gather `xbar[col][b .. b+32)` is one contiguous 256-byte segment - two full lines per nonzero
+// for 32 problems instead of one line per problem as in the single-LP kernels, which is what
+// makes node LPs cheap.  There is no sub-warp reduction at all: a lane accumulates its own row
+// sum.  Every LP keeps its own control block (restart schedule, primal weight, done flag), the
+// same arithmetic as kernels.cuh / solve.cu, one lane per problem.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <vector>
+
 #include "internal.h"
+#include "kernels.cuh"
 
 namespace mipcu {
 
-void solve_lp_batch(mipcu_ctx*, int32_t, const double*, const double*, mipcu_stats*, double*) {
-  throw Error("mipcu_solve_lp_batch is not built yet");
+namespace {
+
+constexpr int kRowsPerCtaB = 64;          // rows per CTA: 8 warps x 8 rows
+constexpr int kWarps = kThreads / 32;
+
+inline int grid_for(int64_t n, int per_block = kThreads) {
+  return (int)((n + per_block - 1) / per_block);
+}
+
+struct BatchArgs {
+  // K by rows and by columns (shared by all LPs)
+  const int *rptr, *ridx, *cptr, *cidx;
+  const double *rval, *cval;
+  const double *lo, *hi, *c, *d1, *d2;      // shared, scaled (d1, d2: the scalings)
+  const double *l, *u;                      // [n][BP] scaled boxes
+  double *xbar, *x0, *aty, *aty0, *xhat_first, *xhat_chk, *aty_cand;   // [n][BP]
+  double *y, *y0, *yhat;                                              // [m][BP]
+  Scalars* sc;                              // [BP]
+  double* partials;                         // [Q_COUNT][nblk_max][BP]
+  int m, n, BP, nblk_max;
+};
+
+// warp-uniform row of the shared matrix times 32 problems' vectors
+__device__ __forceinline__ double row_dot_batch(const int* __restrict__ ptr, const int* __restrict__ idx,
+                                                const double* __restrict__ val,
+                                                const double* __restrict__ vec, int row, int BP, int b) {
+  const int beg = ptr[row], end = ptr[row + 1];
+  double acc0 = 0.0, acc1 = 0.0;
+  int k = beg;
+  for (; k + 1 < end; k += 2) {
+    const double v0 = val[k], v1 = val[k + 1];
+    const int c0 = idx[k], c1 = idx[k + 1];
+    acc0 = fma(v0, vec[(size_t)c0 * BP + b], acc0);
+    acc1 = fma(v1, vec[(size_t)c1 * BP + b], acc1);
+  }
+  if (k < end) acc0 = fma(val[k], vec[(size_t)idx[k] * BP + b], acc0);
+  return acc0 + acc1;
+}
+
+template <int NQ>
+__device__ __forceinline__ void batch_reduce_store(double (&red)[NQ], const int (&q)[NQ], const BatchArgs& a,
+                                                   int b) {
+  __shared__ double s_red[NQ][kWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) s_red[i][warp][lane] = red[i];
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) t += s_red[i][w][lane];
+      a.partials[((size_t)q[i] * a.nblk_max + blockIdx.x) * a.BP + b] = t;
+    }
+  }
+}
+
+template <bool CHECK>
+__global__ void __launch_bounds__(kThreads) k_row_step_batch(const BatchArgs a, int iter_in_block) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y * 32 + lane;
+  const Scalars* sc = a.sc + b;
+  const bool active = !sc->done;
+  const double sigma = sc->sigma;
+  const double k = (double)(sc->k_base + iter_in_block);
+  const double w_new = (k + 1.0) / (k + 2.0);
+  double red[3] = {0.0, 0.0, 0.0};
+  if (__any_sync(0xffffffffu, active)) {
+    for (int i = 0; i < kRowsPerCtaB / kWarps; ++i) {
+      const int row = blockIdx.x * kRowsPerCtaB + warp * (kRowsPerCtaB / kWarps) + i;
+      if (row >= a.m) break;
+      const double kx = row_dot_batch(a.rptr, a.ridx, a.rval, a.xbar, row, a.BP, b);
+      if (!active) continue;
+      const size_t e = (size_t)row * a.BP + b;
+      const double yi = a.y[e], y0i = a.y0[e], lo = a.lo[row], hi = a.hi[row];
+      const double t = kx - yi / sigma;
+      const double yh = sigma * (clampd(t, lo, hi) - t);
+      a.yhat[e] = yh;
+      a.y[e] = w_new * (2.0 * yh - yi) + (1.0 - w_new) * y0i;
+      if (CHECK) {
+        const double dy = yh - yi, d0 = yh - y0i;
+        red[0] += dy * dy;
+        red[1] += d0 * d0;
+        red[2] += (isfinite(lo) ? lo * fmax(yh, 0.0) : 0.0) - (isfinite(hi) ? hi * fmax(-yh, 0.0) : 0.0);
+      }
+    }
+  }
+  if (CHECK) {
+    const int q[3] = {Q_DY2, Q_DY0, Q_DOBJ_ROW};
+    batch_reduce_store<3>(red, q, a, b);
+  }
+}
+
+template <bool CHECK, bool STORE>
+__global__ void __launch_bounds__(kThreads)
+k_col_step_batch(const BatchArgs a, int iter_in_block, const double* xhat_in, double* xhat_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y * 32 + lane;
+  const Scalars* sc = a.sc + b;
+  const bool active = !sc->done;
+  const double tau = sc->tau;
+  const double k = (double)(sc->k_base + iter_in_block);
+  const double w_new = (k + 1.0) / (k + 2.0);
+  double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (__any_sync(0xffffffffu, active)) {
+    for (int i = 0; i < kRowsPerCtaB / kWarps; ++i) {
+      const int j = blockIdx.x * kRowsPerCtaB + warp * (kRowsPerCtaB / kWarps) + i;
+      if (j >= a.n) break;
+      const double atyh = row_dot_batch(a.cptr, a.cidx, a.cval, a.yhat, j, a.BP, b);
+      if (!active) continue;
+      const size_t e = (size_t)j * a.BP + b;
+      const double xb = a.xbar[e], x0 = a.x0[e], at = a.aty[e], at0 = a.aty0[e];
+      const double cj = a.c[j], lj = a.l[e], uj = a.u[e];
+      if (CHECK) {
+        const double xh = xhat_in[e];
+        const double dx = xb - xh, dat = atyh - at, d0 = xh - x0;
+        red[0] += dx * dx;
+        red[1] += dx * dat;
+        red[2] += d0 * d0;
+        const double r = cj - atyh;
+        const double rp = fmax(r, 0.0), rm = fmax(-r, 0.0);
+        const double viol = ((isfinite(lj) ? 0.0 : rp) + (isfinite(uj) ? 0.0 : rm)) / a.d2[j];
+        red[3] += viol * viol;
+        red[4] += cj * xh;
+        red[5] += (isfinite(lj) ? lj * rp : 0.0) - (isfinite(uj) ? uj * rm : 0.0);
+        a.aty_cand[e] = atyh;
+      }
+      const double xn = w_new * xb + (1.0 - w_new) * x0;
+      const double atn = w_new * (2.0 * atyh - at) + (1.0 - w_new) * at0;
+      const double xh2 = clampd(xn - tau * (cj - atn), lj, uj);
+      a.xbar[e] = 2.0 * xh2 - xn;
+      a.aty[e] = atn;
+      if (STORE) xhat_out[e] = xh2;
+    }
+  }
+  if (CHECK) {
+    const int q[6] = {Q_DX2, Q_DXDATY, Q_DX0, Q_DRES2, Q_POBJ, Q_DOBJ_COL};
+    batch_reduce_store<6>(red, q, a, b);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_kkt_row_batch(const BatchArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y * 32 + lane;
+  const bool active = !a.sc[b].done;
+  double red[1] = {0.0};
+  if (__any_sync(0xffffffffu, active)) {
+    for (int i = 0; i < kRowsPerCtaB / kWarps; ++i) {
+      const int row = blockIdx.x * kRowsPerCtaB + warp * (kRowsPerCtaB / kWarps) + i;
+      if (row >= a.m) break;
+      const double kx = row_dot_batch(a.rptr, a.ridx, a.rval, a.xhat_chk, row, a.BP, b);
+      const double v = (kx - clampd(kx, a.lo[row], a.hi[row])) / a.d1[row];
+      red[0] += v * v;
+    }
+  }
+  const int q[1] = {Q_PRES2};
+  batch_reduce_store<1>(red, q, a, b);
+}
+
+// sum over CTAs of one quantity for the 32 problems of this chunk (lane = problem)
+__device__ double batch_sum(const BatchArgs& a, int q, int nblk, int b) {
+  __shared__ double s[kWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double t = 0.0;
+  for (int blk = warp; blk < nblk; blk += kWarps) t += a.partials[((size_t)q * a.nblk_max + blk) * a.BP + b];
+  s[warp][lane] = t;
+  __syncthreads();
+  double r = 0.0;
+  for (int w = 0; w < kWarps; ++w) r += s[w][lane];
+  __syncthreads();
+  return r;
+}
+
+__device__ double fp_error(const Scalars* sc, double dx2, double dxdaty, double dy2) {
+  return sqrt(fmax((sc->w / sc->eta) * dx2 - 2.0 * dxdaty + dy2 / (sc->eta * sc->w), 0.0));
+}
+
+__global__ void __launch_bounds__(kThreads) k_ctrl_first_batch(const BatchArgs a, int nblk_row, int nblk_col) {
+  const int b = blockIdx.x * 32 + (threadIdx.x & 31);
+  const double dy2 = batch_sum(a, Q_DY2, nblk_row, b);
+  const double dx2 = batch_sum(a, Q_DX2, nblk_col, b);
+  const double dxd = batch_sum(a, Q_DXDATY, nblk_col, b);
+  Scalars* sc = a.sc + b;
+  if (threadIdx.x < 32 && !sc->done && sc->k_base == 0) {
+    const double fp = fp_error(sc, dx2, dxd, dy2);
+    sc->fp0 = fp;
+    sc->fp_prev = fp;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_ctrl_check_batch(const BatchArgs a, int nblk_row, int nblk_col) {
+  const int b = blockIdx.x * 32 + (threadIdx.x & 31);
+  double q[Q_COUNT];
+  for (int i = 0; i < Q_COUNT; ++i) {
+    const bool is_row = (i == Q_DY2 || i == Q_DY0 || i == Q_DOBJ_ROW || i == Q_PRES2);
+    q[i] = batch_sum(a, i, is_row ? nblk_row : nblk_col, b);
+  }
+  Scalars* sc = a.sc + b;
+  if (threadIdx.x >= 32 || sc->done) return;
+  // identical to k_ctrl_check in solve.cu, one lane per problem
+  const double fp = fp_error(sc, q[Q_DX2], q[Q_DXDATY], q[Q_DY2]);
+  const double pobj = q[Q_POBJ], dobj = q[Q_DOBJ_ROW] + q[Q_DOBJ_COL];
+  sc->fp = fp;
+  sc->pobj = pobj;
+  sc->dobj = dobj;
+  sc->rel_p = sqrt(q[Q_PRES2]) / (1.0 + sc->bnorm);
+  sc->rel_d = sqrt(q[Q_DRES2]) / (1.0 + sc->cnorm);
+  sc->rel_g = fabs(pobj - dobj) / (1.0 + fabs(pobj) + fabs(dobj));
+  const long long k = sc->k_base + sc->period;
+  sc->total += sc->period;
+  sc->restart_flag = 0;
+  const double worst = fmax(sc->rel_p, fmax(sc->rel_d, sc->rel_g));
+  if (!(worst == worst) || isinf(worst)) { sc->done = 1 + MIPCU_NUMERICAL_ERROR; return; }
+  if (worst <= sc->eps) { sc->done = 1 + MIPCU_OPTIMAL; return; }
+  if (sc->rel_d <= sc->eps && dobj >= sc->cutoff) { sc->done = 1 + MIPCU_CUTOFF; return; }
+  const bool restart = fp <= BETA_SUFFICIENT * sc->fp0 ||
+                       (fp <= BETA_NECESSARY * sc->fp0 && fp > sc->fp_prev) ||
+                       (double)k >= BETA_ARTIFICIAL * (double)sc->total;
+  sc->fp_prev = fp;
+  if (restart) {
+    const double dxn = sqrt(q[Q_DX0]), dyn = sqrt(q[Q_DY0]);
+    if (dxn > WEIGHT_EPS && dyn > WEIGHT_EPS)
+      sc->w = exp(WEIGHT_SMOOTHING * log(dyn / dxn) + (1.0 - WEIGHT_SMOOTHING) * log(sc->w));
+    sc->tau = sc->eta / sc->w;
+    sc->sigma = sc->eta * sc->w;
+    sc->k_base = 0;
+    sc->restart_flag = 1;
+    sc->restarts += 1;
+  } else {
+    sc->k_base = k;
+  }
+}
+
+__global__ void k_restart_apply_batch(const BatchArgs a) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (int)(e % a.BP);
+  const Scalars* sc = a.sc + b;
+  if (sc->done || !sc->restart_flag) return;
+  const size_t row = e / a.BP;
+  if (row < (size_t)a.n) {
+    const double x = a.xhat_chk[e], at = a.aty_cand[e];
+    a.x0[e] = x;
+    a.aty0[e] = at;
+    a.aty[e] = at;
+    const double xh = clampd(x - sc->tau * (a.c[row] - at), a.l[e], a.u[e]);
+    a.xhat_first[e] = xh;
+    a.xbar[e] = 2.0 * xh - x;
+  }
+  if (row < (size_t)a.m) {
+    const double v = a.yhat[e];
+    a.y0[e] = v;
+    a.y[e] = v;
+  }
+}
+
+// boxes arrive [B][n] from the host; store them scaled and batch-fastest, pad lanes copy LP 0
+__global__ void k_load_boxes(const double* __restrict__ lb, const double* __restrict__ ub,
+                             const double* __restrict__ d2, double* __restrict__ l, double* __restrict__ u,
+                             double* __restrict__ xcand, int n, int B, int BP) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)n * BP) return;
+  const int b = (int)(e % BP), j = (int)(e / BP);
+  const int src = b < B ? b : 0;
+  double lo = lb[(size_t)src * n + j], hi = ub[(size_t)src * n + j];
+  if (lo <= -INF_THRESHOLD) lo = -INFINITY;
+  if (hi >= INF_THRESHOLD) hi = INFINITY;
+  lo /= d2[j];
+  hi /= d2[j];
+  l[e] = lo;
+  u[e] = hi;
+  xcand[e] = clampd(0.0, lo, hi);
+}
+
+__global__ void k_unscale_batch(const double* __restrict__ xhat, const double* __restrict__ d2,
+                                double* __restrict__ x_out, int n, int B, int BP) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)n * BP) return;
+  const int b = (int)(e % BP), j = (int)(e / BP);
+  if (b < B) x_out[(size_t)b * n + j] = xhat[e] * d2[j];
+}
+
+struct DeviceBuffers {
+  std::vector<void*> owned;
+  template <class T>
+  T* get(size_t count) {
+    T* p = nullptr;
+    MIPCU_CK(cudaMalloc(&p, sizeof(T) * std::max<size_t>(count, 1)));
+    owned.push_back(p);
+    return p;
+  }
+  ~DeviceBuffers() {
+    for (void* p : owned) cudaFree(p);
+  }
+};
+
+}  // namespace
+
+void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* ub, const double* cutoff,
+                    mipcu_stats* out, double* x_out) {
+  MIPCU_REQUIRE(ctx->loaded, "mipcu_solve_lp_batch: no model loaded");
+  MIPCU_REQUIRE(ctx->world <= 1, "mipcu_solve_lp_batch: node LPs are dealt to GPUs whole, not sharded");
+  MIPCU_REQUIRE(B >= 1 && lb && ub && out, "mipcu_solve_lp_batch: bad arguments");
+  MIPCU_CK(cudaSetDevice(ctx->device));
+  auto t0 = std::chrono::steady_clock::now();
+  cudaStream_t st = ctx->stream;
+  ctx->launches = 0;
+  if (!ctx->d_sc) MIPCU_CK(cudaMalloc(&ctx->d_sc, sizeof(Scalars)));
+  if (!ctx->h_sc) MIPCU_CK(cudaMallocHost(&ctx->h_sc, sizeof(Scalars) * 2));
+  for (auto& e : ctx->ev)
+    if (!e) MIPCU_CK(cudaEventCreate(&e));
+  prepare(ctx);
+  refresh_vectors(ctx);
+
+  const int n = ctx->n, m = ctx->m;
+  const int BP = (B + 31) / 32 * 32;
+  const size_t nB = (size_t)n * BP, mB = (size_t)m * BP;
+  const int nblk_row = grid_for(m, kRowsPerCtaB), nblk_col = grid_for(n, kRowsPerCtaB);
+  const int nblk_max = std::max(1, std::max(nblk_row, nblk_col));
+  const int period = (int)ctx->params[MIPCU_PARAM_CHECK_PERIOD];
+  const int64_t iter_limit = (int64_t)ctx->params[MIPCU_PARAM_ITER_LIMIT];
+  const double time_limit = ctx->params[MIPCU_PARAM_TIME_LIMIT];
+  const double sgn = ctx->maximize ? -1.0 : 1.0;
+
+  DeviceBuffers buf;
+  BatchArgs a{};
+  a.rptr = ctx->rows.ptr; a.ridx = ctx->rows.idx; a.rval = ctx->rows.val;
+  a.cptr = ctx->cols.ptr; a.cidx = ctx->cols.idx; a.cval = ctx->cols.val;
+  a.lo = ctx->los; a.hi = ctx->his; a.c = ctx->cs; a.d1 = ctx->d1; a.d2 = ctx->d2;
+  double* l = buf.get<double>(nB);
+  double* u = buf.get<double>(nB);
+  a.l = l; a.u = u;
+  a.xbar = buf.get<double>(nB); a.x0 = buf.get<double>(nB); a.aty = buf.get<double>(nB);
+  a.aty0 = buf.get<double>(nB); a.xhat_first = buf.get<double>(nB); a.xhat_chk = buf.get<double>(nB);
+  a.aty_cand = buf.get<double>(nB);
+  a.y = buf.get<double>(mB); a.y0 = buf.get<double>(mB); a.yhat = buf.get<double>(mB);
+  a.sc = buf.get<Scalars>(BP);
+  a.partials = buf.get<double>((size_t)Q_COUNT * nblk_max * BP);
+  a.m = m; a.n = n; a.BP = BP; a.nblk_max = nblk_max;
+  MIPCU_CK(cudaMemsetAsync(a.partials, 0, sizeof(double) * Q_COUNT * nblk_max * BP, st));
+
+  // boxes -> device, start point x0 = clamp(0), y0 = 0 (so K'y0 = 0: no SpMM needed to seed)
+  {
+    double* h_l = buf.get<double>((size_t)B * n);
+    double* h_u = buf.get<double>((size_t)B * n);
+    MIPCU_CK(cudaMemcpyAsync(h_l, lb, sizeof(double) * (size_t)B * n, cudaMemcpyHostToDevice, st));
+    MIPCU_CK(cudaMemcpyAsync(h_u, ub, sizeof(double) * (size_t)B * n, cudaMemcpyHostToDevice, st));
+    if (nB) {
+      k_load_boxes<<<grid_for(nB), kThreads, 0, st>>>(h_l, h_u, ctx->d2, l, u, a.xhat_chk, n, B, BP);
+      ctx->launches++;
+    }
+    MIPCU_CK(cudaMemsetAsync(a.aty_cand, 0, sizeof(double) * std::max<size_t>(nB, 1), st));
+    MIPCU_CK(cudaMemsetAsync(a.yhat, 0, sizeof(double) * std::max<size_t>(mB, 1), st));
+  }
+  std::vector<Scalars> h(BP);
+  for (int b = 0; b < BP; ++b) {
+    Scalars& s = h[b];
+    s = Scalars();
+    s.eta = ctx->eta;
+    s.w = ctx->w0;
+    s.tau = s.eta / s.w;
+    s.sigma = s.eta * s.w;
+    s.eps = ctx->params[MIPCU_PARAM_EPS_REL];
+    double cut = cutoff ? cutoff[std::min(b, B - 1)] : ctx->params[MIPCU_PARAM_OBJ_CUTOFF];
+    s.cutoff = (cut == cut) ? sgn * cut : INFINITY;
+    s.bnorm = ctx->bnorm;
+    s.cnorm = ctx->cnorm;
+    s.period = period;
+    s.restart_flag = 1;
+    s.done = b < B ? 0 : 1 + MIPCU_OPTIMAL;     // pad lanes never run
+  }
+  MIPCU_CK(cudaMemcpyAsync(a.sc, h.data(), sizeof(Scalars) * BP, cudaMemcpyHostToDevice, st));
+  const dim3 grid_rows(std::max(nblk_row, 1), BP / 32), grid_cols(std::max(nblk_col, 1), BP / 32);
+  const int grid_elem = grid_for(std::max(nB, mB));
+  if (grid_elem) {
+    k_restart_apply_batch<<<grid_elem, kThreads, 0, st>>>(a);
+    ctx->launches++;
+  }
+
+  auto enqueue_block = [&]() {
+    for (int i = 0; i < period; ++i) {
+      const bool first = i == 0, last = i == period - 1;
+      if (m) {
+        if (first || last) k_row_step_batch<true><<<grid_rows, kThreads, 0, st>>>(a, i);
+        else k_row_step_batch<false><<<grid_rows, kThreads, 0, st>>>(a, i);
+        ctx->launches++;
+        if (last) { k_kkt_row_batch<<<grid_rows, kThreads, 0, st>>>(a); ctx->launches++; }
+      }
+      const double* xin = first ? a.xhat_first : a.xhat_chk;
+      double* xo = last ? a.xhat_first : (i == period - 2 ? a.xhat_chk : nullptr);
+      if (n) {
+        const bool chk = first || last;
+        if (chk && xo) k_col_step_batch<true, true><<<grid_cols, kThreads, 0, st>>>(a, i, xin, xo);
+        else if (chk) k_col_step_batch<true, false><<<grid_cols, kThreads, 0, st>>>(a, i, xin, xo);
+        else if (xo) k_col_step_batch<false, true><<<grid_cols, kThreads, 0, st>>>(a, i, xin, xo);
+        else k_col_step_batch<false, false><<<grid_cols, kThreads, 0, st>>>(a, i, xin, xo);
+        ctx->launches++;
+      }
+      if (first) { k_ctrl_first_batch<<<BP / 32, kThreads, 0, st>>>(a, nblk_row, nblk_col); ctx->launches++; }
+    }
+    k_ctrl_check_batch<<<BP / 32, kThreads, 0, st>>>(a, nblk_row, nblk_col);
+    ctx->launches++;
+    if (grid_elem) { k_restart_apply_batch<<<grid_elem, kThreads, 0, st>>>(a); ctx->launches++; }
+  };
+
+  cudaEvent_t ev_begin = ctx->ev[0], ev_end = ctx->ev[1];
+  MIPCU_CK(cudaEventRecord(ev_begin, st));
+  int64_t total = 0;
+  bool timed_out = false;
+  while (true) {
+    enqueue_block();
+    total += period;
+    MIPCU_CK(cudaMemcpyAsync(h.data(), a.sc, sizeof(Scalars) * BP, cudaMemcpyDeviceToHost, st));
+    MIPCU_CK(cudaStreamSynchronize(st));
+    bool all_done = true;
+    for (int b = 0; b < B; ++b) all_done = all_done && h[b].done;
+    if (all_done || total >= iter_limit) break;
+    if (time_limit > 0.0 &&
+        std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > time_limit) {
+      timed_out = true;
+      break;
+    }
+  }
+  MIPCU_CK(cudaEventRecord(ev_end, st));
+  if (x_out && nB) {
+    double* d_x = buf.get<double>((size_t)B * n);
+    k_unscale_batch<<<grid_for(nB), kThreads, 0, st>>>(a.xhat_chk, ctx->d2, d_x, n, B, BP);
+    ctx->launches++;
+    MIPCU_CK(cudaMemcpyAsync(x_out, d_x, sizeof(double) * (size_t)B * n, cudaMemcpyDeviceToHost, st));
+  }
+  MIPCU_CK(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  MIPCU_CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  for (int b = 0; b < B; ++b) {
+    const Scalars& s = h[b];
+    mipcu_stats& o = out[b];
+    o = mipcu_stats();
+    o.status = s.done ? s.done - 1 : (timed_out ? MIPCU_TIME_LIMIT : MIPCU_ITERATION_LIMIT);
+    o.restarts = s.restarts;
+    o.iterations = s.total;
+    o.kernel_launches = ctx->launches;      // of the whole batch call
+    o.primal_obj = sgn * s.pobj;
+    o.dual_obj = sgn * s.dobj;
+    o.rel_primal_res = s.rel_p;
+    o.rel_dual_res = s.rel_d;
+    o.rel_gap = s.rel_g;
+    o.step_size = ctx->eta;
+    o.primal_weight = s.w;
+    o.solve_seconds = secs;
+    o.iter_seconds = 1e-3 * ms;
+  }
 }
 
 }  // namespace mipcu
