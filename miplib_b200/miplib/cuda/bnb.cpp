@@ -9,6 +9,8 @@
 #include <limits>
 #include <queue>
 #include <stdexcept>
+#include <string>
+#include <thread>
 
 #include <mipcu.h>
 
@@ -214,25 +216,6 @@ void CudaBranchAndBound::try_roundings(std::vector<double> const& x, std::vector
   }
 }
 
-void CudaBranchAndBound::push_device_bounds(std::vector<double> const& lb, std::vector<double> const& ub)
-{
-  double const inf = S.infinity();
-  std::vector<std::int64_t> cols;
-  std::vector<double> nl, nu;
-  for (std::size_t j = 0; j < n; ++j)
-    if (lb[j] != dev_lb[j] || ub[j] != dev_ub[j])
-    {
-      cols.push_back(static_cast<std::int64_t>(j));
-      nl.push_back(std::isinf(lb[j]) ? -inf : lb[j]);
-      nu.push_back(std::isinf(ub[j]) ? inf : ub[j]);
-      dev_lb[j] = lb[j];
-      dev_ub[j] = ub[j];
-    }
-  if (!cols.empty())
-    check(S.m_ctx, mipcu_set_bounds(S.m_ctx, static_cast<std::int64_t>(cols.size()), cols.data(),
-                                    nl.data(), nu.data()));
-}
-
 std::pair<Solver::Result, bool> CudaBranchAndBound::run()
 {
   using R = Solver::Result;
@@ -292,20 +275,17 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
     return finish(true);
   }
 
-  // device model at the root box
+  // device model(s): the primary context plus one per extra GPU asked for with set_nr_threads
   bool const user_verbose = S.m_verbose;
   S.upload_model();
-  dev_lb.assign(n, 0);
-  dev_ub.assign(n, 0);
-  for (std::size_t j = 0; j < n; ++j)
+  std::vector<mipcu_ctx*> gpus = S.node_contexts();
+  for (mipcu_ctx* ctx : gpus)
   {
-    dev_lb[j] = S.m_columns[j].lb <= -inf ? -kInf : S.m_columns[j].lb;
-    dev_ub[j] = S.m_columns[j].ub >= inf ? kInf : S.m_columns[j].ub;
+    check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_EPS_REL, S.m_feas_tol));
+    check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_VERBOSE, 0));
+    check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_ITER_LIMIT, 100000));
+    check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_OBJ_CUTOFF, std::nan("")));
   }
-  mipcu_ctx* ctx = S.m_ctx;
-  check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_EPS_REL, S.m_feas_tol));
-  check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_VERBOSE, 0));
-  check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_ITER_LIMIT, 200000));
 
   // no feasible point of the box can cost more than this: a dual bound above it proves the
   // node LP infeasible (PDHG's dual iterate diverges on infeasible problems)
@@ -327,10 +307,14 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
   std::priority_queue<Node, std::vector<Node>, decltype(by_bound)> open(by_bound);
   open.push(Node{{}, -kInf, 0, {}, {}});
   bool complete = true;
-  std::int64_t const node_limit = 2000000;
-  bool const keep_warm = n + m <= 400000;
+  std::int64_t const node_limit = 4000000;
+  std::size_t const per_gpu = 128;                       // node LPs per GPU per round
+  std::size_t const round_cap = per_gpu * gpus.size();
 
-  std::vector<double> lb, ub, x, y;
+  struct Pending { Node node; std::vector<double> lb, ub; double cut; };
+  std::vector<Pending> round;
+  std::vector<double> box_lb, box_ub, cuts, xs;
+  std::vector<mipcu_stats> stats;
   while (!open.empty())
   {
     if ((S.m_time_limit > 0 && elapsed() > S.m_time_limit) || S.m_info.nodes >= node_limit)
@@ -338,102 +322,133 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
       complete = false;
       break;
     }
-    Node node = open.top();
-    open.pop();
-    if (node.bound >= cutoff()) continue;          // best-first: everything left is no better
-    S.m_info.nodes += 1;
-
-    lb = root_lb;
-    ub = root_ub;
-    for (Change const& c : node.changes) { lb[c.col] = c.lb; ub[c.col] = c.ub; }
-    if (!propagate(lb, ub)) continue;
-    if (all_fixed(lb, ub))
+    // ---- a round: the best open nodes, tightened on the host, the survivors solved together ----
+    round.clear();
+    while (!open.empty() && round.size() < round_cap)
     {
-      try_incumbent(lb);
-      continue;
-    }
-
-    push_device_bounds(lb, ub);
-    double const umax = box_objective_max(lb, ub);
-    double cut = std::min(cutoff(), std::isinf(umax) ? kInf : umax + 1e-6 * (1.0 + std::abs(umax)));
-    check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_OBJ_CUTOFF, std::isinf(cut) ? std::nan("") : sgn * cut));
-    if (S.m_time_limit > 0)
-      check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_TIME_LIMIT, std::max(0.01, S.m_time_limit - elapsed())));
-    bool const warm = !node.x.empty();
-    if (warm)
-    {
-      // the parent's point, moved into the child's box
-      for (std::size_t j = 0; j < n; ++j) node.x[j] = std::min(std::max(node.x[j], lb[j]), ub[j]);
-      check(ctx, mipcu_warm_start(ctx, node.x.data(), node.y.empty() ? nullptr : node.y.data()));
-    }
-    else
-      check(ctx, mipcu_warm_start(ctx, nullptr, nullptr));
-    CudaSolver::LpOutcome const lp = S.solve_lp_on_device(&x, keep_warm ? &y : nullptr);
-    if (user_verbose)
-      std::cerr << "[miplib cuda b&b] node " << S.m_info.nodes << " depth " << node.depth << " open "
-                << open.size() << " lp status " << lp.status << " iters " << lp.iterations << " dual "
-                << lp.dual_obj << " incumbent " << (have_incumbent ? sgn * best : std::nan("")) << "\n";
-
-    if (lp.status == MIPCU_CUTOFF) continue;       // bound (or infeasibility) proven by the dual
-    if (lp.status == MIPCU_NUMERICAL_ERROR) { complete = false; continue; }
-    double node_bound = node.bound;
-    if (lp.status == MIPCU_OPTIMAL)
-    {
-      double const d = sgn * lp.dual_obj;
-      node_bound = std::max(node_bound, d - 1e-6 * (1.0 + std::abs(d)));
-      if (objective_integral) node_bound = std::ceil(node_bound - 1e-9);
-      try_roundings(x, lb, ub);
-      if (node_bound >= cutoff()) continue;
-    }
-    else if (lp.status == MIPCU_TIME_LIMIT)
-    {
-      complete = false;
-      break;
-    }
-    // branching column: the most fractional integer column of the LP point
-    std::int32_t pick = -1;
-    double worst = S.m_int_tol;
-    for (std::size_t j = 0; j < n; ++j)
-      if (is_int[j] && lb[j] < ub[j])
+      Node node = open.top();
+      open.pop();
+      if (node.bound >= cutoff()) continue;            // best-first: cannot improve the incumbent
+      S.m_info.nodes += 1;
+      Pending p{std::move(node), root_lb, root_ub, kInf};
+      for (Change const& c : p.node.changes) { p.lb[c.col] = c.lb; p.ub[c.col] = c.ub; }
+      if (!propagate(p.lb, p.ub)) continue;
+      if (all_fixed(p.lb, p.ub))
       {
-        double const f = std::abs(x[j] - std::round(x[j]));
-        if (f > worst) { worst = f; pick = static_cast<std::int32_t>(j); }
+        try_incumbent(p.lb);
+        continue;
       }
-    if (pick < 0)
+      round.push_back(std::move(p));
+    }
+    if (round.empty()) continue;
+    std::size_t const B = round.size();
+    box_lb.resize(B * n);
+    box_ub.resize(B * n);
+    cuts.resize(B);
+    stats.assign(B, mipcu_stats{});
+    xs.resize(B * n);
+    for (std::size_t b = 0; b < B; ++b)
     {
+      double const umax = box_objective_max(round[b].lb, round[b].ub);
+      double const cut = std::min(cutoff(), std::isinf(umax) ? kInf : umax + 1e-6 * (1.0 + std::abs(umax)));
+      cuts[b] = std::isinf(cut) ? std::nan("") : sgn * cut;
+      for (std::size_t j = 0; j < n; ++j)
+      {
+        box_lb[b * n + j] = std::isinf(round[b].lb[j]) ? -inf : round[b].lb[j];
+        box_ub[b * n + j] = std::isinf(round[b].ub[j]) ? inf : round[b].ub[j];
+      }
+    }
+    // deal the round to the GPUs: nodes are independent, no device-side exchange
+    {
+      std::size_t const G = std::min(gpus.size(), B);
+      std::vector<std::thread> workers;
+      std::vector<std::string> errors(G);
+      for (std::size_t g = 0; g < G; ++g)
+      {
+        std::size_t const b0 = B * g / G, b1 = B * (g + 1) / G;
+        auto job = [&, g, b0, b1]() {
+          mipcu_ctx* ctx = gpus[g];
+          if (S.m_time_limit > 0)
+            mipcu_set_param(ctx, MIPCU_PARAM_TIME_LIMIT, std::max(0.01, S.m_time_limit - elapsed()));
+          if (mipcu_solve_lp_batch(ctx, static_cast<std::int32_t>(b1 - b0), box_lb.data() + b0 * n,
+                                   box_ub.data() + b0 * n, cuts.data() + b0, stats.data() + b0,
+                                   xs.data() + b0 * n))
+            errors[g] = mipcu_last_error(ctx);
+        };
+        if (G == 1) job(); else workers.emplace_back(job);
+      }
+      for (std::thread& t : workers) t.join();
+      for (std::string const& e : errors)
+        if (!e.empty()) throw std::logic_error("Cuda backend: " + e);
+    }
+    S.m_info.lp_solves += static_cast<std::int64_t>(B);
+    S.m_info.kernel_launches += stats[0].kernel_launches;
+    if (user_verbose)
+      std::cerr << "[miplib cuda b&b] round of " << B << " node LPs, " << S.m_info.nodes << " nodes so far, "
+                << open.size() << " open, incumbent " << (have_incumbent ? sgn * best : std::nan("")) << "\n";
+
+    for (std::size_t b = 0; b < B; ++b)
+    {
+      Node const& node = round[b].node;
+      std::vector<double> const& lb = round[b].lb;
+      std::vector<double> const& ub = round[b].ub;
+      mipcu_stats const& lp = stats[b];
+      S.m_info.lp_iterations += lp.iterations;
+      std::vector<double> x(xs.begin() + b * n, xs.begin() + (b + 1) * n);
+      if (lp.status == MIPCU_CUTOFF) continue;       // bound (or infeasibility) proven by the dual
+      if (lp.status == MIPCU_NUMERICAL_ERROR) { complete = false; continue; }
+      if (lp.status == MIPCU_TIME_LIMIT) { complete = false; continue; }
+      double node_bound = node.bound;
       if (lp.status == MIPCU_OPTIMAL)
       {
-        // integral LP optimum: round the integer columns exactly; the continuous ones keep their LP value
-        std::vector<double> cand(x);
-        for (std::size_t j = 0; j < n; ++j)
-          if (is_int[j]) cand[j] = std::min(std::max(std::round(cand[j]), lb[j]), ub[j]);
-        if (!try_incumbent(cand)) complete = false;   // an integral LP point that rounding broke
+        double const d = sgn * lp.dual_obj;
+        node_bound = std::max(node_bound, d - 1e-6 * (1.0 + std::abs(d)));
+        if (objective_integral) node_bound = std::ceil(node_bound - 1e-9);
+        try_roundings(x, lb, ub);
+        if (node_bound >= cutoff()) continue;
       }
-      else
-        complete = false;                            // undecided node with nothing to branch on
-      continue;
-    }
-    double const split = std::floor(x[pick]);
-    for (int side = 0; side < 2; ++side)
-    {
-      Node child;
-      child.changes = node.changes;
-      // carry every bound propagation found, so the child starts from the tightened box
-      child.changes.clear();
+      // branching column: the most fractional integer column of the LP point
+      std::int32_t pick = -1;
+      double worst = S.m_int_tol;
       for (std::size_t j = 0; j < n; ++j)
-        if (lb[j] != root_lb[j] || ub[j] != root_ub[j])
-          child.changes.push_back({static_cast<std::int32_t>(j), lb[j], ub[j]});
-      double cl = lb[pick], cu = ub[pick];
-      if (side == 0) cu = split; else cl = split + 1;
-      if (cl > cu) continue;
-      bool found = false;
-      for (Change& c : child.changes)
-        if (c.col == pick) { c.lb = cl; c.ub = cu; found = true; }
-      if (!found) child.changes.push_back({pick, cl, cu});
-      child.bound = node_bound;
-      child.depth = node.depth + 1;
-      if (keep_warm) { child.x = x; child.y = y; }
-      open.push(std::move(child));
+        if (is_int[j] && lb[j] < ub[j])
+        {
+          double const f = std::abs(x[j] - std::round(x[j]));
+          if (f > worst) { worst = f; pick = static_cast<std::int32_t>(j); }
+        }
+      if (pick < 0)
+      {
+        if (lp.status == MIPCU_OPTIMAL)
+        {
+          // integral LP optimum: round the integer columns exactly; continuous ones keep their LP value
+          std::vector<double> cand(x);
+          for (std::size_t j = 0; j < n; ++j)
+            if (is_int[j]) cand[j] = std::min(std::max(std::round(cand[j]), lb[j]), ub[j]);
+          if (!try_incumbent(cand)) complete = false;   // an integral LP point that rounding broke
+        }
+        else
+          complete = false;                            // undecided node with nothing to branch on
+        continue;
+      }
+      double const split = std::floor(x[pick]);
+      for (int side = 0; side < 2; ++side)
+      {
+        Node child;
+        // carry every bound propagation found, so the child starts from the tightened box
+        for (std::size_t j = 0; j < n; ++j)
+          if (lb[j] != root_lb[j] || ub[j] != root_ub[j])
+            child.changes.push_back({static_cast<std::int32_t>(j), lb[j], ub[j]});
+        double cl = lb[pick], cu = ub[pick];
+        if (side == 0) cu = split; else cl = split + 1;
+        if (cl > cu) continue;
+        bool found = false;
+        for (Change& c : child.changes)
+          if (c.col == pick) { c.lb = cl; c.ub = cu; found = true; }
+        if (!found) child.changes.push_back({pick, cl, cu});
+        child.bound = node_bound;
+        child.depth = node.depth + 1;
+        open.push(std::move(child));
+      }
     }
   }
   S.m_info.best_bound = have_incumbent ? sgn * best : 0;

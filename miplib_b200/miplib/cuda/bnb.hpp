@@ -38,7 +38,6 @@ struct CudaBranchAndBound
   bool try_incumbent(std::vector<double> const& x);   // false: x violates a row
   void try_roundings(std::vector<double> const& x, std::vector<double> const& lb,
                      std::vector<double> const& ub);
-  void push_device_bounds(std::vector<double> const& lb, std::vector<double> const& ub);
   double cutoff() const;           // nodes whose bound reaches this cannot improve the incumbent
 
   CudaSolver& S;
@@ -49,7 +48,6 @@ struct CudaBranchAndBound
   std::vector<double> rval, cval, rlo, rhi, cost;
   std::vector<char> is_int;
   bool pure_integer = true, objective_integral = true;
-  std::vector<double> dev_lb, dev_ub;
   double best = 0;
   bool have_incumbent = false;
   std::vector<double> best_x;

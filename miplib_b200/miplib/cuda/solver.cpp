@@ -46,6 +46,7 @@ CudaSolver::CudaSolver(bool verbose) : m_verbose(verbose) {}
 
 CudaSolver::~CudaSolver()
 {
+  for (mipcu_ctx* ctx : m_extra_ctx) mipcu_destroy(ctx);
   if (m_ctx) mipcu_destroy(m_ctx);
 }
 
@@ -350,6 +351,11 @@ void CudaSolver::upload_model()
     check(m_ctx, mipcu_load_lp(m_ctx, static_cast<std::int64_t>(lo.size()), static_cast<std::int64_t>(n),
                                static_cast<std::int64_t>(idx.size()), ptr.data(), idx.data(), val.data(),
                                m_objective.data(), lb.data(), ub.data(), lo.data(), hi.data(), maximize));
+    m_last_ptr.swap(ptr);
+    m_last_idx.swap(idx);
+    m_last_val.swap(val);
+    m_last_lo.swap(lo);
+    m_last_hi.swap(hi);
     m_structure_dirty = false;
     m_objective_dirty = false;
     m_dirty_columns.clear();
@@ -374,6 +380,38 @@ void CudaSolver::upload_model()
                                   m_dirty_columns.data(), lb.data(), ub.data()));
     m_dirty_columns.clear();
   }
+}
+
+// Contexts that take node LPs of a branch-and-bound round: the primary one plus a copy of the
+// model on every extra GPU requested with set_nr_threads (nodes are
+// independent, the host deals them out, nothing is exchanged on the device).
+std::vector<mipcu_ctx*> CudaSolver::node_contexts()
+{
+  std::vector<mipcu_ctx*> all{m_ctx};
+  std::size_t const want = std::min<std::size_t>(m_nr_gpus, static_cast<std::size_t>(mipcu_device_count()));
+  std::size_t const n = m_columns.size();
+  std::vector<double> lb(n), ub(n);
+  for (std::size_t j = 0; j < n; ++j)
+  {
+    lb[j] = m_columns[j].lb;
+    ub[j] = m_columns[j].ub;
+  }
+  for (std::size_t g = 1; g < want; ++g)
+  {
+    if (m_extra_ctx.size() < g)
+    {
+      mipcu_ctx* ctx = nullptr;
+      if (mipcu_create(&ctx, static_cast<int>(g))) fail(std::string("Cuda backend: ") + mipcu_last_error(nullptr));
+      m_extra_ctx.push_back(ctx);
+    }
+    mipcu_ctx* ctx = m_extra_ctx[g - 1];
+    check(ctx, mipcu_load_lp(ctx, static_cast<std::int64_t>(m_last_lo.size()), static_cast<std::int64_t>(n),
+                             static_cast<std::int64_t>(m_last_idx.size()), m_last_ptr.data(), m_last_idx.data(),
+                             m_last_val.data(), m_objective.data(), lb.data(), ub.data(), m_last_lo.data(),
+                             m_last_hi.data(), m_sense == Solver::Sense::Maximize));
+    all.push_back(ctx);
+  }
+  return all;
 }
 
 CudaSolver::LpOutcome CudaSolver::solve_lp_on_device(std::vector<double>* x_out, std::vector<double>* y_out)

@@ -111,6 +111,7 @@ struct CudaSolver : detail::ISolver
   private:
   friend struct CudaBranchAndBound;
   void ensure_context();
+  std::vector<mipcu_ctx*> node_contexts();   // primary + one loaded copy per extra GPU (B&B rounds)
   void upload_model();
   struct LpOutcome
   {
@@ -124,6 +125,10 @@ struct CudaSolver : detail::ISolver
   std::size_t column_of(Var const& v) const;
 
   mipcu_ctx* m_ctx = nullptr;
+  std::vector<mipcu_ctx*> m_extra_ctx;           // devices 1.. for dealing node LPs (set_nr_threads)
+  std::vector<std::int64_t> m_last_ptr;          // last uploaded CSR, kept to load the extra GPUs
+  std::vector<std::int32_t> m_last_idx;
+  std::vector<double> m_last_val, m_last_lo, m_last_hi;
   bool m_verbose;
   bool m_structure_dirty = true, m_objective_dirty = true;
   std::vector<std::int64_t> m_dirty_columns;

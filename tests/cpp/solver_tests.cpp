@@ -4,8 +4,10 @@
 // exact-solver goldens cover.  Integer columns come back exactly integral (the incumbent is
 // rounded and re-verified on the host), so the reference's `==` holds for them; continuous columns
 // of a first-order LP solve are compared with the tolerance north_star states (1e-6 relative).
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <iostream>
 #include <fstream>
 #include <random>
 #include <string>
@@ -185,9 +187,12 @@ GPU_TEST("Generated models through the expression API match the exact-solver gol
     int maximize;
     double expected, tol;
     in >> maximize >> expected >> tol;
+    auto const t_begin = std::chrono::steady_clock::now();
     auto [r, has_solution] = maximize ? solver.maximize(objective) : solver.minimize(objective);
+    double const secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
     std::cout << "  " << label << ": result " << static_cast<int>(r) << " objective "
-              << (has_solution ? solver.get_objective_value() : NAN) << " expected " << expected << "\n";
+              << (has_solution ? solver.get_objective_value() : NAN) << " expected " << expected
+              << " in " << secs << " s" << std::endl;
     REQUIRE(r == Solver::Result::Optimal && has_solution);
     REQUIRE(std::abs(solver.get_objective_value() - expected) <= tol * (1 + std::abs(expected)));
     REQUIRE(close(objective.value(), solver.get_objective_value(), 1e-9));
