@@ -187,6 +187,7 @@ GPU_TEST("Generated models through the expression API match the exact-solver gol
     int maximize;
     double expected, tol;
     in >> maximize >> expected >> tol;
+    solver.set_time_limit(150);   // a runaway tree must fail the test, not hang it
     auto const t_begin = std::chrono::steady_clock::now();
     auto [r, has_solution] = maximize ? solver.maximize(objective) : solver.minimize(objective);
     double const secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
