@@ -51,6 +51,7 @@ void set_default_params(mipcu_ctx* ctx) {
   ctx->params[MIPCU_PARAM_SCALING] = 1;
   ctx->params[MIPCU_PARAM_THREADS_PER_ROW] = 0;
   ctx->params[MIPCU_PARAM_OBJ_CUTOFF] = NAN;
+  ctx->params[MIPCU_PARAM_USE_TMA] = -1;
 }
 
 mipcu_ctx* create_on(int device) {
@@ -68,6 +69,7 @@ mipcu_ctx* create_on(int device) {
   MIPCU_CK(cudaSetDevice(device));
   mipcu_ctx* ctx = new mipcu_ctx();
   ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
   set_default_params(ctx);
   try {
     MIPCU_CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -186,6 +188,7 @@ int mipcu_set_param(mipcu_ctx* ctx, int key, double value) {
     if ((key == MIPCU_PARAM_SCALING || key == MIPCU_PARAM_STEP_SIZE) && ctx->prepared)
       throw Error("scaling / step size must be set before the first solve of a loaded model");
     ctx->params[key] = value;
+    if (key == MIPCU_PARAM_USE_TMA && ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
     if (key == MIPCU_PARAM_THREADS_PER_ROW && ctx->loaded) {
       int o = (int)value;
       ctx->rows.tpr = choose_tpr(ctx->m ? (double)ctx->nnz / ctx->m : 0.0, o);

@@ -43,6 +43,7 @@ struct Csr {
   int* idx = nullptr;      // nnz (+ padding)
   double* val = nullptr;   // nnz (+ padding)
   int tpr = 8;             // threads per row chosen for this matrix
+  int tile_cap = 0;        // TMA kernels: entries one 64-row tile needs in shared memory (0: n/a)
 };
 
 // Quantities reduced per CTA on check iterations: partials[q * max_blocks + blockIdx.x].
@@ -84,6 +85,7 @@ struct Scalars {
 struct mipcu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  int sm_count = 148;
   std::string err;
   double params[MIPCU_PARAM_COUNT_];
 

@@ -270,6 +270,30 @@ void build_transpose(mipcu_ctx* ctx, const Csr& A, Csr& T) {
   dfree(row_of); dfree(pos); dfree(keys_out); dfree(perm); dfree(counts);
 }
 
+// entries a 64-row tile of A occupies in the TMA kernels' shared-memory stage (its nonzeros plus the
+// slack of aligning the slice to 16 bytes), maximised over the tiles
+__global__ void k_tile_max(const int* __restrict__ ptr, int nrows, int* out) {
+  const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r0 = tile * 64;
+  if (r0 >= nrows) return;
+  const int r1 = min(r0 + 64, nrows);
+  const int kb = ptr[r0] & ~3;
+  atomicMax(out, ((ptr[r1] - kb) + 3) & ~3);
+}
+
+int tile_capacity(mipcu_ctx* ctx, const Csr& A) {
+  if (A.nrows == 0) return 0;
+  int* d = dalloc<int>(1);
+  MIPCU_CK(cudaMemsetAsync(d, 0, sizeof(int), ctx->stream));
+  k_tile_max<<<grid_for(grid_for(A.nrows, 64)), kThreads, 0, ctx->stream>>>(A.ptr, A.nrows, d);
+  ctx->launches++;
+  int h = 0;
+  MIPCU_CK(cudaMemcpyAsync(&h, d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  MIPCU_CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d);
+  return std::max(h, 4);
+}
+
 void free_csr(Csr& A) {
   dfree(A.ptr); dfree(A.idx); dfree(A.val);
   A = Csr();
@@ -283,7 +307,7 @@ int choose_tpr(double avg, int override_tpr) {
     return override_tpr;
   if (avg <= 3.0) return 2;
   if (avg <= 6.0) return 4;
-  if (avg <= 24.0) return 8;
+  if (avg <= 48.0) return 8;     // measured on config 3 rows (avg 32): 8 lanes 175 us, 16 lanes 185 us
   if (avg <= 96.0) return 16;
   return 32;
 }
@@ -376,7 +400,7 @@ void load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* r
   ctx->cols.tpr = choose_tpr(n ? (double)nnz / (double)n : 0.0, tpr_override);
 
   auto upload = [&](double*& dst, const double* src, int64_t count, bool sanitize) {
-    dst = dalloc<double>(count);
+    dst = dalloc<double>(count + 2);
     if (count) {
       MIPCU_CK(cudaMemcpyAsync(dst, src, sizeof(double) * count, cudaMemcpyHostToDevice, st));
       if (sanitize) {
@@ -394,11 +418,13 @@ void load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* r
   double** nvecs[] = {&ctx->cs, &ctx->ls, &ctx->us, &ctx->d2, &ctx->xbar, &ctx->x0, &ctx->aty,
                       &ctx->aty0, &ctx->xhat_first, &ctx->xhat_chk, &ctx->aty_cand, &ctx->tmp_n,
                       &ctx->x_sol};
-  for (double** p : nvecs) *p = dalloc<double>(n);
+  for (double** p : nvecs) *p = dalloc<double>(n + 2);   // +2: TMA reads an even number of doubles
   double** mvecs[] = {&ctx->los, &ctx->his, &ctx->d1, &ctx->y, &ctx->y0, &ctx->yhat, &ctx->tmp_m,
                       &ctx->y_sol};
-  for (double** p : mvecs) *p = dalloc<double>(m);
-  ctx->max_blocks = std::max(1024, std::max(grid_for(m, kRowsPerCta), grid_for(n, kRowsPerCta)));
+  for (double** p : mvecs) *p = dalloc<double>(m + 2);
+  ctx->max_blocks = std::max(1024, std::max(grid_for(m, 64), grid_for(n, 64)));   // 64 = TMA tile rows
+  A.tile_cap = tile_capacity(ctx, A);
+  ctx->cols.tile_cap = tile_capacity(ctx, ctx->cols);
   ctx->partials = dalloc<double>((int64_t)Q_COUNT * ctx->max_blocks);
   MIPCU_CK(cudaMemsetAsync(ctx->partials, 0, sizeof(double) * Q_COUNT * ctx->max_blocks, st));
   if (n) { k_fill<<<grid_for(n), kThreads, 0, st>>>(ctx->d2, 1.0, (int)n); ctx->launches++; }

@@ -7,6 +7,7 @@
 
 #include "internal.h"
 #include "kernels.cuh"
+#include "kernels_tma.cuh"
 
 namespace mipcu {
 
@@ -187,15 +188,59 @@ ColStepArgs col_args(mipcu_ctx* ctx, int i, const double* xhat_in, double* xhat_
   return a;
 }
 
+// TMA-streamed variants are used when the matrix's 64-row tiles fit a shared-memory stage
+bool tma_usable(const mipcu_ctx* ctx, const Csr& A, int nv) {
+  // opt-in: on B200 the LSU-streamed kernels are faster on every config measured so far
+  // (profiles/r01_kernel_variants.md), so "auto" (-1) means LSU
+  const int mode = (int)ctx->params[MIPCU_PARAM_USE_TMA];
+  if (mode != 1 || A.tile_cap <= 0 || ctx->world > 1) return false;
+  return tma_smem_bytes(A.tile_cap, nv) <= 96 * 1024;   // keeps >= 2 CTAs per SM resident
+}
+
+template <class Kernel>
+int persistent_grid(mipcu_ctx* ctx, Kernel kernel, size_t smem, int ntiles) {
+  MIPCU_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  MIPCU_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
+  return std::max(1, std::min(ntiles, std::max(per_sm, 1) * ctx->sm_count));
+}
+
 template <int TPR>
 void launch_row(mipcu_ctx* ctx, const RowStepArgs& a, bool check) {
+  if (tma_usable(ctx, ctx->rows, 4)) {
+    const int cap = ctx->rows.tile_cap, ntiles = grid_for(ctx->m, kTileRows);
+    const size_t smem = tma_smem_bytes(cap, 4);
+    if (check) {
+      const int g = persistent_grid(ctx, k_row_step_tma<TPR, true>, smem, ntiles);
+      k_row_step_tma<TPR, true><<<g, kThreads, smem, ctx->stream>>>(a, cap, ntiles);
+    } else {
+      const int g = persistent_grid(ctx, k_row_step_tma<TPR, false>, smem, ntiles);
+      k_row_step_tma<TPR, false><<<g, kThreads, smem, ctx->stream>>>(a, cap, ntiles);
+    }
+    return;
+  }
   const int g = grid_for(ctx->m, kRowsPerCta);
   if (check) k_row_step<TPR, true><<<g, kThreads, 0, ctx->stream>>>(a);
   else k_row_step<TPR, false><<<g, kThreads, 0, ctx->stream>>>(a);
 }
 
+template <int TPR, bool CHECK, bool STORE>
+void launch_col_tma(mipcu_ctx* ctx, const ColStepArgs& a) {
+  const int cap = ctx->cols.tile_cap, ntiles = grid_for(ctx->n, kTileRows);
+  const size_t smem = tma_smem_bytes(cap, 7);
+  const int g = persistent_grid(ctx, k_col_step_tma<TPR, CHECK, STORE>, smem, ntiles);
+  k_col_step_tma<TPR, CHECK, STORE><<<g, kThreads, smem, ctx->stream>>>(a, cap, ntiles);
+}
+
 template <int TPR>
 void launch_col(mipcu_ctx* ctx, const ColStepArgs& a, bool check, bool store) {
+  if (tma_usable(ctx, ctx->cols, 7)) {
+    if (check && store) launch_col_tma<TPR, true, true>(ctx, a);
+    else if (check) launch_col_tma<TPR, true, false>(ctx, a);
+    else if (store) launch_col_tma<TPR, false, true>(ctx, a);
+    else launch_col_tma<TPR, false, false>(ctx, a);
+    return;
+  }
   const int g = grid_for(ctx->n, kRowsPerCta);
   cudaStream_t st = ctx->stream;
   if (check && store) k_col_step<TPR, true, true><<<g, kThreads, 0, st>>>(a);
@@ -328,8 +373,8 @@ void init_iterate(mipcu_ctx* ctx, Scalars& h) {
   h.cnorm = ctx->cnorm;
   h.period = (int)ctx->params[MIPCU_PARAM_CHECK_PERIOD];
   h.restart_flag = 1;
-  h.nblk_row = grid_for(m, kRowsPerCta);
-  h.nblk_col = grid_for(n, kRowsPerCta);
+  h.nblk_row = grid_for(m, tma_usable(ctx, ctx->rows, 4) ? kTileRows : kRowsPerCta);
+  h.nblk_col = grid_for(n, tma_usable(ctx, ctx->cols, 7) ? kTileRows : kRowsPerCta);
   h.max_blocks = ctx->max_blocks;
   MIPCU_CK(cudaMemcpyAsync(ctx->d_sc, &h, sizeof(Scalars), cudaMemcpyHostToDevice, st));
   if (nm) {

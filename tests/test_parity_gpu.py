@@ -324,3 +324,22 @@ def test_error_reporting(engine):
     assert st.status == "iteration_limit" and st.iterations == 128
     with pytest.raises(MipcuError):
         engine.set_param("check_period", 1)
+
+
+# ---- kernel variants -------------------------------------------------------------------------
+def test_tma_and_lsu_kernels_agree_bit_for_bit(engine):
+    """The TMA-streamed kernels (cp.async.bulk ring) use the same lane order as the LSU-streamed
+    ones: raw iterates are identical, whole solves agree."""
+    for L in (gen.config(1), gen.lp_fast(5000, 9000, 12, 3), gen.set_cover(400, 1000, 8, 20264)):
+        engine.load_lp(L)
+        engine.set_param("use_tma", 0)
+        xa, ya = engine.debug_iterate(50)
+        sa = engine.solve()
+        engine.set_param("use_tma", 1)
+        xb, yb = engine.debug_iterate(50)
+        sb = engine.solve()
+        engine.set_param("use_tma", -1)
+        assert np.array_equal(xa, xb) and np.array_equal(ya, yb)
+        assert sa.status == sb.status == "optimal"
+        assert rel(sa.primal_obj, sb.primal_obj) <= 1e-6
+        assert abs(sa.iterations - sb.iterations) <= 2 * 64
