@@ -57,6 +57,9 @@ miplib::Var::Type to_var_type(miplib_VarType type)
 
 }  // namespace
 
+// shared with the backend-specific C entry points (miplib/cuda/capi.cpp)
+void miplib_store_error(char const* what) { g_last_error = what; }
+
 extern "C" {
 
 char const* miplib_get_last_error() { return g_last_error.c_str(); }

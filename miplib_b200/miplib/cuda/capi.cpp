@@ -1,0 +1,76 @@
+#include "capi.hpp"
+
+#include <exception>
+#include <stdexcept>
+#include <string>
+
+#include "solver.hpp"
+
+extern void miplib_store_error(char const* what);   // capi.cpp
+
+namespace {
+
+template<class Body>
+int guarded(Body&& body) noexcept
+{
+  try
+  {
+    body();
+    return 0;
+  }
+  catch (std::exception const& e) { miplib_store_error(e.what()); }
+  catch (...) { miplib_store_error("unknown error"); }
+  return 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int miplib_cuda_load_csr(miplib::Solver* p_solver, std::int64_t m, std::int64_t n,
+                         std::int64_t const* row_ptr, std::int32_t const* col_idx, double const* val,
+                         double const* c, double const* lb, double const* ub,
+                         std::int32_t const* var_type, double const* row_lo, double const* row_hi,
+                         int maximize)
+{
+  return guarded([&] {
+    miplib::CudaSolver::of(*p_solver).load_csr(*p_solver, m, n, row_ptr, col_idx, val, c, lb, ub, var_type,
+                                               row_lo, row_hi, maximize != 0);
+  });
+}
+
+int miplib_cuda_solve(miplib::Solver* p_solver, int* result, int* has_solution)
+{
+  return guarded([&] {
+    auto const [r, has] = p_solver->solve();
+    if (result) *result = static_cast<int>(r);
+    if (has_solution) *has_solution = has ? 1 : 0;
+  });
+}
+
+int miplib_cuda_get_values(miplib::Solver* p_solver, double* x, double* objective)
+{
+  return guarded([&] {
+    miplib::CudaSolver const& s = miplib::CudaSolver::of(*p_solver);
+    if (!s.m_has_solution) throw std::logic_error("Attempt to access values before a solution was found.");
+    if (x)
+      for (std::size_t j = 0; j < s.m_solution.size(); ++j) x[j] = s.m_solution[j];
+    if (objective) *objective = s.m_objective_value;
+  });
+}
+
+int miplib_cuda_get_shape(miplib::Solver* p_solver, std::int64_t* n, std::int64_t* m)
+{
+  return guarded([&] {
+    miplib::CudaSolver const& s = miplib::CudaSolver::of(*p_solver);
+    if (n) *n = static_cast<std::int64_t>(s.m_columns.size());
+    if (m)
+    {
+      std::int64_t alive = 0;
+      for (char a : s.m_row_alive) alive += a ? 1 : 0;
+      *m = alive;
+    }
+  });
+}
+
+}

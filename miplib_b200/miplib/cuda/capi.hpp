@@ -1,0 +1,35 @@
+// miplib/cuda/capi.hpp - C entry points NEW with the Cuda backend: bulk
+// model ingress that bypasses the expression tree, plus solve / read-back, in the style of the
+// reference's miplib/capi.hpp (rc 0 / 1, message via miplib_get_last_error()).
+//
+// Why: the reference's C API stops at creating solvers and variables (miplib/capi.hpp:16-23), and
+// building a 32 M-nonzero model through Var / Expr objects costs tens of seconds and gigabytes on
+// the host before solve() is ever called (reference miplib/expr.cpp:53-119, :599-633).  These
+// calls hand CSR arrays straight to the backend's row store.
+#pragma once
+
+#include <cstdint>
+
+#include "../capi.hpp"
+
+extern "C" {
+
+// Appends n columns and m rows to a Cuda-backend solver.  col_idx counts from the first NEW column
+// and must be increasing inside a row.  var_type: miplib_VarType values as int32, or NULL for all
+// Continuous.  Bounds / row sides beyond +-1e20 mean "none".  Replaces the objective.
+int miplib_cuda_load_csr(miplib::Solver* p_solver, std::int64_t m, std::int64_t n,
+                         std::int64_t const* row_ptr, std::int32_t const* col_idx, double const* val,
+                         double const* c, double const* lb, double const* ub,
+                         std::int32_t const* var_type, double const* row_lo, double const* row_hi,
+                         int maximize);
+
+// Solver::solve(); *result receives Solver::Result as int, *has_solution 0 / 1.
+int miplib_cuda_solve(miplib::Solver* p_solver, int* result, int* has_solution);
+
+// Values of ALL columns in creation order (x may be NULL) and the objective value.
+int miplib_cuda_get_values(miplib::Solver* p_solver, double* x, double* objective);
+
+// Number of columns / alive rows of the lowered model.
+int miplib_cuda_get_shape(miplib::Solver* p_solver, std::int64_t* n, std::int64_t* m);
+
+}

@@ -189,6 +189,62 @@ void CudaSolver::set_warm_start(PartialSolution const& partial_solution)
   for (auto const& [var, value] : partial_solution) m_start_x[column_of(var)] = value;
 }
 
+// ---- bulk ingress -----------------------------------------------------------------------------------
+
+CudaSolver& CudaSolver::of(Solver const& solver)
+{
+  auto* impl = dynamic_cast<CudaSolver*>(solver.p_impl.get());
+  if (!impl) fail("This entry point needs a Solver created with Backend::Cuda.");
+  return *impl;
+}
+
+void CudaSolver::load_csr(Solver const&, std::int64_t m, std::int64_t n, std::int64_t const* row_ptr,
+                          std::int32_t const* col_idx, double const* val, double const* c,
+                          double const* lb, double const* ub, std::int32_t const* var_type,
+                          double const* row_lo, double const* row_hi, bool maximize)
+{
+  if (m < 0 || n < 0 || !row_ptr || (n > 0 && (!c || !lb || !ub)) || (m > 0 && (!row_lo || !row_hi)))
+    fail("miplib_cuda_load_csr: bad arguments");
+  if (row_ptr[0] != 0 || (row_ptr[m] > 0 && (!col_idx || !val))) fail("miplib_cuda_load_csr: bad row_ptr");
+  std::size_t const first = m_columns.size();
+  double const inf = infinity();
+  m_columns.reserve(first + static_cast<std::size_t>(n));
+  for (std::int64_t j = 0; j < n; ++j)
+  {
+    Column col;
+    int const t = var_type ? var_type[j] : 0;
+    if (t < 0 || t > 2) fail("miplib_cuda_load_csr: unknown variable type");
+    col.type = static_cast<Var::Type>(t);
+    col.lb = col.type == Var::Type::Binary ? 0.0 : std::max(lb[j], -inf);
+    col.ub = col.type == Var::Type::Binary ? 1.0 : std::min(ub[j], inf);
+    m_columns.push_back(col);
+  }
+  m_row_idx.reserve(m_row_idx.size() + static_cast<std::size_t>(row_ptr[m]));
+  m_row_val.reserve(m_row_val.size() + static_cast<std::size_t>(row_ptr[m]));
+  for (std::int64_t i = 0; i < m; ++i)
+  {
+    std::int32_t prev = -1;
+    if (row_ptr[i + 1] < row_ptr[i]) fail("miplib_cuda_load_csr: row_ptr must be non-decreasing");
+    for (std::int64_t k = row_ptr[i]; k < row_ptr[i + 1]; ++k)
+    {
+      if (col_idx[k] <= prev || col_idx[k] >= n)
+        fail("miplib_cuda_load_csr: column indices must be increasing inside a row and below n");
+      prev = col_idx[k];
+      m_row_idx.push_back(static_cast<std::int32_t>(first) + col_idx[k]);
+      m_row_val.push_back(val[k]);
+    }
+    m_row_start.push_back(static_cast<std::int64_t>(m_row_idx.size()));
+    m_row_lo.push_back(std::max(row_lo[i], -inf));
+    m_row_hi.push_back(std::min(row_hi[i], inf));
+    m_row_alive.push_back(1);
+  }
+  m_objective.assign(m_columns.size(), 0.0);
+  for (std::int64_t j = 0; j < n; ++j) m_objective[first + static_cast<std::size_t>(j)] = c[j];
+  m_sense = maximize ? Solver::Sense::Maximize : Solver::Sense::Minimize;
+  m_structure_dirty = true;
+  m_objective_dirty = true;
+}
+
 // ---- dump: free-format MPS or CPLEX-LP text of the lowered model ---------------------------------
 
 void CudaSolver::dump(std::string const& filename) const

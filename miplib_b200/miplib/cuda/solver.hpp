@@ -74,6 +74,16 @@ struct CudaSolver : detail::ISolver
   static std::string backend_info();
   static bool is_available();
 
+  // the backend object behind a facade handle (throws if the Solver uses another backend)
+  static CudaSolver& of(Solver const& solver);
+
+  // Bulk ingress: n new columns and m new rows from CSR arrays, without
+  // building Var / Expr / Constr objects.  col_idx counts from the first new column.
+  void load_csr(Solver const& solver, std::int64_t m, std::int64_t n, std::int64_t const* row_ptr,
+                std::int32_t const* col_idx, double const* val, double const* c, double const* lb,
+                double const* ub, std::int32_t const* var_type, double const* row_lo,
+                double const* row_hi, bool maximize);
+
   // ---- model store (host) --------------------------------------------------------------------
   struct Column
   {

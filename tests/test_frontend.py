@@ -76,3 +76,73 @@ def test_kats_and_generated_models_on_gpu(built, golden, tmp_path):
     print(out)
     assert rc == 0, out
     assert "0 failed" in out and "0 skipped" in out, out
+
+
+# ---- bulk ingress through the C entry points (miplib/cuda/capi.hpp) ---------------------------
+def _front(built):
+    import ctypes as C
+    lib = C.CDLL(str(built.FRONT_LIB))
+    lib.miplib_get_last_error.restype = C.c_char_p
+    return lib, C
+
+
+def _load_csr(lib, C, solver, L, types=None):
+    A = L.A.tocsr(); A.sort_indices()
+    arrs = [np.ascontiguousarray(A.indptr, dtype=np.int64), np.ascontiguousarray(A.indices, dtype=np.int32),
+            np.ascontiguousarray(A.data, dtype=np.float64), np.ascontiguousarray(L.c, dtype=np.float64),
+            np.ascontiguousarray(L.lb, dtype=np.float64), np.ascontiguousarray(L.ub, dtype=np.float64),
+            None if types is None else np.ascontiguousarray(types, dtype=np.int32),
+            np.ascontiguousarray(np.maximum(L.row_lo, -1e30), dtype=np.float64),
+            np.ascontiguousarray(np.minimum(L.row_hi, 1e30), dtype=np.float64)]
+    ptrs = [None if a is None else a.ctypes.data_as(C.c_void_p) for a in arrs]
+    lib.miplib_cuda_load_csr.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 9 + [C.c_int]
+    return lib.miplib_cuda_load_csr(solver, L.m, L.n, *ptrs, int(L.maximize)), arrs
+
+
+def test_bulk_ingress_builds_the_same_row_store(built):
+    lib, C = _front(built)
+    solver = C.c_void_p()
+    assert lib.miplib_create_solver(C.byref(solver), 5) == 0            # miplib_SolverBackend::Cuda
+    L = gen.config(1)
+    rc, _ = _load_csr(lib, C, solver, L)
+    assert rc == 0, lib.miplib_get_last_error()
+    n, m = C.c_int64(), C.c_int64()
+    assert lib.miplib_cuda_get_shape(solver, C.byref(n), C.byref(m)) == 0
+    assert (n.value, m.value) == (L.n, L.m)
+    obj = C.c_double()
+    assert lib.miplib_cuda_get_values(solver, None, C.byref(obj)) == 1   # no solution yet
+    assert b"before a solution" in lib.miplib_get_last_error()
+    bad = gen.LP(L.A[:, ::-1], L.c, L.lb, L.ub, L.row_lo, L.row_hi)
+    A = bad.A.tocsr(); A.indices[:2] = A.indices[:2][::-1].copy()        # a row with decreasing columns
+    bad.A = A
+    s2 = C.c_void_p()
+    assert lib.miplib_create_solver(C.byref(s2), 5) == 0
+    arrs = [np.array([0, 2], dtype=np.int64), np.array([1, 0], dtype=np.int32), np.array([1.0, 1.0])]
+    lib.miplib_cuda_load_csr.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 9 + [C.c_int]
+    z = np.zeros(2); o = np.ones(2); r = np.array([1.0])
+    rc = lib.miplib_cuda_load_csr(s2, 1, 2, *[a.ctypes.data_as(C.c_void_p) for a in arrs],
+                                  z.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p),
+                                  o.ctypes.data_as(C.c_void_p), None, r.ctypes.data_as(C.c_void_p),
+                                  r.ctypes.data_as(C.c_void_p), 0)
+    assert rc == 1 and b"increasing" in lib.miplib_get_last_error()
+    assert lib.miplib_destroy_solver(solver) == 0 and lib.miplib_destroy_solver(s2) == 0
+
+
+@pytest.mark.gpu
+def test_bulk_ingress_solves_lp_and_mip(built, golden):
+    lib, C = _front(built)
+    for key, L, types in [("C1_lp", gen.config(1), None),
+                          ("setcover_200x500_mip", gen.set_cover(200, 500, 8, 20264), np.ones(500, np.int32))]:
+        solver = C.c_void_p()
+        assert lib.miplib_create_solver(C.byref(solver), 5) == 0
+        rc, keep = _load_csr(lib, C, solver, L, types)
+        assert rc == 0, lib.miplib_get_last_error()
+        result, has = C.c_int(-1), C.c_int(-1)
+        assert lib.miplib_cuda_solve(solver, C.byref(result), C.byref(has)) == 0, lib.miplib_get_last_error()
+        assert (result.value, has.value) == (0, 1)                     # Solver::Result::Optimal
+        x = np.empty(L.n); obj = C.c_double()
+        assert lib.miplib_cuda_get_values(solver, x.ctypes.data_as(C.c_void_p), C.byref(obj)) == 0
+        exp = golden[key]["objective"]
+        assert abs(obj.value - exp) <= 1e-6 * (1 + abs(exp))
+        assert abs(float(L.c @ x) - obj.value) <= 1e-9 * (1 + abs(exp))
+        assert lib.miplib_destroy_solver(solver) == 0
