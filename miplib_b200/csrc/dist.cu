@@ -78,7 +78,7 @@ void dist_init(mipcu_ctx* ctx, int rank, int world, const void* unique_id) {
   ctx->nccl_comm = comm;
   ctx->rank = rank;
   ctx->world = world;
-  MIPCU_CK(cudaMalloc(&ctx->row_sums, sizeof(double) * 8));
+  MIPCU_CK(cudaMalloc(&ctx->row_sums, sizeof(double) * 32));
 }
 
 void dist_destroy(mipcu_ctx* ctx) {
@@ -100,10 +100,10 @@ void dist_allreduce(mipcu_ctx* ctx, double* buf, size_t count, bool max_instead_
 // sum of one host scalar over the ranks (setup only)
 double dist_sum_scalar(mipcu_ctx* ctx, double v) {
   if (ctx->world <= 1) return v;
-  MIPCU_CK(cudaMemcpyAsync(ctx->row_sums + 7, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  dist_allreduce(ctx, ctx->row_sums + 7, 1, false);
+  MIPCU_CK(cudaMemcpyAsync(ctx->row_sums + 31, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  dist_allreduce(ctx, ctx->row_sums + 31, 1, false);
   double out = 0;
-  MIPCU_CK(cudaMemcpyAsync(&out, ctx->row_sums + 7, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  MIPCU_CK(cudaMemcpyAsync(&out, ctx->row_sums + 31, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   MIPCU_CK(cudaStreamSynchronize(ctx->stream));
   return out;
 }

@@ -58,6 +58,14 @@ enum Quantity {
   Q_DRES2,       // sum (reduced-cost violation / d2)^2   col step
   Q_POBJ,        // sum c xhat                            col step
   Q_DOBJ_COL,    // sum l r+ - u r-                       col step
+  // certificates of infeasibility from the displacement T(z) - z (dy = yhat - y, dx = xhat - x)
+  Q_RAYD_ROW,    // sum lo dy+ - hi dy-                    row step   (Farkas value, row part)
+  Q_RAYD_ROWV,   // sum (dy+ where lo = -inf, dy- where hi = +inf)^2
+  Q_RAYD_COL,    // sum l r+ - u r-,  r = -K'dy            col step   (Farkas value, column part)
+  Q_RAYD_COLV,   // sum (r+ where l = -inf, r- where u = +inf)^2
+  Q_RAYP_C,      // sum c dx                               col step   (objective along the primal ray)
+  Q_RAYP_COLV,   // sum (dx- where l finite, dx+ where u finite)^2
+  Q_RAYP_ROWV,   // sum ((K dx)- where lo finite, (K dx)+ where hi finite)^2     kkt row pass
   Q_COUNT
 };
 
@@ -75,9 +83,11 @@ struct Scalars {
   int period;
   int done;             // 0 running; 1 + MIPCU_* status once finished
   int restart_flag;     // set by the controller, consumed by k_restart_apply
+  int ray_hits_primal, ray_hits_dual;   // consecutive checks on which a certificate test passed
   int restarts;
   int nblk_row, nblk_col, max_blocks;
   int pad_;
+  double ray_dual_value, ray_primal_value;   // last normalised Farkas value / c.dx (diagnostics)
 };
 
 }  // namespace mipcu
@@ -92,7 +102,7 @@ struct mipcu_ctx {
   // sharding (world == 1: plain single-GPU context)
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;
-  double* row_sums = nullptr;     // 8 doubles: all-reduced row-side scalars of check iterations
+  double* row_sums = nullptr;     // 32 doubles: all-reduced row-side scalars of check iterations
   int64_t collectives = 0;        // NCCL calls issued by the current call
 
   // model as loaded (unscaled), device resident

@@ -103,6 +103,7 @@ struct RowStepArgs {
   double* y; double* yhat;
   const Scalars* sc; double* partials;
   int m; int iter_in_block;
+  double* kx_save;   // CHECK, last iteration of a block: K xbar kept for the primal-ray test (or null)
 };
 
 template <int TPR, bool CHECK>
@@ -116,7 +117,7 @@ k_row_step(const RowStepArgs a) {
   const double k = (double)(sc->k_base + a.iter_in_block);
   const double w_new = (k + 1.0) / (k + 2.0);
   const int i = blockIdx.x * kRowsPerCta + threadIdx.x;
-  double red[3] = {0.0, 0.0, 0.0};
+  double red[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   if (i < a.m) {
     const double kx = s_sum[threadIdx.x];
     const double yi = a.y[i], y0i = a.y0[i], lo = a.lo[i], hi = a.hi[i];
@@ -130,11 +131,17 @@ k_row_step(const RowStepArgs a) {
       red[1] = d0 * d0;
       const double yp = fmax(yh, 0.0), ym = fmax(-yh, 0.0);
       red[2] = (isfinite(lo) ? lo * yp : 0.0) - (isfinite(hi) ? hi * ym : 0.0);
+      // dy as a candidate Farkas ray
+      const double dp = fmax(dy, 0.0), dm = fmax(-dy, 0.0);
+      red[3] = (isfinite(lo) ? lo * dp : 0.0) - (isfinite(hi) ? hi * dm : 0.0);
+      const double rv = (isfinite(lo) ? 0.0 : dp) + (isfinite(hi) ? 0.0 : dm);
+      red[4] = rv * rv;
+      if (a.kx_save) a.kx_save[i] = kx;
     }
   }
   if (CHECK) {
-    const int q[3] = {Q_DY2, Q_DY0, Q_DOBJ_ROW};
-    cta_reduce_store<3>(red, q, a.partials, sc->max_blocks);
+    const int q[5] = {Q_DY2, Q_DY0, Q_DOBJ_ROW, Q_RAYD_ROW, Q_RAYD_ROWV};
+    cta_reduce_store<5>(red, q, a.partials, sc->max_blocks);
   }
 }
 
@@ -156,7 +163,7 @@ struct ColStepArgs {
 // Shared by the fused single-GPU kernel and by k_primal_step of the row-sharded path.
 template <bool CHECK, bool STORE>
 __device__ __forceinline__ void col_epilogue(const ColStepArgs& a, const int j, const double atyh,
-                                             const double tau, const double w_new, double (&red)[6]) {
+                                             const double tau, const double w_new, double (&red)[10]) {
   const double xb = a.xbar[j], x0 = a.x0[j], at = a.aty[j], at0 = a.aty0[j];
   const double cj = a.c[j], lj = a.l[j], uj = a.u[j];
   if (CHECK) {
@@ -174,6 +181,15 @@ __device__ __forceinline__ void col_epilogue(const ColStepArgs& a, const int j, 
     red[4] = cj * xh;
     red[5] = (isfinite(lj) ? lj * rp : 0.0) - (isfinite(uj) ? uj * rm : 0.0);
     a.aty_cand[j] = atyh;
+    // dual ray dy: its reduced costs are -K'dy = -(K'yhat - K'y)
+    const double qp = fmax(-dat, 0.0), qm = fmax(dat, 0.0);
+    red[6] = (isfinite(lj) ? lj * qp : 0.0) - (isfinite(uj) ? uj * qm : 0.0);
+    const double qv = (isfinite(lj) ? 0.0 : qp) + (isfinite(uj) ? 0.0 : qm);
+    red[7] = qv * qv;
+    // primal ray dx: objective along it, and its components that leave a bounded side
+    red[8] = cj * dx;
+    const double pv = (isfinite(lj) ? fmax(-dx, 0.0) : 0.0) + (isfinite(uj) ? fmax(dx, 0.0) : 0.0);
+    red[9] = pv * pv;
   }
   const double xn = w_new * xb + (1.0 - w_new) * x0;
   const double atn = w_new * (2.0 * atyh - at) + (1.0 - w_new) * at0;
@@ -194,11 +210,12 @@ k_col_step(const ColStepArgs a) {
   const double k = (double)(sc->k_base + a.iter_in_block);
   const double w_new = (k + 1.0) / (k + 2.0);
   const int j = blockIdx.x * kRowsPerCta + threadIdx.x;
-  double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  double red[10] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (j < a.n) col_epilogue<CHECK, STORE>(a, j, s_sum[threadIdx.x], tau, w_new, red);
   if (CHECK) {
-    const int q[6] = {Q_DX2, Q_DXDATY, Q_DX0, Q_DRES2, Q_POBJ, Q_DOBJ_COL};
-    cta_reduce_store<6>(red, q, a.partials, sc->max_blocks);
+    const int q[10] = {Q_DX2, Q_DXDATY, Q_DX0, Q_DRES2, Q_POBJ, Q_DOBJ_COL,
+                       Q_RAYD_COL, Q_RAYD_COLV, Q_RAYP_C, Q_RAYP_COLV};
+    cta_reduce_store<10>(red, q, a.partials, sc->max_blocks);
   }
 }
 
@@ -214,11 +231,12 @@ k_primal_step(const ColStepArgs a, const double* __restrict__ atyh) {
   const double k = (double)(sc->k_base + a.iter_in_block);
   const double w_new = (k + 1.0) / (k + 2.0);
   const int j = blockIdx.x * kRowsPerCta + threadIdx.x;
-  double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  double red[10] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (j < a.n) col_epilogue<CHECK, STORE>(a, j, atyh[j], tau, w_new, red);
   if (CHECK) {
-    const int q[6] = {Q_DX2, Q_DXDATY, Q_DX0, Q_DRES2, Q_POBJ, Q_DOBJ_COL};
-    cta_reduce_store<6>(red, q, a.partials, sc->max_blocks);
+    const int q[10] = {Q_DX2, Q_DXDATY, Q_DX0, Q_DRES2, Q_POBJ, Q_DOBJ_COL,
+                       Q_RAYD_COL, Q_RAYD_COLV, Q_RAYP_C, Q_RAYP_COLV};
+    cta_reduce_store<10>(red, q, a.partials, sc->max_blocks);
   }
 }
 
@@ -228,19 +246,23 @@ __global__ void __launch_bounds__(kThreads)
 k_kkt_row(const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
           const double* __restrict__ xhat, const double* __restrict__ lo,
           const double* __restrict__ hi, const double* __restrict__ d1, const Scalars* sc,
-          double* partials, int m) {
+          double* partials, int m, const double* __restrict__ kxbar) {
   __shared__ double s_sum[kRowsPerCta];
   if (sc->done) return;
   cta_row_sums<TPR>(ptr, idx, val, xhat, m, s_sum);
   const int i = blockIdx.x * kRowsPerCta + threadIdx.x;
-  double red[1] = {0.0};
+  double red[2] = {0.0, 0.0};
   if (i < m) {
     const double kx = s_sum[threadIdx.x];
     const double v = (kx - clampd(kx, lo[i], hi[i])) / d1[i];
     red[0] = v * v;
+    // K dx = K xbar - K xhat (dx = xhat - x = xbar - xhat): must stay inside the rows' recession cone
+    const double kdx = kxbar[i] - kx;
+    const double rv = (isfinite(lo[i]) ? fmax(-kdx, 0.0) : 0.0) + (isfinite(hi[i]) ? fmax(kdx, 0.0) : 0.0);
+    red[1] = rv * rv;
   }
-  const int q[1] = {Q_PRES2};
-  cta_reduce_store<1>(red, q, partials, sc->max_blocks);
+  const int q[2] = {Q_PRES2, Q_RAYP_ROWV};
+  cta_reduce_store<2>(red, q, partials, sc->max_blocks);
 }
 
 // Plain out = A v through the same row-sum routine (setup, power iteration, test hook).

@@ -13,6 +13,7 @@ constexpr double BETA_NECESSARY   = 0.8;     // restart if fp <= 0.8 fp0 and fp 
 constexpr double BETA_ARTIFICIAL  = 0.36;    // restart if k >= 0.36 * total iterations
 constexpr double WEIGHT_SMOOTHING = 0.5;     // theta of the primal-weight update
 constexpr double WEIGHT_EPS       = 1e-10;
+constexpr double RAY_TOL          = 1e-8;    // certificate violation allowed relative to its value
 constexpr double INF_THRESHOLD    = 1e20;    // |bound| >= this means "no bound" (MIPCU_INF)
 
 }  // namespace mipcu

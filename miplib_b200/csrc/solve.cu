@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(kThreads) k_sum_row_partials(const Scalars* sc
                                                                double* row_sums) {
   if (sc->done) return;
   const int mb = sc->max_blocks;
-  const int q[4] = {Q_DY2, Q_DY0, Q_DOBJ_ROW, Q_PRES2};
-  for (int i = 0; i < 4; ++i) {
+  const int q[7] = {Q_DY2, Q_DY0, Q_DOBJ_ROW, Q_PRES2, Q_RAYD_ROW, Q_RAYD_ROWV, Q_RAYP_ROWV};
+  for (int i = 0; i < 7; ++i) {
     double v = cta_sum_partials(partials + (size_t)q[i] * mb, sc->nblk_row);
     if (threadIdx.x == 0) row_sums[q[i]] = v;
   }
@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(kThreads) k_ctrl_check(Scalars* sc, const doub
   const int mb = sc->max_blocks;
   double q[Q_COUNT];
   for (int i = 0; i < Q_COUNT; ++i) {
-    const bool is_row = (i == Q_DY2 || i == Q_DY0 || i == Q_DOBJ_ROW || i == Q_PRES2);
+    const bool is_row = (i == Q_DY2 || i == Q_DY0 || i == Q_DOBJ_ROW || i == Q_PRES2 ||
+                         i == Q_RAYD_ROW || i == Q_RAYD_ROWV || i == Q_RAYP_ROWV);
     if (is_row && row_sums) q[i] = row_sums[i];
     else q[i] = cta_sum_partials(partials + (size_t)i * mb, is_row ? sc->nblk_row : sc->nblk_col);
   }
@@ -100,6 +101,29 @@ __global__ void __launch_bounds__(kThreads) k_ctrl_check(Scalars* sc, const doub
   if (sc->rel_d <= sc->eps && dobj >= sc->cutoff) {   // a dual-feasible y bounds the optimum
     sc->done = 1 + MIPCU_CUTOFF;
     return;
+  }
+  // Infeasibility certificates from the displacement T(z) - z, which converges to the infimal
+  // displacement vector when the LP is inconsistent.  dy is a Farkas ray if its value is positive
+  // and it prices nothing through a missing bound; dx is an improving recession direction if
+  // c.dx < 0 and it moves no bounded side.  A test must pass on two consecutive checks.
+  {
+    const double nd = sqrt(q[Q_DY2]), nx = sqrt(q[Q_DX2]);
+    const double dval = nd > 1e-12 ? (q[Q_RAYD_ROW] + q[Q_RAYD_COL]) / nd : 0.0;
+    const double dviol = nd > 1e-12 ? sqrt(q[Q_RAYD_ROWV] + q[Q_RAYD_COLV]) / nd : 0.0;
+    const double pval = nx > 1e-12 ? q[Q_RAYP_C] / nx : 0.0;
+    const double pviol = nx > 1e-12 ? sqrt(q[Q_RAYP_COLV] + q[Q_RAYP_ROWV]) / nx : 0.0;
+    sc->ray_dual_value = dval;
+    sc->ray_primal_value = pval;
+    sc->ray_hits_dual = (dval > 1e-9 && dviol <= RAY_TOL * dval) ? sc->ray_hits_dual + 1 : 0;
+    sc->ray_hits_primal = (pval < -1e-9 && pviol <= RAY_TOL * -pval) ? sc->ray_hits_primal + 1 : 0;
+    if (sc->ray_hits_dual >= 2) {
+      sc->done = 1 + MIPCU_INFEASIBLE;
+      return;
+    }
+    if (sc->ray_hits_primal >= 2) {
+      sc->done = 1 + (sc->rel_p <= 1e-4 ? MIPCU_UNBOUNDED : MIPCU_INFEASIBLE_OR_UNBOUNDED);
+      return;
+    }
   }
   const bool restart = fp <= BETA_SUFFICIENT * sc->fp0 ||
                        (fp <= BETA_NECESSARY * sc->fp0 && fp > sc->fp_prev) ||
@@ -175,6 +199,7 @@ RowStepArgs row_args(mipcu_ctx* ctx, int i) {
   a.xbar = ctx->xbar; a.lo = ctx->los; a.hi = ctx->his; a.y0 = ctx->y0;
   a.y = ctx->y; a.yhat = ctx->yhat; a.sc = ctx->d_sc; a.partials = ctx->partials;
   a.m = ctx->m; a.iter_in_block = i;
+  a.kx_save = nullptr;
   return a;
 }
 
@@ -253,7 +278,7 @@ template <int TPR>
 void launch_kkt(mipcu_ctx* ctx) {
   k_kkt_row<TPR><<<grid_for(ctx->m, kRowsPerCta), kThreads, 0, ctx->stream>>>(
       ctx->rows.ptr, ctx->rows.idx, ctx->rows.val, ctx->xhat_chk, ctx->los, ctx->his, ctx->d1,
-      ctx->d_sc, ctx->partials, ctx->m);
+      ctx->d_sc, ctx->partials, ctx->m, ctx->tmp_m);
 }
 
 #define MIPCU_DISPATCH_TPR(tpr, CALL)                                                          \
@@ -265,9 +290,10 @@ void launch_kkt(mipcu_ctx* ctx) {
     default: { constexpr int T = 32; CALL; } break;                                            \
   }
 
-void row_step(mipcu_ctx* ctx, int i, bool check) {
+void row_step(mipcu_ctx* ctx, int i, bool check, bool keep_kx = false) {
   if (ctx->m == 0) return;
   RowStepArgs a = row_args(ctx, i);
+  if (keep_kx) a.kx_save = ctx->tmp_m;
   MIPCU_DISPATCH_TPR(ctx->rows.tpr, launch_row<T>(ctx, a, check));
   ctx->launches++;
 }
@@ -299,7 +325,7 @@ const double* global_row_sums(mipcu_ctx* ctx) {
   if (ctx->world <= 1) return nullptr;
   k_sum_row_partials<<<1, kThreads, 0, ctx->stream>>>(ctx->d_sc, ctx->partials, ctx->row_sums);
   ctx->launches++;
-  dist_allreduce(ctx, ctx->row_sums, 4, false);
+  dist_allreduce(ctx, ctx->row_sums, Q_COUNT, false);
   return ctx->row_sums;
 }
 
@@ -329,7 +355,7 @@ void enqueue_block(mipcu_ctx* ctx, int period, cudaEvent_t* time_events) {
     const bool first = (i == 0), last = (i == period - 1);
     const bool timed = time_events && i == (period > 2 ? 1 : 0);
     if (timed) MIPCU_CK(cudaEventRecord(time_events[0], st));
-    row_step(ctx, i, first || last);
+    row_step(ctx, i, first || last, last);
     if (timed) MIPCU_CK(cudaEventRecord(time_events[1], st));
     if (last) kkt_row(ctx);
     const double* xin = first ? ctx->xhat_first : ctx->xhat_chk;
@@ -376,6 +402,8 @@ void init_iterate(mipcu_ctx* ctx, Scalars& h) {
   h.nblk_row = grid_for(m, tma_usable(ctx, ctx->rows, 4) ? kTileRows : kRowsPerCta);
   h.nblk_col = grid_for(n, tma_usable(ctx, ctx->cols, 7) ? kTileRows : kRowsPerCta);
   h.max_blocks = ctx->max_blocks;
+  // kernel variants write different ranges of the partial arrays: never sum a stale entry
+  MIPCU_CK(cudaMemsetAsync(ctx->partials, 0, sizeof(double) * Q_COUNT * ctx->max_blocks, st));
   MIPCU_CK(cudaMemcpyAsync(ctx->d_sc, &h, sizeof(Scalars), cudaMemcpyHostToDevice, st));
   if (nm) {
     k_start_point<<<grid_for(nm), kThreads, 0, st>>>(n, m, ctx->x_start, ctx->y_start, ctx->d1,

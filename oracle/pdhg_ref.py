@@ -46,6 +46,7 @@ BETA_NECESSARY = 0.8
 BETA_ARTIFICIAL = 0.36
 WEIGHT_SMOOTHING = 0.5
 WEIGHT_EPS = 1e-10
+RAY_TOL = 1e-8
 
 
 def hash_unit_vector(n: int) -> np.ndarray:
@@ -221,6 +222,28 @@ def kkt_scaled(S: Scaled, xhat, yhat, atyh, kxhat):
     return rel_p, rel_d, rel_g, pobj, dobj
 
 
+def ray_tests(S: Scaled, dx, dy, daty, kdx):
+    """(dual ray dy proves primal infeasibility, primal ray dx proves dual infeasibility) - the two
+    tests of k_ctrl_check on the displacement T(z) - z."""
+    fin = np.isfinite
+    nd, nx = np.linalg.norm(dy), np.linalg.norm(dx)
+    dual_ok = primal_ok = False
+    if nd > 1e-12:
+        dp, dm = np.maximum(dy, 0), np.maximum(-dy, 0)
+        qp, qm = np.maximum(-daty, 0), np.maximum(daty, 0)
+        val = (np.where(fin(S.lo), S.lo, 0) @ dp - np.where(fin(S.hi), S.hi, 0) @ dm
+               + np.where(fin(S.l), S.l, 0) @ qp - np.where(fin(S.u), S.u, 0) @ qm) / nd
+        viol2 = np.sum((np.where(fin(S.lo), 0, dp) + np.where(fin(S.hi), 0, dm)) ** 2) \
+            + np.sum((np.where(fin(S.l), 0, qp) + np.where(fin(S.u), 0, qm)) ** 2)
+        dual_ok = val > 1e-9 and np.sqrt(viol2) / nd <= RAY_TOL * val
+    if nx > 1e-12:
+        val = (S.c @ dx) / nx
+        viol2 = np.sum((np.where(fin(S.l), np.maximum(-dx, 0), 0) + np.where(fin(S.u), np.maximum(dx, 0), 0)) ** 2) \
+            + np.sum((np.where(fin(S.lo), np.maximum(-kdx, 0), 0) + np.where(fin(S.hi), np.maximum(kdx, 0), 0)) ** 2)
+        primal_ok = val < -1e-9 and np.sqrt(viol2) / nx <= RAY_TOL * -val
+    return dual_ok, primal_ok
+
+
 def solve(lpm: LP, eps: float = 1e-6, max_iter: int = 200000, period: int = 64,
           step_size: float | None = None, x_start=None, y_start=None, scale: bool = True,
           trace_at: tuple = (), verbose: bool = False):
@@ -248,6 +271,7 @@ def solve(lpm: LP, eps: float = 1e-6, max_iter: int = 200000, period: int = 64,
     total = 0
     restarts = 0
     fp0 = fp_prev = None
+    ray_hits = [0, 0]
     trace = {}
     hist = []
     res = dict(status="iteration_limit")
@@ -260,7 +284,7 @@ def solve(lpm: LP, eps: float = 1e-6, max_iter: int = 200000, period: int = 64,
             first = (i == 0)
             last = (i == period - 1)
             y_k = y
-            yhat, y, _ = row_step(S, xbar, y, y0, sigma, a)
+            yhat, y, kx_k = row_step(S, xbar, y, y0, sigma, a)
             if first or last:
                 xh_k = xhat_first if first else xhat_chk
                 dx = xbar - xh_k                      # = xhat_k - x_k
@@ -293,6 +317,15 @@ def solve(lpm: LP, eps: float = 1e-6, max_iter: int = 200000, period: int = 64,
                   f"pobj {S.sgn*pobj:.9f} w {w:.3e} fp {fp:.2e}")
         if max(rel_p, rel_d, rel_g) <= eps:
             res = dict(status="optimal")
+            break
+        # certificates of infeasibility from the displacement (k_ctrl_check, same tests)
+        verdict = ray_tests(S, dx, dy, daty, kx_k - kxhat)
+        ray_hits = [ray_hits[0] + 1 if verdict[0] else 0, ray_hits[1] + 1 if verdict[1] else 0]
+        if ray_hits[0] >= 2:
+            res = dict(status="infeasible")
+            break
+        if ray_hits[1] >= 2:
+            res = dict(status="unbounded" if rel_p <= 1e-4 else "infeasible_or_unbounded")
             break
         do_restart = (fp <= BETA_SUFFICIENT * fp0
                       or (fp <= BETA_NECESSARY * fp0 and fp > fp_prev)

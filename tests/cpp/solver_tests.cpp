@@ -136,6 +136,39 @@ GPU_TEST("Continuous LP through the expression API: a textbook optimum")
   REQUIRE(close(solver.get_objective_value(), 0, 1e-5));
 }
 
+GPU_TEST("Result contract: Infeasible and Unbounded LPs (ref miplib/lpsolve/solver.cpp:171-199)")
+{
+  {
+    Solver solver(B, false);
+    Var x(solver, Var::Type::Continuous, 0, 1, "x");
+    Var y(solver, Var::Type::Continuous, 0, 1, "y");
+    solver.add(x + y <= 1);
+    solver.add(x + y >= 1.5);
+    auto [r, has_solution] = solver.minimize(x);
+    REQUIRE(r == Solver::Result::Infeasible);
+    REQUIRE(!has_solution);
+    REQUIRE_THROWS_AS(x.value(), std::logic_error);
+  }
+  {
+    Solver solver(B, false);
+    Var x(solver, Var::Type::Continuous, 0, std::nullopt, "x");
+    Var y(solver, Var::Type::Continuous, 0, std::nullopt, "y");
+    solver.add(x - y <= 1);
+    auto [r, has_solution] = solver.maximize(x);
+    REQUIRE(r == Solver::Result::Unbounded || r == Solver::Result::InfeasibleOrUnbounded);
+    REQUIRE(!has_solution);
+  }
+  {
+    // an integer model whose boxes make a row impossible: decided by propagation, no LP needed
+    Solver solver(B, false);
+    Var a(solver, Var::Type::Integer, 0, 3, "a");
+    Var b(solver, Var::Type::Binary, "b");
+    solver.add(2 * a + b == 9);
+    auto [r, has_solution] = solver.solve();
+    REQUIRE(r == Solver::Result::Infeasible && !has_solution);
+  }
+}
+
 // Replays oracle/gen.py's recipes through Var / Expr / Constr from a text fixture written by the
 // pytest wrapper (tests/test_frontend.py): "n m" / per column "type lb ub cost" / per row
 // "lo hi k (col val)*k" / "maximize expected_objective kind".
