@@ -163,7 +163,8 @@ GPU_TEST("Result contract: Infeasible and Unbounded LPs (ref miplib/lpsolve/solv
     Solver solver(B, false);
     Var a(solver, Var::Type::Integer, 0, 3, "a");
     Var b(solver, Var::Type::Binary, "b");
-    solver.add(2 * a + b == 9);
+    solver.add(a + b == 4);      // each row alone is satisfiable in the boxes ...
+    solver.add(a - b == 3);      // ... together they need a = 3.5
     auto [r, has_solution] = solver.solve();
     REQUIRE(r == Solver::Result::Infeasible && !has_solution);
   }
