@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <deque>
 #include <iostream>
 #include <limits>
@@ -384,8 +385,9 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
     S.m_info.lp_solves += static_cast<std::int64_t>(B);
     S.m_info.kernel_launches += stats[0].kernel_launches;
     if (user_verbose)
-      std::cerr << "[miplib cuda b&b] round of " << B << " node LPs, " << S.m_info.nodes << " nodes so far, "
-                << open.size() << " open, incumbent " << (have_incumbent ? sgn * best : std::nan("")) << "\n";
+      std::fprintf(stderr, "[miplib cuda b&b] round of %zu node LPs, %lld nodes so far, %zu open, incumbent %g\n",
+                   B, static_cast<long long>(S.m_info.nodes), open.size(),
+                   have_incumbent ? sgn * best : std::nan(""));
 
     for (std::size_t b = 0; b < B; ++b)
     {

@@ -170,6 +170,25 @@ GPU_TEST("Result contract: Infeasible and Unbounded LPs (ref miplib/lpsolve/solv
   }
 }
 
+GPU_TEST("Bulk CSR ingress: LP and MIP without Var / Expr objects (miplib/cuda/capi.hpp)")
+{
+  // max 3x + 2y  s.t. x + y <= 4, x + 3y <= 6, x <= 3  ->  (3,1), 11 ; then the same with x, y integer
+  std::int64_t const ptr[] = {0, 2, 4, 5};
+  std::int32_t const idx[] = {0, 1, 0, 1, 0};
+  double const val[] = {1, 1, 1, 3, 1};
+  double const c[] = {3, 2}, lb[] = {0, 0}, ub[] = {1e30, 1e30};
+  double const lo[] = {-1e30, -1e30, -1e30}, hi[] = {4, 6, 3};
+  for (int pass = 0; pass < 2; ++pass)
+  {
+    Solver solver(B);                       // verbose on, like the C API's miplib_create_solver
+    std::int32_t const types[] = {pass ? 2 : 0, pass ? 2 : 0};
+    CudaSolver::of(solver).load_csr(solver, 3, 2, ptr, idx, val, c, lb, ub, types, lo, hi, true);
+    auto [r, has_solution] = solver.solve();
+    REQUIRE(r == Solver::Result::Optimal && has_solution);
+    REQUIRE(close(solver.get_objective_value(), 11, 1e-5));
+  }
+}
+
 // Replays oracle/gen.py's recipes through Var / Expr / Constr from a text fixture written by the
 // pytest wrapper (tests/test_frontend.py): "n m" / per column "type lb ub cost" / per row
 // "lo hi k (col val)*k" / "maximize expected_objective kind".
