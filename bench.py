@@ -309,19 +309,104 @@ def run_cuda(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_nodes(args, rank, world, local_rank):
+    """Secondary workload (configs 4 / 5): rounds of branch-and-bound node LP relaxations that share
+    the matrix, 128 nodes per GPU per round, dealt to the ranks with no device-side exchange (weak
+    scaling).  A step = one round on every rank.  `python bench.py --workload nodes --config 4`."""
+    import torch
+    from miplib_b200 import Engine
+    from oracle import gen, kkt_verify
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    L = gen.config(args.config)
+    per_gpu = args.nodes_per_gpu
+    depth = 12 if args.config == 4 else 30                       # binaries fixed per node
+    rng = np.random.default_rng(1000 + rank)
+
+    def boxes():
+        lb = np.tile(L.lb, (per_gpu, 1)); ub = np.tile(L.ub, (per_gpu, 1))
+        for b in range(per_gpu):
+            if rank == 0 and b == 0:
+                continue                                           # node 0 of rank 0 is the root
+            cols = rng.choice(L.n, depth, replace=False)
+            vals = (rng.random(depth) < (0.5 if args.config == 4 else 0.1)).astype(float)
+            lb[b, cols] = vals; ub[b, cols] = vals
+        return lb, ub
+
+    eng = Engine(local_rank)
+    eng.load_lp(L)
+    eng.set_param("iter_limit", 60000)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        eng.solve_batch(*boxes(), want_x=False)
+    rounds = [boxes() for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    results = [eng.solve_batch(lb, ub, want_x=(rank == 0 and i == 0)) for i, (lb, ub) in enumerate(rounds)]
+    barrier()
+    secs = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    solved = sum(sum(s.status in ("optimal", "cutoff", "infeasible") for s in st) for st, _ in results)
+    if dist is not None:
+        t = torch.tensor([float(solved)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        solved = int(t.item())
+    if rank != 0:
+        return
+    st0, x0 = results[0]
+    root = st0[0]
+    iters = [s.iterations for st, _ in results for s in st]
+    line = {
+        "metric": "node_lps_per_s", "value": per_gpu * world * args.steps / secs, "unit": "node LP/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C{args.config}: node LP relaxations of the synthetic "
+                               f"{'set-cover' if args.config == 4 else 'multi-dimensional knapsack'} MIP "
+                               f"({L.m} x {L.n}), {per_gpu} nodes per GPU per round, {depth} binaries fixed per node",
+                   "parallelism": "nodes dealt to GPUs, no collective"},
+        "node_lps_decided": solved, "node_lps_total": per_gpu * world * args.steps,
+        "iterations_mean": float(np.mean(iters)), "iterations_max": int(np.max(iters)),
+        "root_lp": {"status": root.status, "objective": root.primal_obj, "rel_primal_res": root.rel_primal_res,
+                    "rel_gap": root.rel_gap},
+        "gpu_launches": int(sum(st[0].kernel_launches for st, _ in results)), "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3])
+    ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3, 4, 5])
+    ap.add_argument("--workload", default="lp", choices=["lp", "nodes"])
+    ap.add_argument("--nodes-per-gpu", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    if args.impl == "reference":
+    if args.workload == "nodes":
+        if args.config not in (4, 5):
+            args.config = 4
+        run_nodes(args, rank, world, local_rank)
+    elif args.impl == "reference":
         run_reference(args, rank)
     else:
         run_cuda(args, rank, world, local_rank)
