@@ -114,6 +114,66 @@ __global__ void __launch_bounds__(kThreads) k_row_step_batch(const BatchArgs a, 
   }
 }
 
+// Long rows (config 5: 500 rows of ~1600 nonzeros): one CTA per row, its 8 warps stride over the
+// row's nonzeros and the partial sums meet in shared memory; warp 0 runs the epilogue.  Fixed
+// summation order (warp 0..7), so still bit-reproducible.  MODE 0: row step, MODE 1: KKT residual.
+template <bool CHECK, int MODE>
+__global__ void __launch_bounds__(kThreads) k_row_batch_long(const BatchArgs a, int iter_in_block) {
+  __shared__ double s_part[kWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y * 32 + lane;
+  const int row = blockIdx.x;
+  const Scalars* sc = a.sc + b;
+  const bool active = !sc->done;
+  const double* vec = MODE == 0 ? a.xbar : a.xhat_chk;
+  double acc0 = 0.0, acc1 = 0.0;
+  if (__any_sync(0xffffffffu, active)) {
+    const int beg = a.rptr[row], end = a.rptr[row + 1];
+    int k = beg + warp;
+    for (; k + kWarps < end; k += 2 * kWarps) {
+      const double v0 = a.rval[k], v1 = a.rval[k + kWarps];
+      const int c0 = a.ridx[k], c1 = a.ridx[k + kWarps];
+      acc0 = fma(v0, vec[(size_t)c0 * a.BP + b], acc0);
+      acc1 = fma(v1, vec[(size_t)c1 * a.BP + b], acc1);
+    }
+    if (k < end) acc0 = fma(a.rval[k], vec[(size_t)a.ridx[k] * a.BP + b], acc0);
+  }
+  s_part[warp][lane] = acc0 + acc1;
+  __syncthreads();
+  if (warp != 0) return;
+  double kx = 0.0;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) kx += s_part[w][lane];
+  const size_t slot = (size_t)row * a.BP + b;       // partial index: one entry per row
+  if (MODE == 1) {
+    const double v = (kx - clampd(kx, a.lo[row], a.hi[row])) / a.d1[row];
+    a.partials[((size_t)Q_PRES2 * a.nblk_max + row) * a.BP + b] = v * v;
+    return;
+  }
+  double red[3] = {0.0, 0.0, 0.0};
+  if (active) {
+    const double sigma = sc->sigma;
+    const double kk = (double)(sc->k_base + iter_in_block);
+    const double w_new = (kk + 1.0) / (kk + 2.0);
+    const double yi = a.y[slot], y0i = a.y0[slot], lo = a.lo[row], hi = a.hi[row];
+    const double t = kx - yi / sigma;
+    const double yh = sigma * (clampd(t, lo, hi) - t);
+    a.yhat[slot] = yh;
+    a.y[slot] = w_new * (2.0 * yh - yi) + (1.0 - w_new) * y0i;
+    if (CHECK) {
+      const double dy = yh - yi, d0 = yh - y0i;
+      red[0] = dy * dy;
+      red[1] = d0 * d0;
+      red[2] = (isfinite(lo) ? lo * fmax(yh, 0.0) : 0.0) - (isfinite(hi) ? hi * fmax(-yh, 0.0) : 0.0);
+    }
+  }
+  if (CHECK) {
+    a.partials[((size_t)Q_DY2 * a.nblk_max + row) * a.BP + b] = red[0];
+    a.partials[((size_t)Q_DY0 * a.nblk_max + row) * a.BP + b] = red[1];
+    a.partials[((size_t)Q_DOBJ_ROW * a.nblk_max + row) * a.BP + b] = red[2];
+  }
+}
+
 template <bool CHECK, bool STORE>
 __global__ void __launch_bounds__(kThreads)
 k_col_step_batch(const BatchArgs a, int iter_in_block, const double* xhat_in, double* xhat_out) {
@@ -337,7 +397,9 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
   const int n = ctx->n, m = ctx->m;
   const int BP = (B + 31) / 32 * 32;
   const size_t nB = (size_t)n * BP, mB = (size_t)m * BP;
-  const int nblk_row = grid_for(m, kRowsPerCtaB), nblk_col = grid_for(n, kRowsPerCtaB);
+  // rows far longer than a warp can stream serially get a CTA each (config 5)
+  const bool long_rows = m > 0 && ctx->nnz / std::max(m, 1) > 128;
+  const int nblk_row = long_rows ? m : grid_for(m, kRowsPerCtaB), nblk_col = grid_for(n, kRowsPerCtaB);
   const int nblk_max = std::max(1, std::max(nblk_row, nblk_col));
   const int period = (int)ctx->params[MIPCU_PARAM_CHECK_PERIOD];
   const int64_t iter_limit = (int64_t)ctx->params[MIPCU_PARAM_ITER_LIMIT];
@@ -402,7 +464,13 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
   auto enqueue_block = [&]() {
     for (int i = 0; i < period; ++i) {
       const bool first = i == 0, last = i == period - 1;
-      if (m) {
+      if (m && long_rows) {
+        const dim3 g(m, BP / 32);
+        if (first || last) k_row_batch_long<true, 0><<<g, kThreads, 0, st>>>(a, i);
+        else k_row_batch_long<false, 0><<<g, kThreads, 0, st>>>(a, i);
+        ctx->launches++;
+        if (last) { k_row_batch_long<false, 1><<<g, kThreads, 0, st>>>(a, i); ctx->launches++; }
+      } else if (m) {
         if (first || last) k_row_step_batch<true><<<grid_rows, kThreads, 0, st>>>(a, i);
         else k_row_step_batch<false><<<grid_rows, kThreads, 0, st>>>(a, i);
         ctx->launches++;

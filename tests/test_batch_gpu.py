@@ -23,14 +23,17 @@ def node_boxes(L, B, rng, nfix):
     return lb, ub
 
 
-@pytest.mark.parametrize("case", ["setcover", "mkp"])
+@pytest.mark.parametrize("case", ["setcover", "mkp", "mkp_long_rows"])
 def test_batch_matches_exact_solver_per_node(built, case):
     from miplib_b200 import Engine
     rng = np.random.default_rng(4)
     if case == "setcover":
         L = gen.set_cover(200, 500, 8, 20264); B, nfix = 37, 6      # B not a multiple of 32 on purpose
-    else:
+    elif case == "mkp":
         L = gen.mkp(10, 100, 4, 5, 20265); B, nfix = 64, 5
+    else:                                                    # config-5 shape: CTA-per-row kernels
+        L = gen.mkp(5, 2000, 4, 10, 20265); B, nfix = 33, 40
+        assert L.nnz / L.m > 128
     lb, ub = node_boxes(L, B, rng, nfix)
     with Engine(0) as e:
         e.load_lp(L)
