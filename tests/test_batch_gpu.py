@@ -37,6 +37,7 @@ def test_batch_matches_exact_solver_per_node(built, case):
     lb, ub = node_boxes(L, B, rng, nfix)
     with Engine(0) as e:
         e.load_lp(L)
+        e.set_param("iter_limit", 40000)          # infeasible boxes run to the limit: keep it short
         stats, x = e.solve_batch(lb, ub)
         single = []
         for b in (0, 1, B - 1):
@@ -50,7 +51,8 @@ def test_batch_matches_exact_solver_per_node(built, case):
             assert stats[b].status != "optimal"                 # an infeasible box never "converges"
             continue
         assert stats[b].status == "optimal", (b, stats[b])
-        assert rel(stats[b].primal_obj, ref["obj"]) <= 1e-6, (b, stats[b].primal_obj, ref["obj"])
+        # a 1e-6 relative KKT point is within a few 1e-6 of the optimum (gap + residual terms)
+        assert rel(stats[b].primal_obj, ref["obj"]) <= 3e-6, (b, stats[b].primal_obj, ref["obj"])
         assert np.all(x[b] >= lb[b] - 1e-12) and np.all(x[b] <= ub[b] + 1e-12)
         assert rel(float(L.c @ x[b]), stats[b].primal_obj) <= 1e-9
         checked += 1
