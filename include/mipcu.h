@@ -61,7 +61,9 @@ enum {
   MIPCU_PARAM_OBJ_CUTOFF = 9,     /* stop with MIPCU_CUTOFF once the dual bound proves the optimum is no
                                      better than this objective value (model's own sense); NaN = off */
   MIPCU_PARAM_USE_TMA = 10,       /* -1 auto (default), 0: LSU-streamed kernels, 1: TMA-streamed kernels */
-  MIPCU_PARAM_COUNT_ = 11
+  MIPCU_PARAM_SHARD_EXCHANGE = 11,/* row-sharded contexts: 1 (default) fused reduce-scatter + primal step +
+                                     all-gather kernel over NVLink peer memory; 0: ncclAllReduce. Set before load */
+  MIPCU_PARAM_COUNT_ = 12
 };
 
 typedef struct mipcu_stats {

@@ -52,6 +52,7 @@ void set_default_params(mipcu_ctx* ctx) {
   ctx->params[MIPCU_PARAM_THREADS_PER_ROW] = 0;
   ctx->params[MIPCU_PARAM_OBJ_CUTOFF] = NAN;
   ctx->params[MIPCU_PARAM_USE_TMA] = -1;
+  ctx->params[MIPCU_PARAM_SHARD_EXCHANGE] = 1;
 }
 
 mipcu_ctx* create_on(int device) {
@@ -131,6 +132,7 @@ void mipcu_destroy(mipcu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  try { p2p_teardown(ctx); } catch (...) {}
   try { free_model(ctx); } catch (...) {}
   if (ctx->nccl_comm) { try { dist_destroy(ctx); } catch (...) {} }
   if (ctx->d_sc) cudaFree(ctx->d_sc);
@@ -154,7 +156,9 @@ int mipcu_load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64
   if (!ctx) return 1;
   return guarded(ctx, [&] {
     ctx->launches = 0;
+    p2p_teardown(ctx);
     load_lp(ctx, m, n, nnz, row_ptr, col_idx, val, c, lb, ub, row_lo, row_hi, maximize);
+    p2p_setup(ctx);   // collective on sharded contexts: maps the peers' exchange buffers
   });
 }
 

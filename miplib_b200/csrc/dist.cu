@@ -25,6 +25,7 @@ struct Nccl {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -48,6 +49,7 @@ Nccl& nccl() {
     api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
   });
   if (!error.empty()) throw Error(error);
@@ -94,6 +96,14 @@ void dist_allreduce(mipcu_ctx* ctx, double* buf, size_t count, bool max_instead_
   nccl_check(nccl().AllReduce(buf, buf, count, ncclFloat64, max_instead_of_sum ? ncclMax : ncclSum,
                               static_cast<ncclComm_t>(ctx->nccl_comm), ctx->stream),
              "ncclAllReduce");
+  ctx->collectives++;
+}
+
+// raw bytes from every rank, in rank order (setup only: IPC handle exchange)
+void dist_allgather_bytes(mipcu_ctx* ctx, const void* send_dev, void* recv_dev, size_t bytes_per_rank) {
+  nccl_check(nccl().AllGather(send_dev, recv_dev, bytes_per_rank, ncclUint8,
+                              static_cast<ncclComm_t>(ctx->nccl_comm), ctx->stream),
+             "ncclAllGather");
   ctx->collectives++;
 }
 

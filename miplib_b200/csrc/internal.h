@@ -90,6 +90,18 @@ struct Scalars {
   double ray_dual_value, ray_primal_value;   // last normalised Farkas value / c.dx (diagnostics)
 };
 
+// Row-sharded contexts: the peers' copies of the exchange buffers, mapped with CUDA IPC (p2p.cu)
+constexpr int kMaxPeers = 16;
+struct PeerTable {
+  int world = 0, rank = 0;
+  int j0[kMaxPeers + 1] = {};               // column slice of rank g: [j0[g], j0[g+1])
+  double* partial[kMaxPeers] = {};          // K_g' yhat_g of every rank
+  double* xbar[kMaxPeers] = {};
+  double* xhat_chk[kMaxPeers] = {};
+  double* x_sol[kMaxPeers] = {};
+  unsigned long long* flags[kMaxPeers] = {};
+};
+
 }  // namespace mipcu
 
 struct mipcu_ctx {
@@ -104,6 +116,9 @@ struct mipcu_ctx {
   void* nccl_comm = nullptr;
   double* row_sums = nullptr;     // 32 doubles: all-reduced row-side scalars of check iterations
   int64_t collectives = 0;        // NCCL calls issued by the current call
+  mipcu::PeerTable peers;         // world == peers.world: the fused P2P exchange is usable
+  std::vector<void*> peer_mappings;
+  unsigned long long* p2p_flags = nullptr;
 
   // model as loaded (unscaled), device resident
   int m = 0, n = 0;
@@ -160,6 +175,14 @@ void spmv_host(mipcu_ctx* ctx, int transpose, const double* v, double* out);
 // ---- dist.cu --------------------------------------------------------------------------------
 void dist_allreduce(mipcu_ctx* ctx, double* buf, size_t count, bool max_instead_of_sum);
 double dist_sum_scalar(mipcu_ctx* ctx, double v);
+
+// ---- p2p.cu ---------------------------------------------------------------------------------
+struct ColStepArgs;
+bool p2p_active(const mipcu_ctx* ctx);
+void p2p_setup(mipcu_ctx* ctx);
+void p2p_teardown(mipcu_ctx* ctx);
+void p2p_primal_step(mipcu_ctx* ctx, const ColStepArgs& a, bool check, bool store);
+void p2p_allgather(mipcu_ctx* ctx, int which);   // 0 xbar, 1 xhat_chk, 2 x_sol
 
 // ---- solve.cu -------------------------------------------------------------------------------
 void solve_lp(mipcu_ctx* ctx, mipcu_stats* out);

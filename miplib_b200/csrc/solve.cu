@@ -39,25 +39,30 @@ __device__ double fixed_point_error(const Scalars* sc, double dx2, double dxdaty
 }
 
 // after the FIRST iteration of a block: records the fixed-point error right after a restart
-// row-sharded: the row-side sums of this rank, to be all-reduced before the controllers read them
-__global__ void __launch_bounds__(kThreads) k_sum_row_partials(const Scalars* sc, const double* partials,
-                                                               double* row_sums) {
+// row-sharded: this rank's sums, to be all-reduced before the controllers read them.  Row-side
+// quantities are always partial; column-side ones only when the primal step is sharded too (p2p).
+__global__ void __launch_bounds__(kThreads) k_sum_partials(const Scalars* sc, const double* partials,
+                                                           double* sums, int include_cols) {
   if (sc->done) return;
   const int mb = sc->max_blocks;
-  const int q[7] = {Q_DY2, Q_DY0, Q_DOBJ_ROW, Q_PRES2, Q_RAYD_ROW, Q_RAYD_ROWV, Q_RAYP_ROWV};
-  for (int i = 0; i < 7; ++i) {
-    double v = cta_sum_partials(partials + (size_t)q[i] * mb, sc->nblk_row);
-    if (threadIdx.x == 0) row_sums[q[i]] = v;
+  for (int i = 0; i < Q_COUNT; ++i) {
+    const bool is_row = (i == Q_DY2 || i == Q_DY0 || i == Q_DOBJ_ROW || i == Q_PRES2 ||
+                         i == Q_RAYD_ROW || i == Q_RAYD_ROWV || i == Q_RAYP_ROWV);
+    double v = 0.0;
+    if (is_row || include_cols)
+      v = cta_sum_partials(partials + (size_t)i * mb, is_row ? sc->nblk_row : sc->nblk_col);
+    if (threadIdx.x == 0) sums[i] = v;
   }
 }
 
 __global__ void __launch_bounds__(kThreads) k_ctrl_first(Scalars* sc, const double* partials,
-                                                         const double* row_sums) {
+                                                         const double* row_sums, int cols_from_sums) {
   if (sc->done) return;
   const int mb = sc->max_blocks;
   double dy2 = row_sums ? row_sums[Q_DY2] : cta_sum_partials(partials + (size_t)Q_DY2 * mb, sc->nblk_row);
-  double dx2 = cta_sum_partials(partials + (size_t)Q_DX2 * mb, sc->nblk_col);
-  double dxd = cta_sum_partials(partials + (size_t)Q_DXDATY * mb, sc->nblk_col);
+  double dx2 = cols_from_sums ? row_sums[Q_DX2] : cta_sum_partials(partials + (size_t)Q_DX2 * mb, sc->nblk_col);
+  double dxd = cols_from_sums ? row_sums[Q_DXDATY]
+                              : cta_sum_partials(partials + (size_t)Q_DXDATY * mb, sc->nblk_col);
   if (threadIdx.x == 0 && sc->k_base == 0) {
     double fp = fixed_point_error(sc, dx2, dxd, dy2);
     sc->fp0 = fp;
@@ -67,14 +72,14 @@ __global__ void __launch_bounds__(kThreads) k_ctrl_first(Scalars* sc, const doub
 
 // after the LAST iteration of a block: KKT test, restart test, primal-weight update
 __global__ void __launch_bounds__(kThreads) k_ctrl_check(Scalars* sc, const double* partials,
-                                                         const double* row_sums) {
+                                                         const double* row_sums, int cols_from_sums) {
   if (sc->done) return;
   const int mb = sc->max_blocks;
   double q[Q_COUNT];
   for (int i = 0; i < Q_COUNT; ++i) {
     const bool is_row = (i == Q_DY2 || i == Q_DY0 || i == Q_DOBJ_ROW || i == Q_PRES2 ||
                          i == Q_RAYD_ROW || i == Q_RAYD_ROWV || i == Q_RAYP_ROWV);
-    if (is_row && row_sums) q[i] = row_sums[i];
+    if (row_sums && (is_row || cols_from_sums)) q[i] = row_sums[i];
     else q[i] = cta_sum_partials(partials + (size_t)i * mb, is_row ? sc->nblk_row : sc->nblk_col);
   }
   if (threadIdx.x != 0) return;
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__(kThreads) k_ctrl_check(Scalars* sc, const doub
 }
 
 // new anchor z0 <- (xhat_chk, yhat); re-seed the iteration from it (also used at solve start)
-__global__ void k_restart_apply(const Scalars* sc, int n, int m, const double* __restrict__ xcand,
+__global__ void k_restart_apply(const Scalars* sc, int j_begin, int n, int m, const double* __restrict__ xcand,
                                 const double* __restrict__ aty_cand, const double* __restrict__ yhat,
                                 const double* __restrict__ c, const double* __restrict__ l,
                                 const double* __restrict__ u, double* __restrict__ x0,
@@ -154,7 +159,7 @@ __global__ void k_restart_apply(const Scalars* sc, int n, int m, const double* _
   if (sc->done || !sc->restart_flag) return;
   const double tau = sc->tau;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
+  if (i >= j_begin && i < n) {          // [j_begin, n): this rank's column slice (everything if not sharded)
     const double x = xcand[i], at = aty_cand[i];
     x0[i] = x;
     aty0[i] = at;
@@ -301,8 +306,16 @@ void row_step(mipcu_ctx* ctx, int i, bool check, bool keep_kx = false) {
 void col_step(mipcu_ctx* ctx, int i, bool check, const double* xhat_in, double* xhat_out) {
   if (ctx->n == 0) return;
   ColStepArgs a = col_args(ctx, i, xhat_in, xhat_out);
+  if (p2p_active(ctx)) {
+    // row-sharded, fused exchange: local partial K_g' yhat_g, then ONE kernel that pulls this rank's
+    // slice of every partial over NVLink, runs the primal step on it and pushes xbar to the peers
+    spmv_plain(ctx, ctx->cols, ctx->yhat, ctx->tmp_n);
+    p2p_primal_step(ctx, a, check, xhat_out != nullptr);
+    if (xhat_out == ctx->xhat_chk) p2p_allgather(ctx, 1);   // gathered by the KKT pass: must be whole
+    return;
+  }
   if (ctx->world > 1) {
-    // row-sharded: local partial K_g' yhat_g -> all-reduce over NVLink -> elementwise primal step
+    // row-sharded, NCCL variant: local partial -> all-reduce over NVLink -> elementwise primal step
     // (replicated: every rank computes the same xbar from the same summed vector)
     spmv_plain(ctx, ctx->cols, ctx->yhat, ctx->tmp_n);
     dist_allreduce(ctx, ctx->tmp_n, (size_t)ctx->n, false);
@@ -323,7 +336,8 @@ void col_step(mipcu_ctx* ctx, int i, bool check, const double* xhat_in, double* 
 // row-sharded check iterations: make the row-side sums global before a controller runs
 const double* global_row_sums(mipcu_ctx* ctx) {
   if (ctx->world <= 1) return nullptr;
-  k_sum_row_partials<<<1, kThreads, 0, ctx->stream>>>(ctx->d_sc, ctx->partials, ctx->row_sums);
+  k_sum_partials<<<1, kThreads, 0, ctx->stream>>>(ctx->d_sc, ctx->partials, ctx->row_sums,
+                                                  p2p_active(ctx) ? 1 : 0);
   ctx->launches++;
   dist_allreduce(ctx, ctx->row_sums, Q_COUNT, false);
   return ctx->row_sums;
@@ -338,10 +352,13 @@ void kkt_row(mipcu_ctx* ctx) {
 void restart_apply(mipcu_ctx* ctx) {
   const int nm = std::max(ctx->n, ctx->m);
   if (nm == 0) return;
+  const bool p2p = p2p_active(ctx);
+  const int j0 = p2p ? ctx->peers.j0[ctx->rank] : 0, j1 = p2p ? ctx->peers.j0[ctx->rank + 1] : ctx->n;
   k_restart_apply<<<grid_for(nm), kThreads, 0, ctx->stream>>>(
-      ctx->d_sc, ctx->n, ctx->m, ctx->xhat_chk, ctx->aty_cand, ctx->yhat, ctx->cs, ctx->ls, ctx->us,
+      ctx->d_sc, j0, j1, ctx->m, ctx->xhat_chk, ctx->aty_cand, ctx->yhat, ctx->cs, ctx->ls, ctx->us,
       ctx->x0, ctx->aty0, ctx->aty, ctx->xhat_first, ctx->xbar, ctx->y0, ctx->y);
   ctx->launches++;
+  if (p2p) p2p_allgather(ctx, 0);   // every rank re-seeded its slice of xbar: make it whole again
 }
 
 // One block = `period` iterations.  Iteration 0 and period-1 are "check" iterations (partial sums);
@@ -364,11 +381,13 @@ void enqueue_block(mipcu_ctx* ctx, int period, cudaEvent_t* time_events) {
     col_step(ctx, i, first || last, xin, xout);
     if (timed) MIPCU_CK(cudaEventRecord(time_events[2], st));
     if (first) {
-      k_ctrl_first<<<1, kThreads, 0, st>>>(ctx->d_sc, ctx->partials, global_row_sums(ctx));
+      k_ctrl_first<<<1, kThreads, 0, st>>>(ctx->d_sc, ctx->partials, global_row_sums(ctx),
+                                           p2p_active(ctx) ? 1 : 0);
       ctx->launches++;
     }
   }
-  k_ctrl_check<<<1, kThreads, 0, st>>>(ctx->d_sc, ctx->partials, global_row_sums(ctx));
+  k_ctrl_check<<<1, kThreads, 0, st>>>(ctx->d_sc, ctx->partials, global_row_sums(ctx),
+                                       p2p_active(ctx) ? 1 : 0);
   ctx->launches++;
   restart_apply(ctx);
 }
@@ -401,6 +420,8 @@ void init_iterate(mipcu_ctx* ctx, Scalars& h) {
   h.restart_flag = 1;
   h.nblk_row = grid_for(m, tma_usable(ctx, ctx->rows, 4) ? kTileRows : kRowsPerCta);
   h.nblk_col = grid_for(n, tma_usable(ctx, ctx->cols, 7) ? kTileRows : kRowsPerCta);
+  if (p2p_active(ctx))   // the sharded primal kernel reduces over this rank's column slice only
+    h.nblk_col = std::max(1, grid_for(ctx->peers.j0[ctx->rank + 1] - ctx->peers.j0[ctx->rank], kRowsPerCta));
   h.max_blocks = ctx->max_blocks;
   // kernel variants write different ranges of the partial arrays: never sum a stale entry
   MIPCU_CK(cudaMemsetAsync(ctx->partials, 0, sizeof(double) * Q_COUNT * ctx->max_blocks, st));

@@ -10,19 +10,21 @@ from oracle import gen, kkt_verify
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, uid, which, out):
+def _worker(rank, world, uid, which, exchange, out):
     from miplib_b200 import Engine, sharding
     L = gen.lp(3000, 5000, 8, 21) if which == "small" else gen.config(2)
     ptr, idx, val, lo, hi = sharding.shard_csr(L.A, L.row_lo, L.row_hi, rank, world)
     with Engine(rank, rank, world, uid) as e:
+        e.set_param("shard_exchange", exchange)       # 1: fused P2P kernel, 0: ncclAllReduce
         e.load(ptr, idx, val, L.c, L.lb, L.ub, lo, hi, L.maximize, n=L.n)
         st = e.solve()
         out[rank] = (st.status, st.primal_obj, st.iterations, st.restarts, e.x(), e.y(),
                      st.rel_primal_res, st.rel_gap)
 
 
+@pytest.mark.parametrize("exchange", [1, 0])
 @pytest.mark.parametrize("which", ["small", "C2"])
-def test_two_rank_solve_matches_single_gpu(built, which):
+def test_two_rank_solve_matches_single_gpu(built, which, exchange):
     from miplib_b200 import Engine
     if Engine.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -30,7 +32,7 @@ def test_two_rank_solve_matches_single_gpu(built, which):
     uid = Engine.unique_id()
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(world, uid, which, out), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, uid, which, exchange, out), nprocs=world, join=True)
         res = dict(out)
     L = gen.lp(3000, 5000, 8, 21) if which == "small" else gen.config(2)
     with Engine(0) as e:
