@@ -214,6 +214,7 @@ def run_cuda(args, rank, world, local_rank):
         uid = [Engine.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         eng = Engine(local_rank, rank, world, uid[0])
+        eng.set_param("shard_exchange", args.shard_exchange)
     else:
         eng = Engine(local_rank)
 
@@ -284,7 +285,9 @@ def run_cuda(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": workload_name(args.config), "m": m, "n": n, "nnz": int(A.nnz),
                    "l2": "inputs larger than L2 (no flush)" if A.nnz > 8e6 else "L2-resident working set",
-                   "parallelism": "single GPU" if world == 1 else f"row-sharded x{world}, NCCL all-reduce of K'y"},
+                   "parallelism": "single GPU" if world == 1 else
+                   f"row-sharded x{world}, " + ("fused P2P reduce-scatter + primal step + all-gather kernel over NVLink"
+                                                 if eng.get_param("shard_exchange") == 1 else "NCCL all-reduce of K'y")},
         "time_to_tol_s": resident_s / args.steps,
         "iterations_per_solve": iters / args.steps,
         "device_iter_seconds_per_solve": dev_iter_s / args.steps,
@@ -398,6 +401,8 @@ def main():
     ap.add_argument("--workload", default="lp", choices=["lp", "nodes"])
     ap.add_argument("--nodes-per-gpu", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-exchange", type=int, default=1, choices=[0, 1],
+                    help="N > 1: 1 = fused P2P exchange kernel (default), 0 = ncclAllReduce")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -205,6 +205,7 @@ void p2p_setup(mipcu_ctx* ctx) {
   if (agreed < W - 0.5) {
     for (void* p : ctx->peer_mappings) cudaIpcCloseMemHandle(p);
     ctx->peer_mappings.clear();
+    ctx->params[MIPCU_PARAM_SHARD_EXCHANGE] = 0;   // visible through mipcu_get_param: NCCL path in use
     return;
   }
   ctx->peers = t;

@@ -17,6 +17,7 @@ def _worker(rank, world, uid, which, exchange, out):
     with Engine(rank, rank, world, uid) as e:
         e.set_param("shard_exchange", exchange)       # 1: fused P2P kernel, 0: ncclAllReduce
         e.load(ptr, idx, val, L.c, L.lb, L.ub, lo, hi, L.maximize, n=L.n)
+        assert e.get_param("shard_exchange") == exchange      # no silent fall-back to NCCL
         st = e.solve()
         out[rank] = (st.status, st.primal_obj, st.iterations, st.restarts, e.x(), e.y(),
                      st.rel_primal_res, st.rel_gap)
