@@ -60,7 +60,8 @@ enum {
   MIPCU_PARAM_THREADS_PER_ROW = 8,/* 0 auto; else 2,4,8,16,32 sub-warp width for both SpMVs */
   MIPCU_PARAM_OBJ_CUTOFF = 9,     /* stop with MIPCU_CUTOFF once the dual bound proves the optimum is no
                                      better than this objective value (model's own sense); NaN = off */
-  MIPCU_PARAM_USE_TMA = 10,       /* -1 auto (default), 0: LSU-streamed kernels, 1: TMA-streamed kernels */
+  MIPCU_PARAM_USE_TMA = 10,       /* kernel variant: -1 auto (default), 0: sub-warp per row, 1: TMA-streamed tiles,
+                                     2: CSR-stream (products staged in shared memory) */
   MIPCU_PARAM_SHARD_EXCHANGE = 11,/* row-sharded contexts: 1 (default) fused reduce-scatter + primal step +
                                      all-gather kernel over NVLink peer memory; 0: ncclAllReduce. Set before load */
   MIPCU_PARAM_COUNT_ = 12

@@ -44,6 +44,7 @@ struct Csr {
   double* val = nullptr;   // nnz (+ padding)
   int tpr = 8;             // threads per row chosen for this matrix
   int tile_cap = 0;        // TMA kernels: entries one 64-row tile needs in shared memory (0: n/a)
+  int stream_cap = 0;      // CSR-stream kernels: most nonzeros in one 256-row tile
 };
 
 // Quantities reduced per CTA on check iterations: partials[q * max_blocks + blockIdx.x].

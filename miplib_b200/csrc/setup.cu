@@ -272,20 +272,20 @@ void build_transpose(mipcu_ctx* ctx, const Csr& A, Csr& T) {
 
 // entries a 64-row tile of A occupies in the TMA kernels' shared-memory stage (its nonzeros plus the
 // slack of aligning the slice to 16 bytes), maximised over the tiles
-__global__ void k_tile_max(const int* __restrict__ ptr, int nrows, int* out) {
+__global__ void k_tile_max(const int* __restrict__ ptr, int nrows, int tile_rows, int* out) {
   const int tile = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r0 = tile * 64;
+  const int r0 = tile * tile_rows;
   if (r0 >= nrows) return;
-  const int r1 = min(r0 + 64, nrows);
+  const int r1 = min(r0 + tile_rows, nrows);
   const int kb = ptr[r0] & ~3;
   atomicMax(out, ((ptr[r1] - kb) + 3) & ~3);
 }
 
-int tile_capacity(mipcu_ctx* ctx, const Csr& A) {
+int tile_capacity(mipcu_ctx* ctx, const Csr& A, int tile_rows = 64) {
   if (A.nrows == 0) return 0;
   int* d = dalloc<int>(1);
   MIPCU_CK(cudaMemsetAsync(d, 0, sizeof(int), ctx->stream));
-  k_tile_max<<<grid_for(grid_for(A.nrows, 64)), kThreads, 0, ctx->stream>>>(A.ptr, A.nrows, d);
+  k_tile_max<<<grid_for(grid_for(A.nrows, tile_rows)), kThreads, 0, ctx->stream>>>(A.ptr, A.nrows, tile_rows, d);
   ctx->launches++;
   int h = 0;
   MIPCU_CK(cudaMemcpyAsync(&h, d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -425,6 +425,8 @@ void load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* r
   ctx->max_blocks = std::max(1024, std::max(grid_for(m, 64), grid_for(n, 64)));   // 64 = TMA tile rows
   A.tile_cap = tile_capacity(ctx, A);
   ctx->cols.tile_cap = tile_capacity(ctx, ctx->cols);
+  A.stream_cap = tile_capacity(ctx, A, kRowsPerCta);
+  ctx->cols.stream_cap = tile_capacity(ctx, ctx->cols, kRowsPerCta);
   ctx->partials = dalloc<double>((int64_t)Q_COUNT * ctx->max_blocks);
   MIPCU_CK(cudaMemsetAsync(ctx->partials, 0, sizeof(double) * Q_COUNT * ctx->max_blocks, st));
   if (n) { k_fill<<<grid_for(n), kThreads, 0, st>>>(ctx->d2, 1.0, (int)n); ctx->launches++; }

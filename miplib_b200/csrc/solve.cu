@@ -7,6 +7,7 @@
 
 #include "internal.h"
 #include "kernels.cuh"
+#include "kernels_stream.cuh"
 #include "kernels_tma.cuh"
 
 namespace mipcu {
@@ -227,6 +228,18 @@ bool tma_usable(const mipcu_ctx* ctx, const Csr& A, int nv) {
   return tma_smem_bytes(A.tile_cap, nv) <= 96 * 1024;   // keeps >= 2 CTAs per SM resident
 }
 
+// CSR-stream variants (kernels_stream.cuh): the tile's products live in shared memory
+bool stream_usable(const mipcu_ctx* ctx, const Csr& A) {
+  const int mode = (int)ctx->params[MIPCU_PARAM_USE_TMA];
+  if (mode != 2 || A.stream_cap <= 0 || ctx->world > 1) return false;
+  return stream_smem_bytes(A.stream_cap) <= 110 * 1024;   // >= 2 CTAs per SM
+}
+
+template <class Kernel>
+void allow_smem(Kernel kernel, size_t smem) {
+  MIPCU_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
+
 template <class Kernel>
 int persistent_grid(mipcu_ctx* ctx, Kernel kernel, size_t smem, int ntiles) {
   MIPCU_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -250,8 +263,26 @@ void launch_row(mipcu_ctx* ctx, const RowStepArgs& a, bool check) {
     return;
   }
   const int g = grid_for(ctx->m, kRowsPerCta);
+  if (stream_usable(ctx, ctx->rows)) {
+    const size_t smem = stream_smem_bytes(ctx->rows.stream_cap);
+    if (check) {
+      allow_smem(k_row_step_stream<TPR, true>, smem);
+      k_row_step_stream<TPR, true><<<g, kThreads, smem, ctx->stream>>>(a);
+    } else {
+      allow_smem(k_row_step_stream<TPR, false>, smem);
+      k_row_step_stream<TPR, false><<<g, kThreads, smem, ctx->stream>>>(a);
+    }
+    return;
+  }
   if (check) k_row_step<TPR, true><<<g, kThreads, 0, ctx->stream>>>(a);
   else k_row_step<TPR, false><<<g, kThreads, 0, ctx->stream>>>(a);
+}
+
+template <int TPR, bool CHECK, bool STORE>
+void launch_col_stream(mipcu_ctx* ctx, const ColStepArgs& a) {
+  const size_t smem = stream_smem_bytes(ctx->cols.stream_cap);
+  allow_smem(k_col_step_stream<TPR, CHECK, STORE>, smem);
+  k_col_step_stream<TPR, CHECK, STORE><<<grid_for(ctx->n, kRowsPerCta), kThreads, smem, ctx->stream>>>(a);
 }
 
 template <int TPR, bool CHECK, bool STORE>
@@ -269,6 +300,13 @@ void launch_col(mipcu_ctx* ctx, const ColStepArgs& a, bool check, bool store) {
     else if (check) launch_col_tma<TPR, true, false>(ctx, a);
     else if (store) launch_col_tma<TPR, false, true>(ctx, a);
     else launch_col_tma<TPR, false, false>(ctx, a);
+    return;
+  }
+  if (stream_usable(ctx, ctx->cols)) {
+    if (check && store) launch_col_stream<TPR, true, true>(ctx, a);
+    else if (check) launch_col_stream<TPR, true, false>(ctx, a);
+    else if (store) launch_col_stream<TPR, false, true>(ctx, a);
+    else launch_col_stream<TPR, false, false>(ctx, a);
     return;
   }
   const int g = grid_for(ctx->n, kRowsPerCta);

@@ -338,7 +338,12 @@ def test_tma_and_lsu_kernels_agree_bit_for_bit(engine):
         engine.set_param("use_tma", 1)
         xb, yb = engine.debug_iterate(50)
         sb = engine.solve()
+        engine.set_param("use_tma", 2)            # CSR-stream: product-then-add, so rounding differs
+        xc, yc = engine.debug_iterate(50)
+        sc = engine.solve()
         engine.set_param("use_tma", -1)
+        assert np.abs(xa - xc).max() <= 1e-10 and np.abs(ya - yc).max() <= 1e-10
+        assert sc.status == "optimal" and rel(sa.primal_obj, sc.primal_obj) <= 1e-6
         assert np.array_equal(xa, xb) and np.array_equal(ya, yb)
         assert sa.status == sb.status == "optimal"
         assert rel(sa.primal_obj, sb.primal_obj) <= 1e-6
