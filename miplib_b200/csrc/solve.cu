@@ -4,6 +4,8 @@
 // Restated on the CPU by oracle/pdhg_ref.py: solve().
 #include <chrono>
 #include <cmath>
+#include <unordered_map>
+#include <utility>
 
 #include "internal.h"
 #include "kernels.cuh"
@@ -235,17 +237,30 @@ bool stream_usable(const mipcu_ctx* ctx, const Csr& A) {
   return stream_smem_bytes(A.stream_cap) <= 110 * 1024;   // >= 2 CTAs per SM
 }
 
+// cudaFuncSetAttribute / the occupancy query are driver calls: remember them per kernel FUNCTION
+// (the template parameter is only the pointer type, shared by many instantiations)
+std::unordered_map<const void*, std::pair<size_t, int>>& kernel_cache() {
+  static std::unordered_map<const void*, std::pair<size_t, int>> cache;   // kernel -> (smem, CTAs/SM)
+  return cache;
+}
+
 template <class Kernel>
 void allow_smem(Kernel kernel, size_t smem) {
+  auto& entry = kernel_cache()[reinterpret_cast<const void*>(kernel)];
+  if (smem <= entry.first) return;
   MIPCU_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  entry.first = smem;
 }
 
 template <class Kernel>
 int persistent_grid(mipcu_ctx* ctx, Kernel kernel, size_t smem, int ntiles) {
-  MIPCU_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  MIPCU_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
-  return std::max(1, std::min(ntiles, std::max(per_sm, 1) * ctx->sm_count));
+  auto& entry = kernel_cache()[reinterpret_cast<const void*>(kernel)];
+  if (smem != entry.first || entry.second == 0) {
+    MIPCU_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MIPCU_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&entry.second, kernel, kThreads, smem));
+    entry.first = smem;
+  }
+  return std::max(1, std::min(ntiles, std::max(entry.second, 1) * ctx->sm_count));
 }
 
 template <int TPR>
