@@ -9,7 +9,7 @@ out = {}
 with Engine(0) as e:
     e.load_lp(L)
     e.prepare()
-    for tma in (0, 1, 2):
+    for tma in (0,):
         e.set_param("use_tma", tma)
         for tpr in (4, 8):
             e.set_param("threads_per_row", tpr)
