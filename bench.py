@@ -139,6 +139,7 @@ def cpu_baseline(L, seconds_budget: float = 15.0):
     """The multi-core C port on the same LP: bounded number of iterations, all host cores."""
     from oracle import pdhg_ref, port
     t0 = time.perf_counter()
+    port.use_all_threads()
     S = pdhg_ref.prepare(L, step_size=0.998)     # scaling only (eta pinned: no power iteration)
     st = port.PortState(S)
     setup = time.perf_counter() - t0
@@ -158,6 +159,7 @@ def run_reference(args, rank):
     L = gen.config(args.config)
     per_step = []
     from oracle import pdhg_ref, port
+    port.use_all_threads()
     S = pdhg_ref.prepare(L, step_size=0.998)
     st = port.PortState(S)
     probe = st.iterate(2)
@@ -177,7 +179,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": workload_name(args.config)},
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.config), "m": L.m, "n": L.n, "nnz": L.nnz},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference's own SCIP / lp_solve backends are not installable offline; this arm "

@@ -28,6 +28,15 @@ int port_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1: the baseline asks for every host thread explicitly */
+void port_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 void port_spmv(int64_t nrows, const int64_t* ptr, const int32_t* idx, const double* val,
                const double* v, double* out) {
 #pragma omp parallel for schedule(static)

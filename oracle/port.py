@@ -35,6 +35,8 @@ def lib():
         L = C.CDLL(str(LIB))
         vp, i64, dbl = C.c_void_p, C.c_int64, C.c_double
         L.port_num_threads.restype = C.c_int
+        L.port_set_threads.argtypes = [C.c_int]
+        L.port_set_threads.restype = None
         L.port_spmv.argtypes = [i64, vp, vp, vp, vp, vp]
         L.port_spmv.restype = None
         L.port_row_step.argtypes = [i64] + [vp] * 9 + [dbl, dbl]
@@ -51,6 +53,14 @@ def _p(a):
 
 def num_threads() -> int:
     return lib().port_num_threads()
+
+
+def use_all_threads() -> int:
+    """Ignore an inherited OMP_NUM_THREADS (torchrun sets it to 1) and use every host thread."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().port_set_threads(n)
+    return num_threads()
 
 
 class PortState:
