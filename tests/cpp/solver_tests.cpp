@@ -241,6 +241,7 @@ GPU_TEST("Generated models through the expression API match the exact-solver gol
     double expected, tol;
     in >> maximize >> expected >> tol;
     solver.set_time_limit(150);   // a runaway tree must fail the test, not hang it
+    if (char const* gpus = std::getenv("MIPLIB_TEST_GPUS")) solver.set_nr_threads(std::atoi(gpus));
     auto const t_begin = std::chrono::steady_clock::now();
     auto [r, has_solution] = maximize ? solver.maximize(objective) : solver.minimize(objective);
     double const secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();

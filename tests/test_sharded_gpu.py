@@ -47,3 +47,19 @@ def test_two_rank_solve_matches_single_gpu(built, which, exchange):
     y = np.concatenate([res[0][5], res[1][5]])
     cert = kkt_verify.certificate(L, res[0][4], y)
     assert max(cert["rel_primal_res"], cert["rel_dual_res"], cert["rel_gap"]) <= 1.05e-6, cert
+
+
+def test_branch_and_bound_deals_node_rounds_to_two_gpus(built, golden, tmp_path):
+    """set_nr_threads(2): every round of node LPs is split between two contexts (one per GPU) by
+    host threads; the proven optimum must not change."""
+    from miplib_b200 import Engine
+    if Engine.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from tests.test_frontend import run_unit_test, write_models
+    models = [("setcover_400x1000_mip", gen.set_cover(400, 1000, 8, 20264), golden["setcover_400x1000_mip"]["objective"], 1e-9),
+              ("mkp_5x60_mip", gen.mkp(5, 60, 4, 4, 20265), golden["mkp_5x60_mip"]["objective"], 1e-9)]
+    path = tmp_path / "models.txt"
+    write_models(path, models)
+    rc, out = run_unit_test(built, "--filter", "Generated", env={"MIPLIB_TEST_MODELS": str(path), "MIPLIB_TEST_GPUS": "2"})
+    print(out)
+    assert rc == 0 and "1 passed" in out, out
