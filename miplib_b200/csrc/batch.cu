@@ -37,6 +37,7 @@ struct BatchArgs {
   const double *l, *u;                      // [n][BP] scaled boxes
   double *xbar, *x0, *aty, *aty0, *xhat_first, *xhat_chk, *aty_cand;   // [n][BP]
   double *y, *y0, *yhat;                                              // [m][BP]
+  double *kx_save;                          // [m][BP] K xbar of the last iteration of a block (ray test)
   Scalars* sc;                              // [BP]
   double* partials;                         // [Q_COUNT][nblk_max][BP]
   int m, n, BP, nblk_max;
@@ -79,7 +80,7 @@ __device__ __forceinline__ void batch_reduce_store(double (&red)[NQ], const int 
 }
 
 template <bool CHECK>
-__global__ void __launch_bounds__(kThreads) k_row_step_batch(const BatchArgs a, int iter_in_block) {
+__global__ void __launch_bounds__(kThreads) k_row_step_batch(const BatchArgs a, int iter_in_block, int keep_kx) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y * 32 + lane;
   const Scalars* sc = a.sc + b;
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(kThreads) k_row_step_batch(const BatchArgs a, 
   const double sigma = sc->sigma;
   const double k = (double)(sc->k_base + iter_in_block);
   const double w_new = (k + 1.0) / (k + 2.0);
-  double red[3] = {0.0, 0.0, 0.0};
+  double red[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   if (__any_sync(0xffffffffu, active)) {
     for (int i = 0; i < kRowsPerCtaB / kWarps; ++i) {
       const int row = blockIdx.x * kRowsPerCtaB + warp * (kRowsPerCtaB / kWarps) + i;
@@ -105,12 +106,17 @@ __global__ void __launch_bounds__(kThreads) k_row_step_batch(const BatchArgs a, 
         red[0] += dy * dy;
         red[1] += d0 * d0;
         red[2] += (isfinite(lo) ? lo * fmax(yh, 0.0) : 0.0) - (isfinite(hi) ? hi * fmax(-yh, 0.0) : 0.0);
+        const double dp = fmax(dy, 0.0), dm = fmax(-dy, 0.0);
+        red[3] += (isfinite(lo) ? lo * dp : 0.0) - (isfinite(hi) ? hi * dm : 0.0);
+        const double rv = (isfinite(lo) ? 0.0 : dp) + (isfinite(hi) ? 0.0 : dm);
+        red[4] += rv * rv;
+        if (keep_kx) a.kx_save[e] = kx;
       }
     }
   }
   if (CHECK) {
-    const int q[3] = {Q_DY2, Q_DY0, Q_DOBJ_ROW};
-    batch_reduce_store<3>(red, q, a, b);
+    const int q[5] = {Q_DY2, Q_DY0, Q_DOBJ_ROW, Q_RAYD_ROW, Q_RAYD_ROWV};
+    batch_reduce_store<5>(red, q, a, b);
   }
 }
 
@@ -118,7 +124,7 @@ __global__ void __launch_bounds__(kThreads) k_row_step_batch(const BatchArgs a, 
 // row's nonzeros and the partial sums meet in shared memory; warp 0 runs the epilogue.  Fixed
 // summation order (warp 0..7), so still bit-reproducible.  MODE 0: row step, MODE 1: KKT residual.
 template <bool CHECK, int MODE>
-__global__ void __launch_bounds__(kThreads) k_row_batch_long(const BatchArgs a, int iter_in_block) {
+__global__ void __launch_bounds__(kThreads) k_row_batch_long(const BatchArgs a, int iter_in_block, int keep_kx) {
   __shared__ double s_part[kWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y * 32 + lane;
@@ -146,11 +152,15 @@ __global__ void __launch_bounds__(kThreads) k_row_batch_long(const BatchArgs a, 
   for (int w = 0; w < kWarps; ++w) kx += s_part[w][lane];
   const size_t slot = (size_t)row * a.BP + b;       // partial index: one entry per row
   if (MODE == 1) {
-    const double v = (kx - clampd(kx, a.lo[row], a.hi[row])) / a.d1[row];
+    const double lo = a.lo[row], hi = a.hi[row];
+    const double v = (kx - clampd(kx, lo, hi)) / a.d1[row];
     a.partials[((size_t)Q_PRES2 * a.nblk_max + row) * a.BP + b] = v * v;
+    const double kdx = a.kx_save[slot] - kx;
+    const double rv = (isfinite(lo) ? fmax(-kdx, 0.0) : 0.0) + (isfinite(hi) ? fmax(kdx, 0.0) : 0.0);
+    a.partials[((size_t)Q_RAYP_ROWV * a.nblk_max + row) * a.BP + b] = rv * rv;
     return;
   }
-  double red[3] = {0.0, 0.0, 0.0};
+  double red[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   if (active) {
     const double sigma = sc->sigma;
     const double kk = (double)(sc->k_base + iter_in_block);
@@ -165,12 +175,19 @@ __global__ void __launch_bounds__(kThreads) k_row_batch_long(const BatchArgs a, 
       red[0] = dy * dy;
       red[1] = d0 * d0;
       red[2] = (isfinite(lo) ? lo * fmax(yh, 0.0) : 0.0) - (isfinite(hi) ? hi * fmax(-yh, 0.0) : 0.0);
+      const double dp = fmax(dy, 0.0), dm = fmax(-dy, 0.0);
+      red[3] = (isfinite(lo) ? lo * dp : 0.0) - (isfinite(hi) ? hi * dm : 0.0);
+      const double rv = (isfinite(lo) ? 0.0 : dp) + (isfinite(hi) ? 0.0 : dm);
+      red[4] = rv * rv;
+      if (keep_kx) a.kx_save[slot] = kx;
     }
   }
   if (CHECK) {
     a.partials[((size_t)Q_DY2 * a.nblk_max + row) * a.BP + b] = red[0];
     a.partials[((size_t)Q_DY0 * a.nblk_max + row) * a.BP + b] = red[1];
     a.partials[((size_t)Q_DOBJ_ROW * a.nblk_max + row) * a.BP + b] = red[2];
+    a.partials[((size_t)Q_RAYD_ROW * a.nblk_max + row) * a.BP + b] = red[3];
+    a.partials[((size_t)Q_RAYD_ROWV * a.nblk_max + row) * a.BP + b] = red[4];
   }
 }
 
@@ -184,7 +201,7 @@ k_col_step_batch(const BatchArgs a, int iter_in_block, const double* xhat_in, do
   const double tau = sc->tau;
   const double k = (double)(sc->k_base + iter_in_block);
   const double w_new = (k + 1.0) / (k + 2.0);
-  double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  double red[10] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (__any_sync(0xffffffffu, active)) {
     for (int i = 0; i < kRowsPerCtaB / kWarps; ++i) {
       const int j = blockIdx.x * kRowsPerCtaB + warp * (kRowsPerCtaB / kWarps) + i;
@@ -207,6 +224,13 @@ k_col_step_batch(const BatchArgs a, int iter_in_block, const double* xhat_in, do
         red[4] += cj * xh;
         red[5] += (isfinite(lj) ? lj * rp : 0.0) - (isfinite(uj) ? uj * rm : 0.0);
         a.aty_cand[e] = atyh;
+        const double qp = fmax(-dat, 0.0), qm = fmax(dat, 0.0);
+        red[6] += (isfinite(lj) ? lj * qp : 0.0) - (isfinite(uj) ? uj * qm : 0.0);
+        const double qv = (isfinite(lj) ? 0.0 : qp) + (isfinite(uj) ? 0.0 : qm);
+        red[7] += qv * qv;
+        red[8] += cj * dx;
+        const double pv = (isfinite(lj) ? fmax(-dx, 0.0) : 0.0) + (isfinite(uj) ? fmax(dx, 0.0) : 0.0);
+        red[9] += pv * pv;
       }
       const double xn = w_new * xb + (1.0 - w_new) * x0;
       const double atn = w_new * (2.0 * atyh - at) + (1.0 - w_new) * at0;
@@ -217,8 +241,9 @@ k_col_step_batch(const BatchArgs a, int iter_in_block, const double* xhat_in, do
     }
   }
   if (CHECK) {
-    const int q[6] = {Q_DX2, Q_DXDATY, Q_DX0, Q_DRES2, Q_POBJ, Q_DOBJ_COL};
-    batch_reduce_store<6>(red, q, a, b);
+    const int q[10] = {Q_DX2, Q_DXDATY, Q_DX0, Q_DRES2, Q_POBJ, Q_DOBJ_COL,
+                       Q_RAYD_COL, Q_RAYD_COLV, Q_RAYP_C, Q_RAYP_COLV};
+    batch_reduce_store<10>(red, q, a, b);
   }
 }
 
@@ -226,18 +251,22 @@ __global__ void __launch_bounds__(kThreads) k_kkt_row_batch(const BatchArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y * 32 + lane;
   const bool active = !a.sc[b].done;
-  double red[1] = {0.0};
+  double red[2] = {0.0, 0.0};
   if (__any_sync(0xffffffffu, active)) {
     for (int i = 0; i < kRowsPerCtaB / kWarps; ++i) {
       const int row = blockIdx.x * kRowsPerCtaB + warp * (kRowsPerCtaB / kWarps) + i;
       if (row >= a.m) break;
       const double kx = row_dot_batch(a.rptr, a.ridx, a.rval, a.xhat_chk, row, a.BP, b);
-      const double v = (kx - clampd(kx, a.lo[row], a.hi[row])) / a.d1[row];
+      const double lo = a.lo[row], hi = a.hi[row];
+      const double v = (kx - clampd(kx, lo, hi)) / a.d1[row];
       red[0] += v * v;
+      const double kdx = a.kx_save[(size_t)row * a.BP + b] - kx;      // K (xbar - xhat) = K dx
+      const double rv = (isfinite(lo) ? fmax(-kdx, 0.0) : 0.0) + (isfinite(hi) ? fmax(kdx, 0.0) : 0.0);
+      red[1] += rv * rv;
     }
   }
-  const int q[1] = {Q_PRES2};
-  batch_reduce_store<1>(red, q, a, b);
+  const int q[2] = {Q_PRES2, Q_RAYP_ROWV};
+  batch_reduce_store<2>(red, q, a, b);
 }
 
 // sum over CTAs of one quantity for the 32 problems of this chunk (lane = problem)
@@ -275,7 +304,8 @@ __global__ void __launch_bounds__(kThreads) k_ctrl_check_batch(const BatchArgs a
   const int b = blockIdx.x * 32 + (threadIdx.x & 31);
   double q[Q_COUNT];
   for (int i = 0; i < Q_COUNT; ++i) {
-    const bool is_row = (i == Q_DY2 || i == Q_DY0 || i == Q_DOBJ_ROW || i == Q_PRES2);
+    const bool is_row = (i == Q_DY2 || i == Q_DY0 || i == Q_DOBJ_ROW || i == Q_PRES2 ||
+                         i == Q_RAYD_ROW || i == Q_RAYD_ROWV || i == Q_RAYP_ROWV);
     q[i] = batch_sum(a, i, is_row ? nblk_row : nblk_col, b);
   }
   Scalars* sc = a.sc + b;
@@ -296,6 +326,20 @@ __global__ void __launch_bounds__(kThreads) k_ctrl_check_batch(const BatchArgs a
   if (!(worst == worst) || isinf(worst)) { sc->done = 1 + MIPCU_NUMERICAL_ERROR; return; }
   if (worst <= sc->eps) { sc->done = 1 + MIPCU_OPTIMAL; return; }
   if (sc->rel_d <= sc->eps && dobj >= sc->cutoff) { sc->done = 1 + MIPCU_CUTOFF; return; }
+  {  // certificates of infeasibility from the displacement (same tests as k_ctrl_check)
+    const double nd = sqrt(q[Q_DY2]), nx = sqrt(q[Q_DX2]);
+    const double dval = nd > 1e-12 ? (q[Q_RAYD_ROW] + q[Q_RAYD_COL]) / nd : 0.0;
+    const double dviol = nd > 1e-12 ? sqrt(q[Q_RAYD_ROWV] + q[Q_RAYD_COLV]) / nd : 0.0;
+    const double pval = nx > 1e-12 ? q[Q_RAYP_C] / nx : 0.0;
+    const double pviol = nx > 1e-12 ? sqrt(q[Q_RAYP_COLV] + q[Q_RAYP_ROWV]) / nx : 0.0;
+    sc->ray_hits_dual = (dval > 1e-9 && dviol <= RAY_TOL * dval) ? sc->ray_hits_dual + 1 : 0;
+    sc->ray_hits_primal = (pval < -1e-9 && pviol <= RAY_TOL * -pval) ? sc->ray_hits_primal + 1 : 0;
+    if (sc->ray_hits_dual >= 2) { sc->done = 1 + MIPCU_INFEASIBLE; return; }
+    if (sc->ray_hits_primal >= 2) {
+      sc->done = 1 + (sc->rel_p <= 1e-4 ? MIPCU_UNBOUNDED : MIPCU_INFEASIBLE_OR_UNBOUNDED);
+      return;
+    }
+  }
   const bool restart = fp <= BETA_SUFFICIENT * sc->fp0 ||
                        (fp <= BETA_NECESSARY * sc->fp0 && fp > sc->fp_prev) ||
                        (double)k >= BETA_ARTIFICIAL * (double)sc->total;
@@ -418,6 +462,7 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
   a.aty0 = buf.get<double>(nB); a.xhat_first = buf.get<double>(nB); a.xhat_chk = buf.get<double>(nB);
   a.aty_cand = buf.get<double>(nB);
   a.y = buf.get<double>(mB); a.y0 = buf.get<double>(mB); a.yhat = buf.get<double>(mB);
+  a.kx_save = buf.get<double>(mB);
   a.sc = buf.get<Scalars>(BP);
   a.partials = buf.get<double>((size_t)Q_COUNT * nblk_max * BP);
   a.m = m; a.n = n; a.BP = BP; a.nblk_max = nblk_max;
@@ -466,13 +511,13 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
       const bool first = i == 0, last = i == period - 1;
       if (m && long_rows) {
         const dim3 g(m, BP / 32);
-        if (first || last) k_row_batch_long<true, 0><<<g, kThreads, 0, st>>>(a, i);
-        else k_row_batch_long<false, 0><<<g, kThreads, 0, st>>>(a, i);
+        if (first || last) k_row_batch_long<true, 0><<<g, kThreads, 0, st>>>(a, i, last ? 1 : 0);
+        else k_row_batch_long<false, 0><<<g, kThreads, 0, st>>>(a, i, 0);
         ctx->launches++;
-        if (last) { k_row_batch_long<false, 1><<<g, kThreads, 0, st>>>(a, i); ctx->launches++; }
+        if (last) { k_row_batch_long<false, 1><<<g, kThreads, 0, st>>>(a, i, 0); ctx->launches++; }
       } else if (m) {
-        if (first || last) k_row_step_batch<true><<<grid_rows, kThreads, 0, st>>>(a, i);
-        else k_row_step_batch<false><<<grid_rows, kThreads, 0, st>>>(a, i);
+        if (first || last) k_row_step_batch<true><<<grid_rows, kThreads, 0, st>>>(a, i, last ? 1 : 0);
+        else k_row_step_batch<false><<<grid_rows, kThreads, 0, st>>>(a, i, 0);
         ctx->launches++;
         if (last) { k_kkt_row_batch<<<grid_rows, kThreads, 0, st>>>(a); ctx->launches++; }
       }

@@ -308,6 +308,7 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
   std::priority_queue<Node, std::vector<Node>, decltype(by_bound)> open(by_bound);
   open.push(Node{{}, -kInf, 0, {}, {}});
   bool complete = true;
+  bool unbounded_relaxation = false;
   std::int64_t const node_limit = 4000000;
   std::size_t const per_gpu = 128;                       // node LPs per GPU per round
   std::size_t const round_cap = per_gpu * gpus.size();
@@ -398,6 +399,13 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
       S.m_info.lp_iterations += lp.iterations;
       std::vector<double> x(xs.begin() + b * n, xs.begin() + (b + 1) * n);
       if (lp.status == MIPCU_CUTOFF) continue;       // bound (or infeasibility) proven by the dual
+      if (lp.status == MIPCU_INFEASIBLE) continue;   // Farkas certificate from the engine
+      if (lp.status == MIPCU_UNBOUNDED || lp.status == MIPCU_INFEASIBLE_OR_UNBOUNDED)
+      {
+        unbounded_relaxation = true;                 // an unbounded node LP: no finite optimum to prove
+        complete = false;
+        continue;
+      }
       if (lp.status == MIPCU_NUMERICAL_ERROR) { complete = false; continue; }
       if (lp.status == MIPCU_TIME_LIMIT) { complete = false; continue; }
       double node_bound = node.bound;
@@ -454,6 +462,7 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
     }
   }
   S.m_info.best_bound = have_incumbent ? sgn * best : 0;
+  if (unbounded_relaxation && !have_incumbent) return {R::InfeasibleOrUnbounded, false};
   return finish(complete);
 }
 
