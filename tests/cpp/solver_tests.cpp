@@ -247,7 +247,9 @@ GPU_TEST("Generated models through the expression API match the exact-solver gol
     double const secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
     std::cout << "  " << label << ": result " << static_cast<int>(r) << " objective "
               << (has_solution ? solver.get_objective_value() : NAN) << " expected " << expected
-              << " in " << secs << " s" << std::endl;
+              << " in " << secs << " s  [nodes " << CudaSolver::of(solver).m_info.nodes << ", node LPs "
+              << CudaSolver::of(solver).m_info.lp_solves << ", PDHG iterations "
+              << CudaSolver::of(solver).m_info.lp_iterations << "]" << std::endl;
     REQUIRE(r == Solver::Result::Optimal && has_solution);
     REQUIRE(std::abs(solver.get_objective_value() - expected) <= tol * (1 + std::abs(expected)));
     REQUIRE(close(objective.value(), solver.get_objective_value(), 1e-9));
