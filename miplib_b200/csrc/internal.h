@@ -42,7 +42,15 @@ struct Csr {
   int* ptr = nullptr;      // nrows + 1
   int* idx = nullptr;      // nnz (+ padding)
   double* val = nullptr;   // nnz (+ padding)
-  int tpr = 8;             // threads per row chosen for this matrix
+  int tpr = 8;             // threads per row chosen for this matrix (CSR kernels)
+  // sliced-ELL copy of the SCALED matrix for the lane-per-row kernels (setup.cu:build_sell);
+  // null when the matrix is not eligible (long or badly unbalanced rows)
+  int* sptr = nullptr;              // 8 * nblk + 1 slice offsets (32 rows per slice)
+  int* sidx = nullptr;              // padded entries, -1 = padding
+  double* sval = nullptr;
+  unsigned char* perm = nullptr;    // 256 * nblk: sorted position -> CTA-local row
+  int64_t sell_entries = 0;         // padded entry count
+  bool sell = false;                // SELL copy present and selected
   int tile_cap = 0;        // TMA kernels: entries one 64-row tile needs in shared memory (0: n/a)
   int stream_cap = 0;      // CSR-stream kernels: most nonzeros in one 256-row tile
 };
@@ -169,6 +177,7 @@ void refresh_vectors(mipcu_ctx* ctx);   // scaled c / bounds / norms / w0 (after
 void spmv_plain(mipcu_ctx* ctx, const Csr& A, const double* v, double* out);
 double device_norm2(mipcu_ctx* ctx, const double* v, int64_t len);
 int choose_tpr(double avg_row_len, int override_tpr);
+int kernel_format(const mipcu_ctx* ctx, const Csr& A);   // 0: SELL lane-per-row, else CSR lanes per row
 void set_bounds(mipcu_ctx* ctx, int64_t n_changed, const int64_t* cols, const double* lb,
                 const double* ub);
 void spmv_host(mipcu_ctx* ctx, int transpose, const double* v, double* out);

@@ -35,42 +35,83 @@ __device__ __forceinline__ double clampd(double v, double lo, double hi) {
 }
 
 // Sum of A[row, :] * vec for the kRowsPerCta rows owned by this CTA, left in s_sum[0..kRowsPerCta).
-// TPR lanes cooperate on one row; a warp therefore streams 32/TPR consecutive rows, i.e. one
-// contiguous span of the val/idx arrays.  Two independent (val, idx, gather) chains per lane are
-// kept in flight to cover the L2 gather latency.
+//
+// Two storage formats share this entry point (the template parameter selects one):
+//
+//  TPR == 0: sliced ELL ("SELL-32-256", built by setup.cu:build_sell once the matrix is scaled).
+//    The 256 rows of a CTA are sorted by length; 32 consecutive rows of that order form a slice
+//    whose entries are stored lane-major (entry j of lane l at ptr[slice] + 32 j + l, padded to
+//    the slice's longest row with idx = -1).  One lane owns one row: the val / idx streams are
+//    perfectly coalesced, there is no shuffle reduction, no row-pointer dependency and no
+//    divergence inside a warp; kSellUnroll independent (val, idx, gather) chains per lane cover
+//    the L2 gather latency.  perm[] maps the sorted position back to the CTA-local row, so the
+//    vectors of the epilogue keep their natural order.  Measured on config 3 (scripts/spmv_lab.cu,
+//    profiles/r01_spmv_lab.md): row step 174 -> 140 us, col step 165 -> 137 us.
+//
+//  TPR in {2,4,8,16,32}: CSR with TPR lanes cooperating on one row (long or few rows, where one
+//    lane per row would leave the machine empty); a warp streams 32/TPR consecutive rows, two
+//    independent chains per lane.
+constexpr int kSellUnroll = 8;
+
 template <int TPR>
 __device__ __forceinline__ void cta_row_sums(const int* __restrict__ ptr,
                                              const int* __restrict__ idx,
                                              const double* __restrict__ val,
+                                             const unsigned char* __restrict__ perm,
                                              const double* __restrict__ vec, int nrows,
                                              double* s_sum) {
-  constexpr int SUBS = kThreads / TPR;        // rows in flight per pass
-  const int lane = threadIdx.x % TPR;
-  const int sub = threadIdx.x / TPR;
-  const int row0 = blockIdx.x * kRowsPerCta;
-#pragma unroll 2
-  for (int r = sub; r < kRowsPerCta; r += SUBS) {
-    const int row = row0 + r;
+  if constexpr (TPR == 0) {
+    constexpr int U = kSellUnroll;
+    const int lane = threadIdx.x & 31;
+    const int slice = blockIdx.x * (kRowsPerCta / 32) + (threadIdx.x >> 5);
+    const int beg = ptr[slice], end = ptr[slice + 1];
     double acc0 = 0.0, acc1 = 0.0;
-    if (row < nrows) {
-      const int b = ptr[row], e = ptr[row + 1];
-      int k = b + lane;
-      for (; k + TPR < e; k += 2 * TPR) {
-        const double v0 = ld_stream(val + k);
-        const int c0 = ld_stream(idx + k);
-        const double v1 = ld_stream(val + k + TPR);
-        const int c1 = ld_stream(idx + k + TPR);
-        acc0 = fma(v0, __ldg(vec + c0), acc0);
-        acc1 = fma(v1, __ldg(vec + c1), acc1);
-      }
-      if (k < e) acc0 = fma(ld_stream(val + k), __ldg(vec + ld_stream(idx + k)), acc0);
-    }
-    double acc = acc0 + acc1;
+    for (int p = beg + lane; p < end; p += 32 * U) {
+      double v[U];
+      int c[U];
 #pragma unroll
-    for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, TPR);
-    if (lane == 0) s_sum[r] = acc;
+      for (int u = 0; u < U; ++u) {
+        const bool ok = p + 32 * u < end;     // warp-uniform: a slice is padded to whole lanes
+        v[u] = ok ? ld_stream(val + p + 32 * u) : 0.0;
+        c[u] = ok ? ld_stream(idx + p + 32 * u) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const double x = c[u] >= 0 ? __ldg(vec + c[u]) : 0.0;
+        if (u & 1) acc1 = fma(v[u], x, acc1); else acc0 = fma(v[u], x, acc0);
+      }
+    }
+    s_sum[perm[blockIdx.x * kRowsPerCta + threadIdx.x]] = acc0 + acc1;
+    __syncthreads();
+  } else {
+    constexpr int SUBS = kThreads / TPR;        // rows in flight per pass
+    const int lane = threadIdx.x % TPR;
+    const int sub = threadIdx.x / TPR;
+    const int row0 = blockIdx.x * kRowsPerCta;
+#pragma unroll 2
+    for (int r = sub; r < kRowsPerCta; r += SUBS) {
+      const int row = row0 + r;
+      double acc0 = 0.0, acc1 = 0.0;
+      if (row < nrows) {
+        const int b = ptr[row], e = ptr[row + 1];
+        int k = b + lane;
+        for (; k + TPR < e; k += 2 * TPR) {
+          const double v0 = ld_stream(val + k);
+          const int c0 = ld_stream(idx + k);
+          const double v1 = ld_stream(val + k + TPR);
+          const int c1 = ld_stream(idx + k + TPR);
+          acc0 = fma(v0, __ldg(vec + c0), acc0);
+          acc1 = fma(v1, __ldg(vec + c1), acc1);
+        }
+        if (k < e) acc0 = fma(ld_stream(val + k), __ldg(vec + ld_stream(idx + k)), acc0);
+      }
+      double acc = acc0 + acc1;
+#pragma unroll
+      for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, TPR);
+      if (lane == 0) s_sum[r] = acc;
+    }
+    __syncthreads();
   }
-  __syncthreads();
 }
 
 // Deterministic CTA reduction of NQ running sums; thread 0 stores them to
@@ -97,7 +138,8 @@ __device__ __forceinline__ void cta_reduce_store(double (&v)[NQ], const int (&q)
 }
 
 struct RowStepArgs {
-  const int* ptr; const int* idx; const double* val;   // K by rows
+  const int* ptr; const int* idx; const double* val;   // K by rows (CSR, or SELL when TPR == 0)
+  const unsigned char* perm;                            // SELL: sorted position -> CTA-local row
   const double* xbar;                                   // gathered
   const double* lo; const double* hi; const double* y0;
   double* y; double* yhat;
@@ -112,7 +154,7 @@ k_row_step(const RowStepArgs a) {
   __shared__ double s_sum[kRowsPerCta];
   const Scalars* sc = a.sc;
   if (sc->done) return;
-  cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.xbar, a.m, s_sum);
+  cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.perm, a.xbar, a.m, s_sum);
   const double sigma = sc->sigma;
   const double k = (double)(sc->k_base + a.iter_in_block);
   const double w_new = (k + 1.0) / (k + 2.0);
@@ -146,7 +188,8 @@ k_row_step(const RowStepArgs a) {
 }
 
 struct ColStepArgs {
-  const int* ptr; const int* idx; const double* val;   // K by columns (CSR of K')
+  const int* ptr; const int* idx; const double* val;   // K by columns (CSR of K', or SELL)
+  const unsigned char* perm;
   const double* yhat;                                   // gathered
   const double* x0; const double* aty0; const double* c; const double* l; const double* u;
   const double* d2;
@@ -205,7 +248,7 @@ k_col_step(const ColStepArgs a) {
   __shared__ double s_sum[kRowsPerCta];
   const Scalars* sc = a.sc;
   if (sc->done) return;
-  cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.yhat, a.n, s_sum);
+  cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.perm, a.yhat, a.n, s_sum);
   const double tau = sc->tau;
   const double k = (double)(sc->k_base + a.iter_in_block);
   const double w_new = (k + 1.0) / (k + 2.0);
@@ -244,12 +287,12 @@ k_primal_step(const ColStepArgs a, const double* __restrict__ atyh) {
 template <int TPR>
 __global__ void __launch_bounds__(kThreads)
 k_kkt_row(const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
-          const double* __restrict__ xhat, const double* __restrict__ lo,
+          const unsigned char* __restrict__ perm, const double* __restrict__ xhat, const double* __restrict__ lo,
           const double* __restrict__ hi, const double* __restrict__ d1, const Scalars* sc,
           double* partials, int m, const double* __restrict__ kxbar) {
   __shared__ double s_sum[kRowsPerCta];
   if (sc->done) return;
-  cta_row_sums<TPR>(ptr, idx, val, xhat, m, s_sum);
+  cta_row_sums<TPR>(ptr, idx, val, perm, xhat, m, s_sum);
   const int i = blockIdx.x * kRowsPerCta + threadIdx.x;
   double red[2] = {0.0, 0.0};
   if (i < m) {
@@ -269,9 +312,9 @@ k_kkt_row(const int* __restrict__ ptr, const int* __restrict__ idx, const double
 template <int TPR>
 __global__ void __launch_bounds__(kThreads)
 k_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
-       const double* __restrict__ v, double* __restrict__ out, int nrows) {
+       const unsigned char* __restrict__ perm, const double* __restrict__ v, double* __restrict__ out, int nrows) {
   __shared__ double s_sum[kRowsPerCta];
-  cta_row_sums<TPR>(ptr, idx, val, v, nrows, s_sum);
+  cta_row_sums<TPR>(ptr, idx, val, perm, v, nrows, s_sum);
   const int i = blockIdx.x * kRowsPerCta + threadIdx.x;
   if (i < nrows) out[i] = s_sum[threadIdx.x];
 }

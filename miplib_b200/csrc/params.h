@@ -14,6 +14,7 @@ constexpr double BETA_ARTIFICIAL  = 0.36;    // restart if k >= 0.36 * total ite
 constexpr double WEIGHT_SMOOTHING = 0.5;     // theta of the primal-weight update
 constexpr double WEIGHT_EPS       = 1e-10;
 constexpr double RAY_TOL          = 1e-8;    // certificate violation allowed relative to its value
+constexpr double kSellMaxAvgRow   = 96.0;    // SELL (one lane per row) only for matrices with short rows
 constexpr double INF_THRESHOLD    = 1e20;    // |bound| >= this means "no bound" (MIPCU_INF)
 
 }  // namespace mipcu

@@ -223,9 +223,106 @@ double sumsq(mipcu_ctx* ctx, const double* a, const double* b, int64_t count) {
 template <int TPR>
 void launch_spmv(mipcu_ctx* ctx, const Csr& A, const double* v, double* out) {
   if (A.nrows == 0) return;
-  k_spmv<TPR><<<grid_for(A.nrows, kRowsPerCta), kThreads, 0, ctx->stream>>>(A.ptr, A.idx, A.val, v,
-                                                                           out, A.nrows);
+  const int g = grid_for(A.nrows, kRowsPerCta);
+  if (TPR == 0)
+    k_spmv<TPR><<<g, kThreads, 0, ctx->stream>>>(A.sptr, A.sidx, A.sval, A.perm, v, out, A.nrows);
+  else
+    k_spmv<TPR><<<g, kThreads, 0, ctx->stream>>>(A.ptr, A.idx, A.val, nullptr, v, out, A.nrows);
   ctx->launches++;
+}
+
+// ---- sliced ELL (SELL-32-256) ----------------------------------------------------------------
+// One CTA per block of 256 rows: stable sort of the rows by decreasing length (rank by counting,
+// 256 x 256 comparisons in shared memory), perm[sorted position] = CTA-local row, and the padded
+// size of each of the block's 8 slices (32 x the length of the slice's first = longest row).
+__global__ void __launch_bounds__(kThreads)
+k_sell_plan(const int* __restrict__ ptr, int nrows, unsigned char* __restrict__ perm,
+            long long* __restrict__ slice_size) {
+  __shared__ int s_len[kRowsPerCta];
+  __shared__ int s_sorted[kRowsPerCta];
+  const int t = threadIdx.x;
+  const int r = blockIdx.x * kRowsPerCta + t;
+  const int len = r < nrows ? ptr[r + 1] - ptr[r] : -1;    // rows past the end sort last
+  s_len[t] = len;
+  __syncthreads();
+  int rank = 0;
+  for (int o = 0; o < kRowsPerCta; ++o) {
+    const int lo = s_len[o];
+    rank += (lo > len) || (lo == len && o < t);
+  }
+  perm[blockIdx.x * kRowsPerCta + rank] = (unsigned char)t;
+  s_sorted[rank] = max(len, 0);
+  __syncthreads();
+  if (t < kRowsPerCta / 32) slice_size[blockIdx.x * (kRowsPerCta / 32) + t] = 32ll * s_sorted[32 * t];
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_sell_fill(const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
+            int nrows, const unsigned char* __restrict__ perm, const int* __restrict__ sptr,
+            int* __restrict__ sidx, double* __restrict__ sval) {
+  const int t = threadIdx.x, lane = t & 31;
+  const int r = blockIdx.x * kRowsPerCta + perm[blockIdx.x * kRowsPerCta + t];
+  const int slice = blockIdx.x * (kRowsPerCta / 32) + (t >> 5);
+  const int beg = sptr[slice], width = (sptr[slice + 1] - beg) / 32;
+  const int k0 = r < nrows ? ptr[r] : 0;
+  const int len = r < nrows ? ptr[r + 1] - k0 : 0;
+  for (int j = 0; j < width; ++j) {
+    sidx[beg + 32 * j + lane] = j < len ? idx[k0 + j] : -1;
+    sval[beg + 32 * j + lane] = j < len ? val[k0 + j] : 0.0;
+  }
+}
+
+__global__ void k_narrow_ll(const long long* in, int* out, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = (int)in[i];
+}
+
+void free_sell(Csr& A) {
+  dfree(A.sptr); dfree(A.sidx); dfree(A.sval);
+  if (A.perm) { cudaFree(A.perm); A.perm = nullptr; }
+  A.sell_entries = 0;
+  A.sell = false;
+}
+
+// Builds the SELL copy of the (already scaled) matrix.  Eligible: short rows on average (one lane
+// per row must still fill the machine) and a padded size within 35 % of the nonzero count.
+void build_sell(mipcu_ctx* ctx, Csr& A) {
+  free_sell(A);
+  if (A.nrows == 0 || A.nnz == 0) return;
+  if ((double)A.nnz / (double)A.nrows > kSellMaxAvgRow) return;
+  cudaStream_t st = ctx->stream;
+  const int nblk = grid_for(A.nrows, kRowsPerCta), nslices = nblk * (kRowsPerCta / 32);
+  MIPCU_CK(cudaMalloc(&A.perm, (size_t)nblk * kRowsPerCta));
+  long long* sizes = dalloc<long long>(nslices + 1);
+  long long* offs = dalloc<long long>(nslices + 1);
+  MIPCU_CK(cudaMemsetAsync(sizes, 0, sizeof(long long) * (nslices + 1), st));
+  k_sell_plan<<<nblk, kThreads, 0, st>>>(A.ptr, A.nrows, A.perm, sizes);
+  ctx->launches++;
+  size_t tmp_bytes = 0;
+  MIPCU_CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, sizes, offs, nslices + 1, st));
+  void* tmp = nullptr;
+  MIPCU_CK(cudaMalloc(&tmp, tmp_bytes + 16));
+  MIPCU_CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, sizes, offs, nslices + 1, st));
+  long long total = 0;
+  MIPCU_CK(cudaMemcpyAsync(&total, offs + nslices, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  MIPCU_CK(cudaStreamSynchronize(st));
+  cudaFree(tmp);
+  const bool ok = total < (1ll << 31) - 1024 && (double)total <= 1.35 * (double)A.nnz + 8192.0;
+  if (ok) {
+    A.sptr = dalloc<int>(nslices + 1);
+    A.sidx = dalloc<int>(total + 4);
+    A.sval = dalloc<double>(total + 4);
+    k_narrow_ll<<<grid_for(nslices + 1), kThreads, 0, st>>>(offs, A.sptr, nslices + 1);
+    k_sell_fill<<<nblk, kThreads, 0, st>>>(A.ptr, A.idx, A.val, A.nrows, A.perm, A.sptr, A.sidx, A.sval);
+    ctx->launches += 2;
+    MIPCU_CK(cudaStreamSynchronize(st));
+    A.sell_entries = total;
+    A.sell = true;
+  } else {
+    cudaFree(A.perm);
+    A.perm = nullptr;
+  }
+  dfree(sizes); dfree(offs);
 }
 
 // CSR of the transpose on the device: stable radix sort of (col, position) pairs, so the entries
@@ -295,6 +392,7 @@ int tile_capacity(mipcu_ctx* ctx, const Csr& A, int tile_rows = 64) {
 }
 
 void free_csr(Csr& A) {
+  free_sell(A);
   dfree(A.ptr); dfree(A.idx); dfree(A.val);
   A = Csr();
 }
@@ -312,8 +410,18 @@ int choose_tpr(double avg, int override_tpr) {
   return 32;
 }
 
+// Which kernel family a matrix runs through: the SELL copy when it exists and nothing asks for a
+// CSR variant (an explicit lanes-per-row override, or one of the opt-in TMA / CSR-stream kernels).
+int kernel_format(const mipcu_ctx* ctx, const Csr& A) {
+  const int tma = (int)ctx->params[MIPCU_PARAM_USE_TMA];
+  const int lanes = (int)ctx->params[MIPCU_PARAM_THREADS_PER_ROW];
+  if (A.sell && lanes == 0 && tma != 1 && tma != 2) return 0;
+  return A.tpr;
+}
+
 void spmv_plain(mipcu_ctx* ctx, const Csr& A, const double* v, double* out) {
-  switch (A.tpr) {
+  switch (kernel_format(ctx, A)) {
+    case 0: launch_spmv<0>(ctx, A, v, out); break;
     case 2: launch_spmv<2>(ctx, A, v, out); break;
     case 4: launch_spmv<4>(ctx, A, v, out); break;
     case 8: launch_spmv<8>(ctx, A, v, out); break;
@@ -468,6 +576,9 @@ void prepare(mipcu_ctx* ctx) {
       ctx->launches += 6;
     }
   }
+  // lane-per-row copies of the scaled matrix for the iteration kernels
+  build_sell(ctx, R);
+  build_sell(ctx, C);
   // step size
   double step = ctx->params[MIPCU_PARAM_STEP_SIZE];
   if (step > 0.0) {

@@ -203,7 +203,9 @@ __global__ void k_flush(double* buf, int64_t count) {
 
 RowStepArgs row_args(mipcu_ctx* ctx, int i) {
   RowStepArgs a;
-  a.ptr = ctx->rows.ptr; a.idx = ctx->rows.idx; a.val = ctx->rows.val;
+  const Csr& R = ctx->rows;
+  if (kernel_format(ctx, R) == 0) { a.ptr = R.sptr; a.idx = R.sidx; a.val = R.sval; a.perm = R.perm; }
+  else { a.ptr = R.ptr; a.idx = R.idx; a.val = R.val; a.perm = nullptr; }
   a.xbar = ctx->xbar; a.lo = ctx->los; a.hi = ctx->his; a.y0 = ctx->y0;
   a.y = ctx->y; a.yhat = ctx->yhat; a.sc = ctx->d_sc; a.partials = ctx->partials;
   a.m = ctx->m; a.iter_in_block = i;
@@ -213,7 +215,9 @@ RowStepArgs row_args(mipcu_ctx* ctx, int i) {
 
 ColStepArgs col_args(mipcu_ctx* ctx, int i, const double* xhat_in, double* xhat_out) {
   ColStepArgs a;
-  a.ptr = ctx->cols.ptr; a.idx = ctx->cols.idx; a.val = ctx->cols.val;
+  const Csr& C = ctx->cols;
+  if (kernel_format(ctx, C) == 0) { a.ptr = C.sptr; a.idx = C.sidx; a.val = C.sval; a.perm = C.perm; }
+  else { a.ptr = C.ptr; a.idx = C.idx; a.val = C.val; a.perm = nullptr; }
   a.yhat = ctx->yhat; a.x0 = ctx->x0; a.aty0 = ctx->aty0; a.c = ctx->cs; a.l = ctx->ls;
   a.u = ctx->us; a.d2 = ctx->d2; a.xbar = ctx->xbar; a.aty = ctx->aty; a.xhat_in = xhat_in;
   a.xhat_out = xhat_out; a.aty_cand = ctx->aty_cand; a.sc = ctx->d_sc;
@@ -334,9 +338,30 @@ void launch_col(mipcu_ctx* ctx, const ColStepArgs& a, bool check, bool store) {
 
 template <int TPR>
 void launch_kkt(mipcu_ctx* ctx) {
-  k_kkt_row<TPR><<<grid_for(ctx->m, kRowsPerCta), kThreads, 0, ctx->stream>>>(
-      ctx->rows.ptr, ctx->rows.idx, ctx->rows.val, ctx->xhat_chk, ctx->los, ctx->his, ctx->d1,
-      ctx->d_sc, ctx->partials, ctx->m, ctx->tmp_m);
+  const Csr& R = ctx->rows;
+  const int g = grid_for(ctx->m, kRowsPerCta);
+  if (TPR == 0)
+    k_kkt_row<TPR><<<g, kThreads, 0, ctx->stream>>>(R.sptr, R.sidx, R.sval, R.perm, ctx->xhat_chk,
+        ctx->los, ctx->his, ctx->d1, ctx->d_sc, ctx->partials, ctx->m, ctx->tmp_m);
+  else
+    k_kkt_row<TPR><<<g, kThreads, 0, ctx->stream>>>(R.ptr, R.idx, R.val, nullptr, ctx->xhat_chk,
+        ctx->los, ctx->his, ctx->d1, ctx->d_sc, ctx->partials, ctx->m, ctx->tmp_m);
+}
+
+// SELL (lane per row) launches: no TMA / CSR-stream variants exist for this format
+void launch_row_sell(mipcu_ctx* ctx, const RowStepArgs& a, bool check) {
+  const int g = grid_for(ctx->m, kRowsPerCta);
+  if (check) k_row_step<0, true><<<g, kThreads, 0, ctx->stream>>>(a);
+  else k_row_step<0, false><<<g, kThreads, 0, ctx->stream>>>(a);
+}
+
+void launch_col_sell(mipcu_ctx* ctx, const ColStepArgs& a, bool check, bool store) {
+  const int g = grid_for(ctx->n, kRowsPerCta);
+  cudaStream_t st = ctx->stream;
+  if (check && store) k_col_step<0, true, true><<<g, kThreads, 0, st>>>(a);
+  else if (check) k_col_step<0, true, false><<<g, kThreads, 0, st>>>(a);
+  else if (store) k_col_step<0, false, true><<<g, kThreads, 0, st>>>(a);
+  else k_col_step<0, false, false><<<g, kThreads, 0, st>>>(a);
 }
 
 #define MIPCU_DISPATCH_TPR(tpr, CALL)                                                          \
@@ -352,7 +377,9 @@ void row_step(mipcu_ctx* ctx, int i, bool check, bool keep_kx = false) {
   if (ctx->m == 0) return;
   RowStepArgs a = row_args(ctx, i);
   if (keep_kx) a.kx_save = ctx->tmp_m;
-  MIPCU_DISPATCH_TPR(ctx->rows.tpr, launch_row<T>(ctx, a, check));
+  const int fmt = kernel_format(ctx, ctx->rows);
+  if (fmt == 0) launch_row_sell(ctx, a, check);
+  else MIPCU_DISPATCH_TPR(fmt, launch_row<T>(ctx, a, check));
   ctx->launches++;
 }
 
@@ -382,7 +409,9 @@ void col_step(mipcu_ctx* ctx, int i, bool check, const double* xhat_in, double* 
     ctx->launches++;
     return;
   }
-  MIPCU_DISPATCH_TPR(ctx->cols.tpr, launch_col<T>(ctx, a, check, xhat_out != nullptr));
+  const int fmt = kernel_format(ctx, ctx->cols);
+  if (fmt == 0) launch_col_sell(ctx, a, check, xhat_out != nullptr);
+  else MIPCU_DISPATCH_TPR(fmt, launch_col<T>(ctx, a, check, xhat_out != nullptr));
   ctx->launches++;
 }
 
@@ -398,7 +427,9 @@ const double* global_row_sums(mipcu_ctx* ctx) {
 
 void kkt_row(mipcu_ctx* ctx) {
   if (ctx->m == 0) return;
-  MIPCU_DISPATCH_TPR(ctx->rows.tpr, launch_kkt<T>(ctx));
+  const int fmt = kernel_format(ctx, ctx->rows);
+  if (fmt == 0) launch_kkt<0>(ctx);
+  else MIPCU_DISPATCH_TPR(fmt, launch_kkt<T>(ctx));
   ctx->launches++;
 }
 
@@ -496,15 +527,26 @@ void init_iterate(mipcu_ctx* ctx, Scalars& h) {
 
 }  // namespace
 
+// Index structure besides the 12 bytes per nonzero: CSR reads a 4-byte pointer per row; SELL reads
+// a 4-byte offset per 32-row slice and a 1-byte local permutation entry per row.  Padding entries
+// of the SELL copy are waste, not algorithmic bytes, and are not counted.
+int64_t index_bytes(const mipcu_ctx* ctx, const Csr& A) {
+  if (kernel_format(ctx, A) == 0) {
+    const int64_t nblk = grid_for(A.nrows, kRowsPerCta);
+    return 4 * (nblk * (kRowsPerCta / 32) + 1) + nblk * kRowsPerCta;
+  }
+  return 4 * ((int64_t)A.nrows + 1);
+}
+
 int64_t row_kernel_bytes(const mipcu_ctx* ctx) {
-  // CSR stream 12/nnz + row ptr 4(m+1) + gathered xbar once 8n + reads y,y0,lo,hi + writes y,yhat
-  return 12 * ctx->nnz + 4 * ((int64_t)ctx->m + 1) + 8 * (int64_t)ctx->n + 48 * (int64_t)ctx->m;
+  // matrix stream 12/nnz + index structure + gathered xbar once 8n + reads y,y0,lo,hi + writes y,yhat
+  return 12 * ctx->nnz + index_bytes(ctx, ctx->rows) + 8 * (int64_t)ctx->n + 48 * (int64_t)ctx->m;
 }
 
 int64_t col_kernel_bytes(const mipcu_ctx* ctx) {
   // CSC stream 12/nnz + col ptr 4(n+1) + gathered yhat once 8m + reads xbar,x0,aty,aty0,c,l,u
   // + writes xbar,aty
-  return 12 * ctx->nnz + 4 * ((int64_t)ctx->n + 1) + 8 * (int64_t)ctx->m + 72 * (int64_t)ctx->n;
+  return 12 * ctx->nnz + index_bytes(ctx, ctx->cols) + 8 * (int64_t)ctx->m + 72 * (int64_t)ctx->n;
 }
 
 void solve_lp(mipcu_ctx* ctx, mipcu_stats* out) {

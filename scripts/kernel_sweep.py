@@ -11,7 +11,7 @@ with Engine(0) as e:
     e.prepare()
     for tma in (0,):
         e.set_param("use_tma", tma)
-        for tpr in (4, 8):
+        for tpr in (0, 8):
             e.set_param("threads_per_row", tpr)
             for which, nm in ((2, "row_step"), (3, "col_step")):
                 us, nb = e.time_kernel(which, 30, 0)

@@ -79,6 +79,32 @@ def test_spmv_long_rows_and_empty_rows(engine):
     assert np.abs(engine.spmv(w, transpose=True) - A.T @ w).max() <= 1e-12
 
 
+@pytest.mark.parametrize("m,n", [(1000, 2000), (255, 700), (513, 257), (4096, 300)])
+def test_sell_copy_matches_csr_kernels(engine, m, n):
+    """After prepare() the SpMVs run on the sliced-ELL copy (one lane per row, rows sorted by length
+    inside each block of 256): ragged row lengths 0..60, row counts that are not multiples of 256."""
+    rng = np.random.default_rng(m + n)
+    lens = rng.integers(0, min(60, n), size=m)
+    lens[rng.integers(0, m, size=m // 10)] = 0                      # empty rows
+    rows = np.repeat(np.arange(m), lens)
+    cols = np.concatenate([rng.choice(n, size=k, replace=False) for k in lens]) if lens.sum() else np.zeros(0, int)
+    A = sp.csr_matrix((rng.uniform(0.1, 1.0, size=rows.size) * rng.choice([-1, 1], size=rows.size), (rows, cols)), shape=(m, n))
+    A.sort_indices()
+    L = gen.LP(A, np.zeros(n), np.zeros(n), np.ones(n), np.full(m, -np.inf), np.ones(m))
+    engine.load_lp(L)
+    engine.prepare()
+    v, w = rng.standard_normal(n), rng.standard_normal(m)
+    ref_ax, ref_aty = A @ v, A.T @ w
+    out = {}
+    for lanes in (0, 8):                      # 0: SELL when eligible; 8: the CSR kernels
+        engine.set_param("threads_per_row", lanes)
+        out[lanes] = (engine.spmv(v), engine.spmv(w, transpose=True))
+        # FP64, different summation order: 1e-12 relative to the largest entry
+        assert np.abs(out[lanes][0] - ref_ax).max() <= 1e-12 * max(1.0, np.abs(ref_ax).max())
+        assert np.abs(out[lanes][1] - ref_aty).max() <= 1e-12 * max(1.0, np.abs(ref_aty).max())
+    engine.set_param("threads_per_row", 0)
+
+
 def test_scaling_matches_oracle(engine):
     L = gen.config(1)
     engine.load_lp(L)
@@ -328,13 +354,19 @@ def test_error_reporting(engine):
 
 # ---- kernel variants -------------------------------------------------------------------------
 def test_tma_and_lsu_kernels_agree_bit_for_bit(engine):
-    """The TMA-streamed kernels (cp.async.bulk ring) use the same lane order as the LSU-streamed
-    ones: raw iterates are identical, whole solves agree."""
+    """The TMA-streamed kernels (cp.async.bulk ring) use the same lane order as the LSU-streamed CSR
+    ones (8 lanes per row on these models): raw iterates are identical, whole solves agree.  The
+    default lane-per-row SELL kernels sum each row in a different order: equal to 1e-10."""
     for L in (gen.config(1), gen.lp_fast(5000, 9000, 12, 3), gen.set_cover(400, 1000, 8, 20264)):
         engine.load_lp(L)
         engine.set_param("use_tma", 0)
+        xs, ys = engine.debug_iterate(50)          # SELL (default)
+        ss = engine.solve()
+        engine.set_param("threads_per_row", 8)     # CSR, 8 lanes per row
         xa, ya = engine.debug_iterate(50)
         sa = engine.solve()
+        assert np.abs(xa - xs).max() <= 1e-10 and np.abs(ya - ys).max() <= 1e-10
+        assert ss.status == "optimal" and rel(sa.primal_obj, ss.primal_obj) <= 1e-6
         engine.set_param("use_tma", 1)
         xb, yb = engine.debug_iterate(50)
         sb = engine.solve()
@@ -342,6 +374,7 @@ def test_tma_and_lsu_kernels_agree_bit_for_bit(engine):
         xc, yc = engine.debug_iterate(50)
         sc = engine.solve()
         engine.set_param("use_tma", -1)
+        engine.set_param("threads_per_row", 0)
         assert np.abs(xa - xc).max() <= 1e-10 and np.abs(ya - yc).max() <= 1e-10
         assert sc.status == "optimal" and rel(sa.primal_obj, sc.primal_obj) <= 1e-6
         assert np.array_equal(xa, xb) and np.array_equal(ya, yb)
