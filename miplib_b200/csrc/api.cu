@@ -19,13 +19,22 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
                     mipcu_stats* out, double* x_out);
 }  // namespace mipcu
 
+thread_local const mipcu_ctx* g_alloc_ctx = nullptr;
+
 namespace {
 
 std::string g_create_error;   // errors raised before a context exists
 std::mutex g_mutex;
 
+struct AllocScope {
+  const mipcu_ctx* saved;
+  explicit AllocScope(const mipcu_ctx* ctx) : saved(g_alloc_ctx) { g_alloc_ctx = ctx; }
+  ~AllocScope() { g_alloc_ctx = saved; }
+};
+
 template <class F>
 int guarded(mipcu_ctx* ctx, F&& f) {
+  AllocScope scope(ctx);
   try {
     f();
     return 0;
@@ -74,6 +83,16 @@ mipcu_ctx* create_on(int device) {
   set_default_params(ctx);
   try {
     MIPCU_CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    // keep freed model arrays in the device's memory pool (see setup.cu: dalloc)
+    int pools = 0;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, device) == cudaSuccess && pools &&
+        cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      if (cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess)
+        ctx->pool_alloc = true;
+    }
+    cudaGetLastError();
   } catch (...) {
     delete ctx;
     throw;
@@ -118,6 +137,7 @@ int mipcu_create_sharded(mipcu_ctx** out, int device, int rank, int world, const
   return guarded(nullptr, [&] {
     MIPCU_REQUIRE(world >= 1 && rank >= 0 && rank < world, "mipcu_create_sharded: bad rank/world");
     mipcu_ctx* ctx = create_on(device);
+    if (world > 1) ctx->pool_alloc = false;   // exchange buffers are exported over CUDA IPC
     try {
       if (world > 1) dist_init(ctx, rank, world, unique_id);
     } catch (...) {
@@ -132,6 +152,7 @@ void mipcu_destroy(mipcu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  AllocScope scope(ctx);
   try { p2p_teardown(ctx); } catch (...) {}
   try { free_model(ctx); } catch (...) {}
   if (ctx->nccl_comm) { try { dist_destroy(ctx); } catch (...) {} }
@@ -140,7 +161,15 @@ void mipcu_destroy(mipcu_ctx* ctx) {
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream) {
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->pool_alloc) {   // hand the pool's cached memory back to the device
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
+    cudaStreamDestroy(ctx->stream);
+  }
+  cudaGetLastError();
   delete ctx;
 }
 

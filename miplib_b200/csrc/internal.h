@@ -163,7 +163,12 @@ struct mipcu_ctx {
   void* flush_buf = nullptr;
 
   int64_t launches = 0;   // kernels launched by the current call
+  bool pool_alloc = false;   // model arrays come from the stream-ordered memory pool (single-GPU contexts)
 };
+
+// context whose call is executing on this thread: tells setup.cu's allocator which stream / pool
+// to use (set by the entry points in api.cu)
+extern thread_local const mipcu_ctx* g_alloc_ctx;
 
 namespace mipcu {
 

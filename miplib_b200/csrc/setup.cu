@@ -17,16 +17,28 @@ inline int grid_for(int64_t n, int per_block = kThreads) {
   return (int)((n + per_block - 1) / per_block);
 }
 
+// Device allocations of this file.  A single-GPU context allocates stream-ordered from the device's
+// memory pool (release threshold raised at creation, api.cu): cudaMalloc / cudaFree synchronise the
+// device and map / unmap memory on every call, which made RE-loading a config-3 model cost 0.7 s;
+// from the pool the same buffers are reused.  Row-sharded contexts export buffers over CUDA IPC,
+// which pool memory does not support, so they keep cudaMalloc.
 template <class T>
 T* dalloc(int64_t count) {
   T* p = nullptr;
-  MIPCU_CK(cudaMalloc(&p, sizeof(T) * (size_t)(count > 0 ? count : 1)));
+  const size_t bytes = sizeof(T) * (size_t)(count > 0 ? count : 1);
+  const mipcu_ctx* ctx = g_alloc_ctx;
+  if (ctx && ctx->pool_alloc) MIPCU_CK(cudaMallocAsync(&p, bytes, ctx->stream));
+  else MIPCU_CK(cudaMalloc(&p, bytes));
   return p;
 }
 
 template <class T>
 void dfree(T*& p) {
-  if (p) cudaFree(p);
+  if (p) {
+    const mipcu_ctx* ctx = g_alloc_ctx;
+    if (ctx && ctx->pool_alloc) cudaFreeAsync(p, ctx->stream);
+    else cudaFree(p);
+  }
   p = nullptr;
 }
 
@@ -279,7 +291,7 @@ __global__ void k_narrow_ll(const long long* in, int* out, int count) {
 
 void free_sell(Csr& A) {
   dfree(A.sptr); dfree(A.sidx); dfree(A.sval);
-  if (A.perm) { cudaFree(A.perm); A.perm = nullptr; }
+  dfree(A.perm);
   A.sell_entries = 0;
   A.sell = false;
 }
@@ -292,7 +304,7 @@ void build_sell(mipcu_ctx* ctx, Csr& A) {
   if ((double)A.nnz / (double)A.nrows > kSellMaxAvgRow) return;
   cudaStream_t st = ctx->stream;
   const int nblk = grid_for(A.nrows, kRowsPerCta), nslices = nblk * (kRowsPerCta / 32);
-  MIPCU_CK(cudaMalloc(&A.perm, (size_t)nblk * kRowsPerCta));
+  A.perm = dalloc<unsigned char>((int64_t)nblk * kRowsPerCta);
   long long* sizes = dalloc<long long>(nslices + 1);
   long long* offs = dalloc<long long>(nslices + 1);
   MIPCU_CK(cudaMemsetAsync(sizes, 0, sizeof(long long) * (nslices + 1), st));
@@ -300,13 +312,12 @@ void build_sell(mipcu_ctx* ctx, Csr& A) {
   ctx->launches++;
   size_t tmp_bytes = 0;
   MIPCU_CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, sizes, offs, nslices + 1, st));
-  void* tmp = nullptr;
-  MIPCU_CK(cudaMalloc(&tmp, tmp_bytes + 16));
+  char* tmp = dalloc<char>((int64_t)tmp_bytes + 16);
   MIPCU_CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, sizes, offs, nslices + 1, st));
   long long total = 0;
   MIPCU_CK(cudaMemcpyAsync(&total, offs + nslices, sizeof(long long), cudaMemcpyDeviceToHost, st));
   MIPCU_CK(cudaStreamSynchronize(st));
-  cudaFree(tmp);
+  dfree(tmp);
   const bool ok = total < (1ll << 31) - 1024 && (double)total <= 1.35 * (double)A.nnz + 8192.0;
   if (ok) {
     A.sptr = dalloc<int>(nslices + 1);
@@ -319,8 +330,7 @@ void build_sell(mipcu_ctx* ctx, Csr& A) {
     A.sell_entries = total;
     A.sell = true;
   } else {
-    cudaFree(A.perm);
-    A.perm = nullptr;
+    dfree(A.perm);
   }
   dfree(sizes); dfree(offs);
 }
@@ -355,15 +365,14 @@ void build_transpose(mipcu_ctx* ctx, const Csr& A, Csr& T) {
   MIPCU_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, A.idx, keys_out, pos, perm,
                                            (int)A.nnz, 0, end_bit, st));
   MIPCU_CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, counts, T.ptr, T.nrows + 1, st));
-  void* tmp = nullptr;
-  MIPCU_CK(cudaMalloc(&tmp, std::max(tmp_bytes, tmp2) + 16));
+  char* tmp = dalloc<char>((int64_t)std::max(tmp_bytes, tmp2) + 16);
   MIPCU_CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, A.idx, keys_out, pos, perm, (int)A.nnz,
                                            0, end_bit, st));
   MIPCU_CK(cub::DeviceScan::ExclusiveSum(tmp, tmp2, counts, T.ptr, T.nrows + 1, st));
   k_permute<<<grid_for(A.nnz), kThreads, 0, st>>>(perm, row_of, A.val, T.idx, T.val, A.nnz);
   ctx->launches++;
   MIPCU_CK(cudaStreamSynchronize(st));
-  cudaFree(tmp);
+  dfree(tmp);
   dfree(row_of); dfree(pos); dfree(keys_out); dfree(perm); dfree(counts);
 }
 
@@ -387,7 +396,7 @@ int tile_capacity(mipcu_ctx* ctx, const Csr& A, int tile_rows = 64) {
   int h = 0;
   MIPCU_CK(cudaMemcpyAsync(&h, d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   MIPCU_CK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d);
+  dfree(d);
   return std::max(h, 4);
 }
 
@@ -475,7 +484,7 @@ void load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* r
     k_narrow_ptr<<<grid_for(m + 1), kThreads, 0, st>>>(tmp64, A.ptr, (int)(m + 1));
     ctx->launches++;
     MIPCU_CK(cudaStreamSynchronize(st));
-    cudaFree(tmp64);
+    dfree(tmp64);
   }
   MIPCU_CK(cudaMemsetAsync(A.idx + nnz, 0, sizeof(int) * 4, st));
   MIPCU_CK(cudaMemsetAsync(A.val + nnz, 0, sizeof(double) * 4, st));
@@ -494,7 +503,7 @@ void load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* r
     int hbad = 0;
     MIPCU_CK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     MIPCU_CK(cudaStreamSynchronize(st));
-    cudaFree(bad);
+    dfree(bad);
     if (hbad) {
       free_model(ctx);
       throw Error(hbad == 1 ? "mipcu_load_lp: row_ptr is not non-decreasing"
@@ -576,9 +585,18 @@ void prepare(mipcu_ctx* ctx) {
       ctx->launches += 6;
     }
   }
+  const bool verbose = ctx->params[MIPCU_PARAM_VERBOSE] != 0.0;
+  auto lap = [&](const char* what) {
+    if (!verbose) return;
+    MIPCU_CK(cudaStreamSynchronize(st));
+    fprintf(stderr, "[mipcu] prepare: %-16s at %.1f ms\n", what,
+            1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  };
+  lap("scaling");
   // lane-per-row copies of the scaled matrix for the iteration kernels
   build_sell(ctx, R);
   build_sell(ctx, C);
+  lap("sell copies");
   // step size
   double step = ctx->params[MIPCU_PARAM_STEP_SIZE];
   if (step > 0.0) {
@@ -614,7 +632,9 @@ void prepare(mipcu_ctx* ctx) {
       prev = s;
     }
     ctx->eta = (!zero && s > 0.0) ? STEP_SAFETY / s : 1.0;
+    if (verbose) fprintf(stderr, "[mipcu] prepare: %d power iterations, sigma_max %.9g\n", it, s);
   }
+  lap("step size");
   MIPCU_CK(cudaStreamSynchronize(st));
   ctx->prepared = true;
   ctx->vectors_dirty = true;
@@ -666,8 +686,8 @@ void set_bounds(mipcu_ctx* ctx, int64_t n_changed, const int64_t* cols, const do
   k_scatter_bounds<<<grid_for(n_changed), kThreads, 0, st>>>(dcols, dl, du, ctx->lb, ctx->ub, (int)n_changed);
   ctx->launches++;
   MIPCU_CK(cudaStreamSynchronize(st));
-  cudaFree(dcols);
-  cudaFree(dl);
+  dfree(dcols);
+  dfree(dl);
   ctx->vectors_dirty = true;
 }
 

@@ -50,7 +50,22 @@ CudaBranchAndBound::CudaBranchAndBound(CudaSolver& solver) : S(solver)
     rhi.push_back(S.m_row_hi[r] >= inf ? kInf : S.m_row_hi[r]);
   }
   m = rlo.size();
-  // CSC (which rows to revisit when a column's box shrinks)
+  rebuild_columns();
+  cost.resize(n);
+  is_int.resize(n);
+  for (std::size_t j = 0; j < n; ++j)
+  {
+    cost[j] = sgn * (j < S.m_objective.size() ? S.m_objective[j] : 0.0);
+    is_int[j] = S.m_columns[j].type != Var::Type::Continuous;
+    if (!is_int[j]) pure_integer = false;
+    if (cost[j] != 0 && (!is_int[j] || !integral(cost[j]))) objective_integral = false;
+  }
+}
+
+// CSC of the rows (which rows to revisit when a column's box shrinks)
+void CudaBranchAndBound::rebuild_columns()
+{
+  m = rlo.size();
   cptr.assign(n + 1, 0);
   for (std::int32_t j : ridx) cptr[j + 1]++;
   for (std::size_t j = 0; j < n; ++j) cptr[j + 1] += cptr[j];
@@ -63,15 +78,94 @@ CudaBranchAndBound::CudaBranchAndBound(CudaSolver& solver) : S(solver)
       cidx[fill[ridx[k]]] = static_cast<std::int32_t>(r);
       cval[fill[ridx[k]]++] = rval[k];
     }
-  cost.resize(n);
-  is_int.resize(n);
-  for (std::size_t j = 0; j < n; ++j)
+}
+
+// Implied-bound rows from the root box (see bnb.hpp).  Each side of a row is normalised to
+// sum alpha_k x_k <= b.  Fixing a binary z at the value that RAISES the row's minimum activity
+// (0 if alpha_z < 0, 1 if alpha_z > 0) by delta = |alpha_z| leaves column j the room
+//   alpha_j x_j <= b - (minact + delta) + min(alpha_j l_j, alpha_j u_j);
+// if that is tighter than j's own bound, "bound(z fixed) ... bound(z free)" interpolated in z is
+// a valid row with two nonzeros.  Only pairs with |alpha_z| >= |alpha_j| are generated (the other
+// orientation yields the same row), and a z is skipped in O(1) unless delta + (largest range of
+// another term) exceeds the row's slack b - minact, which keeps knapsack rows linear.
+std::size_t CudaBranchAndBound::add_implied_bound_rows(std::vector<double> const& lb, std::vector<double> const& ub)
+{
+  std::size_t const m0 = m, cap = 4 * n + 1024;
+  std::size_t added = 0;
+  auto is_binary = [&](std::int32_t j) { return is_int[j] && lb[j] == 0.0 && ub[j] == 1.0; };
+  auto emit = [&](std::int32_t j, double aj, std::int32_t z, double az, double lo, double hi) {
+    if (j < z) { ridx.push_back(j); rval.push_back(aj); ridx.push_back(z); rval.push_back(az); }
+    else { ridx.push_back(z); rval.push_back(az); ridx.push_back(j); rval.push_back(aj); }
+    rptr.push_back(static_cast<std::int64_t>(ridx.size()));
+    rlo.push_back(lo);
+    rhi.push_back(hi);
+    ++added;
+  };
+  for (std::size_t r = 0; r < m0 && added < cap; ++r)
   {
-    cost[j] = sgn * (j < S.m_objective.size() ? S.m_objective[j] : 0.0);
-    is_int[j] = S.m_columns[j].type != Var::Type::Continuous;
-    if (!is_int[j]) pure_integer = false;
-    if (cost[j] != 0 && (!is_int[j] || !integral(cost[j]))) objective_integral = false;
+    std::int64_t const k0 = rptr[r], k1 = rptr[r + 1];
+    if (k1 - k0 < 2) continue;
+    for (int side = 0; side < 2 && added < cap; ++side)
+    {
+      double const s = side == 0 ? 1.0 : -1.0;
+      double const b = side == 0 ? rhi[r] : -rlo[r];
+      if (std::isinf(b)) continue;
+      double minact = 0, range1 = 0, range2 = 0;   // two largest term ranges
+      bool bounded = true;
+      for (std::int64_t k = k0; k < k1 && bounded; ++k)
+      {
+        double const a = s * rval[k], l = lb[ridx[k]], u = ub[ridx[k]];
+        if (std::isinf(l) || std::isinf(u)) { bounded = false; break; }
+        minact += std::min(a * l, a * u);
+        double const range = std::abs(a) * (u - l);
+        if (range > range1) { range2 = range1; range1 = range; } else if (range > range2) range2 = range;
+      }
+      if (!bounded) continue;
+      double const slack = b - minact;
+      if (slack < 0) continue;
+      for (std::int64_t kz = k0; kz < k1 && added < cap; ++kz)
+      {
+        std::int32_t const z = ridx[kz];
+        double const az = s * rval[kz];
+        if (az == 0 || !is_binary(z)) continue;
+        double const delta = std::abs(az);
+        double const other = (delta == range1) ? range2 : range1;   // binary: range == |alpha|
+        if (delta + other <= slack * (1 + 1e-12) + 1e-9) continue;
+        bool const z_at_zero = az < 0;
+        for (std::int64_t k = k0; k < k1 && added < cap; ++k)
+        {
+          if (k == kz) continue;
+          std::int32_t const j = ridx[k];
+          double const aj = s * rval[k], l = lb[j], u = ub[j];
+          if (aj == 0 || l == u) continue;
+          if (std::abs(aj) > delta || (std::abs(aj) == delta && j < z)) continue;
+          double const room = slack - delta;   // what |alpha_j| (x_j - its min-activity side) may still use
+          if (room >= std::abs(aj) * (u - l) - 1e-9) continue;          // no tightening
+          if (room < -1e-9) continue;                                   // z cannot take that value: propagation's job
+          if (aj > 0)
+          {
+            double nu = l + std::max(room, 0.0) / aj;
+            if (is_int[j]) nu = std::floor(nu + 1e-6);
+            if (nu > u - 1e-9) continue;
+            // z = 0 forces x_j <= nu:  x_j - (u - nu) z <= nu ;  z = 1 forces it:  x_j + (u - nu) z <= u
+            if (z_at_zero) emit(j, 1.0, z, -(u - nu), -kInf, nu);
+            else emit(j, 1.0, z, (u - nu), -kInf, u);
+          }
+          else
+          {
+            double nl = u - std::max(room, 0.0) / -aj;
+            if (is_int[j]) nl = std::ceil(nl - 1e-6);
+            if (nl < l + 1e-9) continue;
+            // z = 0 forces x_j >= nl:  x_j + (nl - l) z >= nl ;  z = 1 forces it:  x_j - (nl - l) z >= l
+            if (z_at_zero) emit(j, 1.0, z, (nl - l), nl, kInf);
+            else emit(j, 1.0, z, -(nl - l), l, kInf);
+          }
+        }
+      }
+    }
   }
+  if (added) rebuild_columns();
+  return added;
 }
 
 double CudaBranchAndBound::objective(std::vector<double> const& x) const
@@ -278,7 +372,20 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
 
   // device model(s): the primary context plus one per extra GPU asked for with set_nr_threads
   bool const user_verbose = S.m_verbose;
-  S.upload_model();
+  S.m_info.cuts = static_cast<std::int64_t>(add_implied_bound_rows(root_lb, root_ub));
+  if (S.m_info.cuts)
+  {
+    if (!propagate(root_lb, root_ub)) return {R::Infeasible, false};
+    std::vector<double> lo(rlo), hi(rhi);
+    for (double& v : lo) if (std::isinf(v)) v = -inf;
+    for (double& v : hi) if (std::isinf(v)) v = inf;
+    S.upload_rows(rptr, ridx, rval, lo, hi);
+    if (user_verbose)
+      std::fprintf(stderr, "[miplib cuda b&b] %lld implied-bound rows added at the root\n",
+                   static_cast<long long>(S.m_info.cuts));
+  }
+  else
+    S.upload_model();
   std::vector<mipcu_ctx*> gpus = S.node_contexts();
   for (mipcu_ctx* ctx : gpus)
   {

@@ -441,6 +441,33 @@ void CudaSolver::upload_model()
 // Contexts that take node LPs of a branch-and-bound round: the primary one plus a copy of the
 // model on every extra GPU requested with set_nr_threads (nodes are
 // independent, the host deals them out, nothing is exchanged on the device).
+void CudaSolver::upload_rows(std::vector<std::int64_t> const& ptr, std::vector<std::int32_t> const& idx,
+                             std::vector<double> const& val, std::vector<double> const& lo,
+                             std::vector<double> const& hi)
+{
+  ensure_context();
+  std::size_t const n = m_columns.size();
+  m_objective.resize(n, 0.0);
+  std::vector<double> lb(n), ub(n);
+  for (std::size_t j = 0; j < n; ++j)
+  {
+    lb[j] = m_columns[j].lb;
+    ub[j] = m_columns[j].ub;
+  }
+  check(m_ctx, mipcu_load_lp(m_ctx, static_cast<std::int64_t>(lo.size()), static_cast<std::int64_t>(n),
+                             static_cast<std::int64_t>(idx.size()), ptr.data(), idx.data(), val.data(),
+                             m_objective.data(), lb.data(), ub.data(), lo.data(), hi.data(),
+                             m_sense == Solver::Sense::Maximize));
+  m_last_ptr = ptr;
+  m_last_idx = idx;
+  m_last_val = val;
+  m_last_lo = lo;
+  m_last_hi = hi;
+  m_structure_dirty = true;   // the device no longer holds the user's own rows
+  m_objective_dirty = false;
+  m_dirty_columns.clear();
+}
+
 std::vector<mipcu_ctx*> CudaSolver::node_contexts()
 {
   std::vector<mipcu_ctx*> all{m_ctx};

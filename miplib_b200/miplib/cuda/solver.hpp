@@ -109,7 +109,7 @@ struct CudaSolver : detail::ISolver
   // ---- statistics of the last solve (tests and bench read them) --------------------------------
   struct SolveInfo
   {
-    std::int64_t lp_solves = 0, lp_iterations = 0, nodes = 0, kernel_launches = 0;
+    std::int64_t lp_solves = 0, lp_iterations = 0, nodes = 0, kernel_launches = 0, cuts = 0;
     double seconds = 0, best_bound = 0;
     bool proven_optimal = false;
   };
@@ -123,6 +123,10 @@ struct CudaSolver : detail::ISolver
   void ensure_context();
   std::vector<mipcu_ctx*> node_contexts();   // primary + one loaded copy per extra GPU (B&B rounds)
   void upload_model();
+  // B&B: load the model with extra valid rows appended (cuts); the next plain solve re-uploads
+  void upload_rows(std::vector<std::int64_t> const& ptr, std::vector<std::int32_t> const& idx,
+                   std::vector<double> const& val, std::vector<double> const& lo,
+                   std::vector<double> const& hi);
   struct LpOutcome
   {
     int status;

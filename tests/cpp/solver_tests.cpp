@@ -240,7 +240,9 @@ GPU_TEST("Generated models through the expression API match the exact-solver gol
     int maximize;
     double expected, tol;
     in >> maximize >> expected >> tol;
-    solver.set_time_limit(150);   // a runaway tree must fail the test, not hang it
+    double limit = 150;           // a runaway tree must fail the test, not hang it
+    if (char const* t = std::getenv("MIPLIB_TEST_TIME_LIMIT")) limit = std::atof(t);
+    solver.set_time_limit(limit);
     if (char const* gpus = std::getenv("MIPLIB_TEST_GPUS")) solver.set_nr_threads(std::atoi(gpus));
     auto const t_begin = std::chrono::steady_clock::now();
     auto [r, has_solution] = maximize ? solver.maximize(objective) : solver.minimize(objective);
@@ -249,7 +251,8 @@ GPU_TEST("Generated models through the expression API match the exact-solver gol
               << (has_solution ? solver.get_objective_value() : NAN) << " expected " << expected
               << " in " << secs << " s  [nodes " << CudaSolver::of(solver).m_info.nodes << ", node LPs "
               << CudaSolver::of(solver).m_info.lp_solves << ", PDHG iterations "
-              << CudaSolver::of(solver).m_info.lp_iterations << "]" << std::endl;
+              << CudaSolver::of(solver).m_info.lp_iterations << ", implied-bound rows "
+              << CudaSolver::of(solver).m_info.cuts << "]" << std::endl;
     REQUIRE(r == Solver::Result::Optimal && has_solution);
     REQUIRE(std::abs(solver.get_objective_value() - expected) <= tol * (1 + std::abs(expected)));
     REQUIRE(close(objective.value(), solver.get_objective_value(), 1e-9));

@@ -69,6 +69,8 @@ def test_kats_and_generated_models_on_gpu(built, golden, tmp_path):
         ("setcover_200x500_mip", gen.set_cover(200, 500, 8, 20264), golden["setcover_200x500_mip"]["objective"], 1e-9),
         ("mkp_5x60_mip", gen.mkp(5, 60, 4, 4, 20265), golden["mkp_5x60_mip"]["objective"], 1e-9),
         ("setcover_400x1000_mip", gen.set_cover(400, 1000, 8, 20264), golden["setcover_400x1000_mip"]["objective"], 1e-9),
+        # 7.5 k nodes: only tractable with the implied-bound rows of the big-M switch rows (bnb.hpp)
+        ("mkp_8x80_mip", gen.mkp(8, 80, 4, 4, 20265), golden["mkp_8x80_mip"]["objective"], 1e-9),
     ]
     path = tmp_path / "models.txt"
     write_models(path, models)
