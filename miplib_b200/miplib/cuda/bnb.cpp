@@ -279,14 +279,44 @@ bool CudaBranchAndBound::row_feasible(std::vector<double> const& x, double tol_s
 bool CudaBranchAndBound::try_incumbent(std::vector<double> const& x)
 {
   double const tol = pure_integer ? 1e-9 : std::max(10 * S.m_feas_tol, 1e-6);
+  lazy_rejected = lazy_added = false;
   if (!row_feasible(x, tol)) return false;
   double const v = objective(x);
   if (!have_incumbent || v < best - 1e-12 * (1 + std::abs(best)))
   {
+    // lazy constraints (reference miplib/lazy.hpp:19-41): the handlers see every point that is
+    // about to become the incumbent; a rejected point is dropped and the rows they posted join
+    // the tree before the next round of node LPs
+    if (!S.lazy_accepts(x, &lazy_added))
+    {
+      lazy_rejected = true;
+      return false;
+    }
     have_incumbent = true;
     best = v;
     best_x = x;
   }
+  return true;
+}
+
+bool CudaBranchAndBound::absorb_lazy_rows()
+{
+  if (S.m_lazy_new_rows.empty()) return false;
+  double const inf = S.infinity();
+  for (std::int64_t r : S.m_lazy_new_rows)
+  {
+    for (std::int64_t k = S.m_row_start[r]; k < S.m_row_start[r + 1]; ++k)
+    {
+      ridx.push_back(S.m_row_idx[k]);
+      rval.push_back(S.m_row_val[k]);
+    }
+    rptr.push_back(static_cast<std::int64_t>(ridx.size()));
+    rlo.push_back(S.m_row_lo[r] <= -inf ? -kInf : S.m_row_lo[r]);
+    rhi.push_back(S.m_row_hi[r] >= inf ? kInf : S.m_row_hi[r]);
+  }
+  S.m_info.lazy_rows += static_cast<std::int64_t>(S.m_lazy_new_rows.size());
+  S.m_lazy_new_rows.clear();
+  rebuild_columns();
   return true;
 }
 
@@ -372,28 +402,34 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
 
   // device model(s): the primary context plus one per extra GPU asked for with set_nr_threads
   bool const user_verbose = S.m_verbose;
+  bool custom_rows = absorb_lazy_rows();      // a start point may already have met the handlers
   S.m_info.cuts = static_cast<std::int64_t>(add_implied_bound_rows(root_lb, root_ub));
-  if (S.m_info.cuts)
-  {
-    if (!propagate(root_lb, root_ub)) return {R::Infeasible, false};
-    std::vector<double> lo(rlo), hi(rhi);
-    for (double& v : lo) if (std::isinf(v)) v = -inf;
-    for (double& v : hi) if (std::isinf(v)) v = inf;
-    S.upload_rows(rptr, ridx, rval, lo, hi);
-    if (user_verbose)
-      std::fprintf(stderr, "[miplib cuda b&b] %lld implied-bound rows added at the root\n",
-                   static_cast<long long>(S.m_info.cuts));
-  }
-  else
-    S.upload_model();
-  std::vector<mipcu_ctx*> gpus = S.node_contexts();
-  for (mipcu_ctx* ctx : gpus)
-  {
-    check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_EPS_REL, S.m_feas_tol));
-    check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_VERBOSE, 0));
-    check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_ITER_LIMIT, 100000));
-    check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_OBJ_CUTOFF, std::nan("")));
-  }
+  if (S.m_info.cuts) custom_rows = true;
+  if (custom_rows && !propagate(root_lb, root_ub)) return finish(true);
+  if (user_verbose && S.m_info.cuts)
+    std::fprintf(stderr, "[miplib cuda b&b] %lld implied-bound rows added at the root\n",
+                 static_cast<long long>(S.m_info.cuts));
+  std::vector<mipcu_ctx*> gpus;
+  auto upload = [&]() {
+    if (custom_rows)
+    {
+      std::vector<double> lo(rlo), hi(rhi);
+      for (double& v : lo) if (std::isinf(v)) v = -inf;
+      for (double& v : hi) if (std::isinf(v)) v = inf;
+      S.upload_rows(rptr, ridx, rval, lo, hi);
+    }
+    else
+      S.upload_model();
+    gpus = S.node_contexts();
+    for (mipcu_ctx* ctx : gpus)
+    {
+      check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_EPS_REL, S.m_feas_tol));
+      check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_VERBOSE, 0));
+      check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_ITER_LIMIT, 100000));
+      check(ctx, mipcu_set_param(ctx, MIPCU_PARAM_OBJ_CUTOFF, std::nan("")));
+    }
+  };
+  upload();
 
   // no feasible point of the box can cost more than this: a dual bound above it proves the
   // node LP infeasible (PDHG's dual iterate diverges on infeasible problems)
@@ -431,10 +467,18 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
       complete = false;
       break;
     }
+    // rows posted by lazy handlers during the last round join the tree and the device model
+    if (absorb_lazy_rows())
+    {
+      custom_rows = true;
+      if (!propagate(root_lb, root_ub)) break;      // nothing left inside the root box
+      upload();
+    }
     // ---- a round: the best open nodes, tightened on the host, the survivors solved together ----
     round.clear();
     while (!open.empty() && round.size() < round_cap)
     {
+      if (!S.m_lazy_new_rows.empty()) break;   // a handler just posted rows: take them in first
       Node node = open.top();
       open.pop();
       if (node.bound >= cutoff()) continue;            // best-first: cannot improve the incumbent
@@ -541,7 +585,22 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
           std::vector<double> cand(x);
           for (std::size_t j = 0; j < n; ++j)
             if (is_int[j]) cand[j] = std::min(std::max(std::round(cand[j]), lb[j]), ub[j]);
-          if (!try_incumbent(cand)) complete = false;   // an integral LP point that rounding broke
+          if (!try_incumbent(cand))
+          {
+            if (lazy_rejected && lazy_added)
+            {
+              // the handlers cut this point off: solve the same box again under the new rows
+              Node again;
+              for (std::size_t j = 0; j < n; ++j)
+                if (lb[j] != root_lb[j] || ub[j] != root_ub[j])
+                  again.changes.push_back({static_cast<std::int32_t>(j), lb[j], ub[j]});
+              again.bound = node_bound;
+              again.depth = node.depth;
+              open.push(std::move(again));
+            }
+            else
+              complete = false;                        // an integral LP point that rounding broke
+          }
         }
         else
           complete = false;                            // undecided node with nothing to branch on

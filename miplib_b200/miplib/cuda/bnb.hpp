@@ -44,7 +44,8 @@ struct CudaBranchAndBound
   void rebuild_columns();
   bool row_feasible(std::vector<double> const& x, double tol_scale) const;
   double objective(std::vector<double> const& x) const;
-  bool try_incumbent(std::vector<double> const& x);   // false: x violates a row
+  bool try_incumbent(std::vector<double> const& x);   // false: x violates a row or a lazy handler
+  bool absorb_lazy_rows();         // rows posted by lazy handlers -> this tree's row set; true if any
   void try_roundings(std::vector<double> const& x, std::vector<double> const& lb,
                      std::vector<double> const& ub);
   double cutoff() const;           // nodes whose bound reaches this cannot improve the incumbent
@@ -59,6 +60,7 @@ struct CudaBranchAndBound
   bool pure_integer = true, objective_integral = true;
   double best = 0;
   bool have_incumbent = false;
+  bool lazy_rejected = false, lazy_added = false;   // outcome of the last try_incumbent
   std::vector<double> best_x;
 };
 

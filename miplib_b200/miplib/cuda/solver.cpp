@@ -131,6 +131,9 @@ void CudaSolver::add(Constr const& constr)
   m_row_alive.push_back(1);
   impl.m_row = static_cast<std::int64_t>(m_row_hi.size()) - 1;
   m_structure_dirty = true;
+  // posted from inside a lazy-constraint handler (reference: ScipSolver::add forwards to
+  // add_lazy while in a callback, miplib/scip/solver.cpp:197-203): the running solve takes it in
+  if (is_in_callback()) m_lazy_new_rows.push_back(impl.m_row);
 }
 
 void CudaSolver::add(IndicatorConstr const&)
@@ -147,7 +150,36 @@ void CudaSolver::remove(Constr const& constr)
   m_structure_dirty = true;
 }
 
-void CudaSolver::add_lazy_constr_handler(LazyConstrHandler const&, bool) { fail("Not implemented yet."); }
+// at_integral_only is accepted for interface parity; handlers are always run on the candidates the
+// solve would otherwise accept (integral points / the LP optimum), never on fractional node LPs.
+void CudaSolver::add_lazy_constr_handler(LazyConstrHandler const& handler, bool)
+{
+  if (!handler.valid()) fail("Cuda backend: null lazy constraint handler.");
+  m_lazy_handlers.push_back(handler);
+}
+
+bool CudaSolver::lazy_accepts(std::vector<double> const& x, bool* added)
+{
+  if (added) *added = false;
+  if (m_lazy_handlers.empty()) return true;
+  struct Scope
+  {
+    CudaSolver& s;
+    std::vector<double> const* saved;
+    ~Scope() { s.m_callback_x = saved; }
+  } scope{*this, m_callback_x};
+  m_callback_x = &x;
+  bool ok = true;
+  for (LazyConstrHandler& h : m_lazy_handlers)
+  {
+    if (h.is_feasible()) continue;
+    ok = false;
+    std::size_t const before = m_lazy_new_rows.size();
+    h.add();
+    if (added && m_lazy_new_rows.size() > before) *added = true;
+  }
+  return ok;
+}
 
 void CudaSolver::set_objective(Solver::Sense const& sense, Expr const& e)
 {
@@ -524,6 +556,7 @@ std::pair<Solver::Result, bool> CudaSolver::solve()
   m_info = SolveInfo();
   m_has_solution = false;
   m_solution.clear();
+  m_lazy_new_rows.clear();
   m_objective.resize(m_columns.size(), 0.0);
 
   for (Column const& c : m_columns)
@@ -547,33 +580,160 @@ std::pair<Solver::Result, bool> CudaSolver::solve()
   return result;
 }
 
+// Crossover-lite ("polishing").  The reference's backends return vertex
+// solutions of a simplex method and its tests compare values with == (test/unit/solver.cpp:37);
+// a first-order method stops at a point that satisfies the KKT conditions to 1e-6.  For small
+// continuous models this guesses the optimal face from that point - columns sitting on a bound,
+// rows that are tight - solves the remaining square (or consistent over-determined) system
+// exactly by Gaussian elimination on the host, and accepts the result only if it satisfies every
+// row and bound to 1e-9 and does not move the objective.  Anything else keeps the PDHG point.
+void CudaSolver::polish_vertex(std::vector<double>& x)
+{
+  std::size_t const n = m_columns.size(), m = m_last_lo.size();
+  if (n == 0 || m_last_ptr.size() != m + 1) return;
+  double const inf = infinity(), tol = 1e-5;
+  std::vector<double> snapped(x);
+  std::vector<std::int32_t> free_of(n, -1);
+  std::vector<std::int32_t> F;
+  for (std::size_t j = 0; j < n; ++j)
+  {
+    double const l = m_columns[j].lb, u = m_columns[j].ub;
+    if (l > -inf && x[j] - l <= tol * (1 + std::abs(l))) snapped[j] = l;
+    else if (u < inf && u - x[j] <= tol * (1 + std::abs(u))) snapped[j] = u;
+    else { free_of[j] = static_cast<std::int32_t>(F.size()); F.push_back(static_cast<std::int32_t>(j)); }
+  }
+  if (F.size() > m_polish_limit) return;
+  // tight rows and their targets
+  std::vector<std::int32_t> R;
+  std::vector<double> target;
+  for (std::size_t r = 0; r < m; ++r)
+  {
+    double act = 0;
+    bool touches_free = false;
+    for (std::int64_t k = m_last_ptr[r]; k < m_last_ptr[r + 1]; ++k)
+    {
+      act += m_last_val[k] * x[m_last_idx[k]];
+      touches_free = touches_free || free_of[m_last_idx[k]] >= 0;
+    }
+    double const lo = m_last_lo[r], hi = m_last_hi[r];
+    bool const at_hi = hi < inf && std::abs(act - hi) <= tol * (1 + std::abs(hi));
+    bool const at_lo = lo > -inf && std::abs(act - lo) <= tol * (1 + std::abs(lo));
+    if (!touches_free || !(at_hi || at_lo)) continue;
+    R.push_back(static_cast<std::int32_t>(r));
+    target.push_back(at_hi ? hi : lo);
+  }
+  std::size_t const nf = F.size(), nr = R.size();
+  if (nr < nf || nr > 4 * m_polish_limit) return;          // face not pinned down by the tight rows
+  std::vector<double> cand(snapped);
+  if (nf > 0)
+  {
+    // dense [nr x (nf + 1)] system  M x_F = target - A_N x_N
+    std::size_t const w = nf + 1;
+    std::vector<double> M(nr * w, 0.0);
+    for (std::size_t i = 0; i < nr; ++i)
+    {
+      std::int32_t const r = R[i];
+      double rhs = target[i];
+      for (std::int64_t k = m_last_ptr[r]; k < m_last_ptr[r + 1]; ++k)
+      {
+        std::int32_t const f = free_of[m_last_idx[k]];
+        if (f >= 0) M[i * w + f] += m_last_val[k];
+        else rhs -= m_last_val[k] * snapped[m_last_idx[k]];
+      }
+      M[i * w + nf] = rhs;
+    }
+    std::vector<std::size_t> pivot_row(nf);
+    std::vector<char> used(nr, 0);
+    for (std::size_t c = 0; c < nf; ++c)
+    {
+      std::size_t best = nr;
+      double big = 1e-9;
+      for (std::size_t i = 0; i < nr; ++i)
+        if (!used[i] && std::abs(M[i * w + c]) > big) { big = std::abs(M[i * w + c]); best = i; }
+      if (best == nr) return;                               // rank deficient: no unique vertex here
+      used[best] = 1;
+      pivot_row[c] = best;
+      double const inv = 1.0 / M[best * w + c];
+      for (std::size_t i = 0; i < nr; ++i)
+      {
+        if (i == best || M[i * w + c] == 0.0) continue;
+        double const f = M[i * w + c] * inv;
+        for (std::size_t k = c; k < w; ++k) M[i * w + k] -= f * M[best * w + k];
+      }
+    }
+    for (std::size_t i = 0; i < nr; ++i)
+      if (!used[i] && std::abs(M[i * w + nf]) > 1e-7) return;   // redundant tight rows disagree
+    for (std::size_t c = 0; c < nf; ++c) cand[F[c]] = M[pivot_row[c] * w + nf] / M[pivot_row[c] * w + c];
+  }
+  // accept only a point that is feasible to 1e-9 everywhere and leaves the objective where it was
+  double obj_old = 0, obj_new = 0;
+  for (std::size_t j = 0; j < n; ++j)
+  {
+    double const l = m_columns[j].lb, u = m_columns[j].ub;
+    if (cand[j] < l - 1e-9 * (1 + std::abs(l)) || cand[j] > u + 1e-9 * (1 + std::abs(u))) return;
+    cand[j] = std::min(std::max(cand[j], l), u);
+    obj_old += m_objective[j] * x[j];
+    obj_new += m_objective[j] * cand[j];
+  }
+  if (std::abs(obj_new - obj_old) > 1e-5 * (1 + std::abs(obj_old))) return;
+  for (std::size_t r = 0; r < m; ++r)
+  {
+    double act = 0;
+    for (std::int64_t k = m_last_ptr[r]; k < m_last_ptr[r + 1]; ++k) act += m_last_val[k] * cand[m_last_idx[k]];
+    double const lo = m_last_lo[r], hi = m_last_hi[r];
+    if (hi < inf && act > hi + 1e-9 * (1 + std::abs(hi))) return;
+    if (lo > -inf && act < lo - 1e-9 * (1 + std::abs(lo))) return;
+  }
+  x.swap(cand);
+  m_info.polished = true;
+}
+
 std::pair<Solver::Result, bool> CudaSolver::solve_continuous()
 {
-  upload_model();
-  check(m_ctx, mipcu_set_param(m_ctx, MIPCU_PARAM_EPS_REL, m_feas_tol));
-  check(m_ctx, mipcu_set_param(m_ctx, MIPCU_PARAM_TIME_LIMIT, m_time_limit));
-  check(m_ctx, mipcu_set_param(m_ctx, MIPCU_PARAM_VERBOSE, m_verbose ? 1 : 0));
-  check(m_ctx, mipcu_set_param(m_ctx, MIPCU_PARAM_OBJ_CUTOFF, std::nan("")));
-  check(m_ctx, mipcu_warm_start(m_ctx, m_start_x.size() == m_columns.size() ? m_start_x.data() : nullptr, nullptr));
-  std::vector<double> x;
-  LpOutcome const lp = solve_lp_on_device(&x, nullptr);
   using R = Solver::Result;
-  switch (lp.status)
+  // lazy constraints on a continuous model: solve, let the handlers see the optimum, re-solve
+  // with the rows they posted (warm started from the rejected point) until they accept
+  std::vector<double> x, restart;
+  for (int round = 0;; ++round)
   {
-    case MIPCU_OPTIMAL:
-      m_solution = std::move(x);
-      m_has_solution = true;
-      m_objective_value = std::inner_product(m_solution.begin(), m_solution.end(), m_objective.begin(), 0.0);
-      m_info.best_bound = lp.dual_obj;
-      m_info.proven_optimal = true;
-      return {R::Optimal, true};
-    case MIPCU_INFEASIBLE: return {R::Infeasible, false};
-    case MIPCU_UNBOUNDED: return {R::Unbounded, false};
-    case MIPCU_INFEASIBLE_OR_UNBOUNDED: return {R::InfeasibleOrUnbounded, false};
-    case MIPCU_ITERATION_LIMIT:
-    case MIPCU_TIME_LIMIT: return {R::Interrupted, false};
-    case MIPCU_NUMERICAL_ERROR: return {R::Error, false};
-    default: return {R::Other, false};
+    upload_model();
+    check(m_ctx, mipcu_set_param(m_ctx, MIPCU_PARAM_EPS_REL, m_feas_tol));
+    check(m_ctx, mipcu_set_param(m_ctx, MIPCU_PARAM_TIME_LIMIT, m_time_limit));
+    check(m_ctx, mipcu_set_param(m_ctx, MIPCU_PARAM_VERBOSE, m_verbose ? 1 : 0));
+    check(m_ctx, mipcu_set_param(m_ctx, MIPCU_PARAM_OBJ_CUTOFF, std::nan("")));
+    double const* start = !restart.empty() ? restart.data()
+                          : m_start_x.size() == m_columns.size() ? m_start_x.data() : nullptr;
+    check(m_ctx, mipcu_warm_start(m_ctx, start, nullptr));
+    LpOutcome const lp = solve_lp_on_device(&x, nullptr);
+    switch (lp.status)
+    {
+      case MIPCU_OPTIMAL:
+      {
+        bool added = false;
+        m_lazy_new_rows.clear();
+        if (!lazy_accepts(x, &added))
+        {
+          if (!added || round >= 1000) return {R::Other, false};   // rejected, nothing to learn from
+          m_info.lazy_rows += static_cast<std::int64_t>(m_lazy_new_rows.size());
+          restart = x;
+          continue;
+        }
+        polish_vertex(x);
+        m_solution = std::move(x);
+        m_has_solution = true;
+        m_objective_value = std::inner_product(m_solution.begin(), m_solution.end(), m_objective.begin(), 0.0);
+        m_info.best_bound = lp.dual_obj;
+        m_info.proven_optimal = true;
+        return {R::Optimal, true};
+      }
+      case MIPCU_INFEASIBLE: return {R::Infeasible, false};
+      case MIPCU_UNBOUNDED: return {R::Unbounded, false};
+      case MIPCU_INFEASIBLE_OR_UNBOUNDED: return {R::InfeasibleOrUnbounded, false};
+      case MIPCU_ITERATION_LIMIT:
+      case MIPCU_TIME_LIMIT: return {R::Interrupted, false};
+      case MIPCU_NUMERICAL_ERROR: return {R::Error, false};
+      default: return {R::Other, false};
+    }
   }
 }
 

@@ -109,11 +109,24 @@ struct CudaSolver : detail::ISolver
   // ---- statistics of the last solve (tests and bench read them) --------------------------------
   struct SolveInfo
   {
-    std::int64_t lp_solves = 0, lp_iterations = 0, nodes = 0, kernel_launches = 0, cuts = 0;
+    std::int64_t lp_solves = 0, lp_iterations = 0, nodes = 0, kernel_launches = 0, cuts = 0, lazy_rows = 0;
+    bool polished = false;   // the continuous optimum was snapped to an exact vertex (polish_vertex)
     double seconds = 0, best_bound = 0;
     bool proven_optimal = false;
   };
   SolveInfo m_info;
+
+  // ---- lazy constraints (reference miplib/lazy.hpp:19-41, miplib/scip/solver.cpp:544-651) -----
+  // Handlers are consulted for every candidate point the solve is about to accept (integral B&B
+  // candidates, the LP optimum of a continuous model).  While one runs, Var::value() answers
+  // with the candidate (ScipVar::value does the same, miplib/scip/var.cpp:69-74) and Solver::add
+  // posts the row AND records it as "new during this solve" so the tree can take it in.
+  std::vector<LazyConstrHandler> m_lazy_handlers;
+  std::vector<double> const* m_callback_x = nullptr;   // non-null: inside a handler call
+  std::vector<std::int64_t> m_lazy_new_rows;            // host rows posted from inside handlers
+  bool is_in_callback() const { return m_callback_x != nullptr; }
+  // true: every handler accepts x.  false: x was rejected; *added says whether a row was posted
+  bool lazy_accepts(std::vector<double> const& x, bool* added);
 
   void column_bounds_changed(std::size_t column);
   void hint(std::size_t column, double value);   // IVar::set_hint: start value of one column
@@ -135,6 +148,7 @@ struct CudaSolver : detail::ISolver
   };
   LpOutcome solve_lp_on_device(std::vector<double>* x_out, std::vector<double>* y_out);
   std::pair<Solver::Result, bool> solve_continuous();
+  void polish_vertex(std::vector<double>& x);   // crossover-lite, see solver.cpp
   std::pair<Solver::Result, bool> solve_integer();
   std::size_t column_of(Var const& v) const;
 
@@ -151,6 +165,8 @@ struct CudaSolver : detail::ISolver
   double m_feas_tol = 1e-6, m_int_tol = 1e-6, m_epsilon = 1e-9;
   double m_time_limit = 0;
   std::size_t m_nr_gpus = 1;
+  public:
+  std::size_t m_polish_limit = 400;              // polish_vertex: most free columns it will factor (0: off)
 };
 
 }  // namespace miplib

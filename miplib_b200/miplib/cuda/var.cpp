@@ -11,6 +11,8 @@ CudaSolver& CudaVar::backend() const { return static_cast<CudaSolver&>(*m_solver
 double CudaVar::value() const
 {
   CudaSolver const& s = backend();
+  // inside a lazy-constraint handler: the candidate under test (reference miplib/scip/var.cpp:69-74)
+  if (s.m_callback_x && m_column < s.m_callback_x->size()) return (*s.m_callback_x)[m_column];
   if (!s.m_has_solution || m_column >= s.m_solution.size())
     throw std::logic_error("Attempt to access value of variable before a solution was found.");
   return s.m_solution[m_column];

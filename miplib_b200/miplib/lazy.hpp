@@ -1,6 +1,7 @@
 // miplib/lazy.hpp - lazy-constraint callback interface (reference miplib/lazy.hpp:11-66).
-// The Cuda backend, like the reference's Lpsolve backend (miplib/lpsolve/solver.hpp:41),
-// answers add_lazy_constr_handler with "Not implemented yet."; the types exist so code compiles.
+// The Cuda backend consults the handlers for every candidate point its solve is about to accept
+// (integral branch-and-bound candidates, the optimum of a continuous model): see
+// cuda/solver.hpp "lazy constraints" and cuda/bnb.cpp.
 #pragma once
 
 #include <memory>
@@ -36,6 +37,7 @@ struct LazyConstrHandler
   std::vector<Var> depends() const { return p_impl->depends(); }
   bool is_feasible() { return p_impl->is_feasible(); }
   bool add() { return p_impl->add(); }
+  bool valid() const { return static_cast<bool>(p_impl); }   // not in the reference: null-handler guard
 
   private:
   std::shared_ptr<ILazyConstrHandler> p_impl;

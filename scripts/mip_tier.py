@@ -21,8 +21,8 @@ for nm in names:
     with tempfile.TemporaryDirectory() as d:
         path = Path(d) / "models.txt"
         write_models(path, [(nm, ALL[nm](), golden[nm]["objective"], 1e-9)])
-        env = {**os.environ, "MIPLIB_TEST_MODELS": str(path), "MIPLIB_TEST_ONLY_MODELS": "1",
+        env = {**os.environ, "MIPLIB_TEST_MODELS": str(path),
                "MIPLIB_TEST_TIME_LIMIT": os.environ.get("MIPLIB_TEST_TIME_LIMIT", "300")}
-        p = subprocess.run([str(build.UNIT_TEST)], capture_output=True, text=True, env=env)
+        p = subprocess.run([str(build.UNIT_TEST), "--filter", "Generated models"], capture_output=True, text=True, env=env)
         lines = [l for l in (p.stdout + p.stderr).splitlines() if nm in l or "failed" in l]
         print("\n".join(lines), flush=True)

@@ -125,15 +125,126 @@ GPU_TEST("Continuous LP through the expression API: a textbook optimum")
   REQUIRE(close(x.value(), 3, 1e-5) && close(y.value(), 1, 1e-5));
   REQUIRE(close(solver.get_objective_value(), 11, 1e-5));
   REQUIRE(close((3 * x + 2 * y).value(), 11, 1e-5));
+  // crossover-lite (CudaSolver::polish_vertex): the vertex is recovered exactly, so the
+  // reference's `==` style of assertion (test/unit/solver.cpp:37) holds for continuous columns too
+  REQUIRE(CudaSolver::of(solver).m_info.polished);
+  REQUIRE(x.value() == 3 && y.value() == 1);
+  REQUIRE(solver.get_objective_value() == 11);
   // tighten a bound through the Var handle and re-solve: only bounds go to the device
   x.set_ub(2);
   std::tie(r, has_solution) = solver.maximize(3 * x + 2 * y);
   REQUIRE(r == Solver::Result::Optimal);
   REQUIRE(close(x.value(), 2, 1e-5) && close(y.value(), 4.0 / 3, 1e-5));
+  REQUIRE(x.value() == 2 && close(y.value(), 4.0 / 3, 1e-15));
+  // polishing off: the first-order point itself, good to the stated tolerance only
+  CudaSolver::of(solver).m_polish_limit = 0;
+  std::tie(r, has_solution) = solver.maximize(3 * x + 2 * y);
+  REQUIRE(r == Solver::Result::Optimal && !CudaSolver::of(solver).m_info.polished);
+  REQUIRE(close(x.value(), 2, 1e-5) && close(y.value(), 4.0 / 3, 1e-5));
+  CudaSolver::of(solver).m_polish_limit = 400;
   // a new objective on the same rows
   std::tie(r, has_solution) = solver.minimize(x + y);
   REQUIRE(r == Solver::Result::Optimal);
   REQUIRE(close(solver.get_objective_value(), 0, 1e-5));
+}
+
+namespace {
+// the reference's own handler (test/unit/solver.cpp:171-198): v1 != v2, repaired by v1 + v2 == 1
+struct DifferHandler : ILazyConstrHandler
+{
+  DifferHandler(Solver const& solver, Var const& v1, Var const& v2) : m_solver(solver), m_v1(v1), m_v2(v2) {}
+  std::vector<Var> depends() const override { return {m_v1, m_v2}; }
+  bool is_feasible() override { ++calls; return m_v1.value_as<int>() != m_v2.value_as<int>(); }
+  bool add() override
+  {
+    if (m_v1.value_as<int>() != m_v2.value_as<int>()) return false;
+    m_solver.add(m_v1 + m_v2 == 1);
+    return true;
+  }
+  Solver m_solver;
+  Var m_v1, m_v2;
+  int calls = 0;
+};
+}  // namespace
+
+GPU_TEST("Lazy constraints at integral nodes (ref test/unit/solver.cpp:155-227)")
+{
+  for (int sense = 0; sense < 2; ++sense)
+  {
+    Solver solver(B, false);
+    Var v1(solver, Var::Type::Integer, 0, 1, "v1");
+    Var v2(solver, Var::Type::Integer, 0, 1, "v2");
+    auto handler = std::make_shared<DifferHandler>(solver, v1, v2);
+    solver.add_lazy_constr_handler(LazyConstrHandler(handler), true);
+    auto [r, has_solution] = sense == 0 ? solver.maximize(v1) : solver.minimize(v1);
+    REQUIRE(r == Solver::Result::Optimal);
+    REQUIRE(has_solution);
+    REQUIRE(v1.value() + v2.value() == 1);
+    REQUIRE(v1.value() == (sense == 0 ? 1 : 0));
+    REQUIRE(handler->calls >= 1);
+  }
+  // a model where the first integral candidates are all rejected: maximise x1 + x2 + x3 over
+  // binaries, the handler allows at most one of each pair (posted one pair at a time)
+  {
+    Solver solver(B, false);
+    std::vector<Var> x;
+    for (int i = 0; i < 3; ++i) x.emplace_back(solver, Var::Type::Binary, std::nullopt, std::nullopt, "x" + std::to_string(i));
+    struct PairHandler : ILazyConstrHandler
+    {
+      PairHandler(Solver const& s, std::vector<Var> const& v) : m_solver(s), m_x(v) {}
+      std::vector<Var> depends() const override { return m_x; }
+      bool is_feasible() override
+      {
+        for (int i = 0; i < 3; ++i)
+          for (int j = i + 1; j < 3; ++j)
+            if (m_x[i].value_as<int>() + m_x[j].value_as<int>() > 1) return false;
+        return true;
+      }
+      bool add() override
+      {
+        for (int i = 0; i < 3; ++i)
+          for (int j = i + 1; j < 3; ++j)
+            if (m_x[i].value_as<int>() + m_x[j].value_as<int>() > 1)
+            {
+              m_solver.add(m_x[i] + m_x[j] <= 1);
+              ++posted;
+              return true;
+            }
+        return false;
+      }
+      Solver m_solver;
+      std::vector<Var> m_x;
+      int posted = 0;
+    };
+    auto handler = std::make_shared<PairHandler>(solver, x);
+    solver.add_lazy_constr_handler(LazyConstrHandler(handler), true);
+    auto [r, has_solution] = solver.maximize(3 * x[0] + 2 * x[1] + x[2]);
+    REQUIRE(r == Solver::Result::Optimal && has_solution);
+    REQUIRE(x[0].value() == 1 && x[1].value() == 0 && x[2].value() == 0);
+    REQUIRE(solver.get_objective_value() == 3);
+    REQUIRE(handler->posted >= 1 && CudaSolver::of(solver).m_info.lazy_rows == handler->posted);
+  }
+}
+
+GPU_TEST("Lazy constraints on a continuous model: re-solve until the handlers accept")
+{
+  Solver solver(B, false);
+  Var x(solver, Var::Type::Continuous, 0, 1, "x");
+  Var y(solver, Var::Type::Continuous, 0, 1, "y");
+  struct CapHandler : ILazyConstrHandler
+  {
+    CapHandler(Solver const& s, Var const& a, Var const& b) : m_solver(s), m_a(a), m_b(b) {}
+    std::vector<Var> depends() const override { return {m_a, m_b}; }
+    bool is_feasible() override { return m_a.value() + m_b.value() <= 1.5 + 1e-6; }
+    bool add() override { m_solver.add(m_a + m_b <= 1.5); return true; }
+    Solver m_solver;
+    Var m_a, m_b;
+  };
+  solver.add_lazy_constr_handler(LazyConstrHandler(std::make_shared<CapHandler>(solver, x, y)), false);
+  auto [r, has_solution] = solver.maximize(2 * x + y);
+  REQUIRE(r == Solver::Result::Optimal && has_solution);
+  REQUIRE(close(x.value(), 1, 1e-5) && close(y.value(), 0.5, 1e-5));
+  REQUIRE(CudaSolver::of(solver).m_info.lazy_rows == 1);
 }
 
 GPU_TEST("Result contract: Infeasible and Unbounded LPs (ref miplib/lpsolve/solver.cpp:171-199)")
