@@ -302,11 +302,16 @@ def run_cuda(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
-                     "peak_source": peak_src, "traffic": ncu_traffic(dom),
+                     "peak_source": peak_src, "traffic": ncu_traffic(dom) if world == 1 else None,
                      "algorithmic_bytes_per_launch": int(dom_bytes), "launch_us": dom_us,
                      "all_kernels": {k: {"launch_us": v[0], "bytes": int(v[1]), "GBps": v[1] / v[0] / 1e3}
                                      for k, v in kernels.items()}},
     }
+    line["config"]["matrix_format"] = "SELL-32-256, one lane per row (CSR lanes-per-row kernels for long-row models)"
+    if world > 1:
+        line["roofline"]["col_step_split_us"] = {
+            "partial_spmv": float(np.mean([s.col_partial_us for s in stats])),
+            "exchange_and_primal": float(np.mean([s.col_exchange_us for s in stats]))}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(L)
     print(json.dumps(line), flush=True)

@@ -86,6 +86,8 @@ typedef struct mipcu_stats {
   double  col_kernel_us;   /* mean in-situ duration of the fused K'.yhat / primal-step kernel */
   int64_t row_kernel_bytes;/* algorithmic bytes of one launch of each */
   int64_t col_kernel_bytes;
+  double  col_partial_us;  /* row-sharded contexts: the local partial K_g'.yhat_g SpMV inside col_kernel_us */
+  double  col_exchange_us; /* row-sharded contexts: exchange (+ primal step) inside col_kernel_us */
 } mipcu_stats;
 
 /* --- lifetime ------------------------------------------------------------------------------ */

@@ -36,7 +36,7 @@ class _Stats(C.Structure):
         ("step_size", C.c_double), ("primal_weight", C.c_double), ("solve_seconds", C.c_double),
         ("iter_seconds", C.c_double), ("setup_seconds", C.c_double), ("row_kernel_us", C.c_double),
         ("col_kernel_us", C.c_double), ("row_kernel_bytes", C.c_int64),
-        ("col_kernel_bytes", C.c_int64),
+        ("col_kernel_bytes", C.c_int64), ("col_partial_us", C.c_double), ("col_exchange_us", C.c_double),
     ]
 
 
@@ -60,6 +60,8 @@ class Stats:
     col_kernel_us: float
     row_kernel_bytes: int
     col_kernel_bytes: int
+    col_partial_us: float = 0.0
+    col_exchange_us: float = 0.0
 
     @classmethod
     def from_c(cls, s: _Stats) -> "Stats":

@@ -137,7 +137,6 @@ int mipcu_create_sharded(mipcu_ctx** out, int device, int rank, int world, const
   return guarded(nullptr, [&] {
     MIPCU_REQUIRE(world >= 1 && rank >= 0 && rank < world, "mipcu_create_sharded: bad rank/world");
     mipcu_ctx* ctx = create_on(device);
-    if (world > 1) ctx->pool_alloc = false;   // exchange buffers are exported over CUDA IPC
     try {
       if (world > 1) dist_init(ctx, rank, world, unique_id);
     } catch (...) {

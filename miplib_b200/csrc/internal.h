@@ -163,7 +163,9 @@ struct mipcu_ctx {
   void* flush_buf = nullptr;
 
   int64_t launches = 0;   // kernels launched by the current call
-  bool pool_alloc = false;   // model arrays come from the stream-ordered memory pool (single-GPU contexts)
+  cudaEvent_t split_event = nullptr;   // sharded col step: recorded between the partial SpMV and the exchange
+  bool pool_alloc = false;   // model arrays come from the stream-ordered memory pool
+  std::vector<void*> raw_allocs;   // arrays that had to come from cudaMalloc (exported over CUDA IPC)
 };
 
 // context whose call is executing on this thread: tells setup.cu's allocator which stream / pool

@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cmath>
 
+#include <algorithm>
 #include "internal.h"
 #include "kernels.cuh"
 
@@ -17,27 +18,38 @@ inline int grid_for(int64_t n, int per_block = kThreads) {
   return (int)((n + per_block - 1) / per_block);
 }
 
-// Device allocations of this file.  A single-GPU context allocates stream-ordered from the device's
-// memory pool (release threshold raised at creation, api.cu): cudaMalloc / cudaFree synchronise the
+// Device allocations of this file.  A context allocates stream-ordered from the device's memory
+// pool (release threshold raised at creation, api.cu): cudaMalloc / cudaFree synchronise the
 // device and map / unmap memory on every call, which made RE-loading a config-3 model cost 0.7 s;
-// from the pool the same buffers are reused.  Row-sharded contexts export buffers over CUDA IPC,
-// which pool memory does not support, so they keep cudaMalloc.
+// from the pool the same buffers are reused.  The few vectors a row-sharded context exports over
+// CUDA IPC (pool memory cannot be exported) come from cudaMalloc and are remembered as such.
+thread_local bool g_alloc_exported = false;
+
 template <class T>
 T* dalloc(int64_t count) {
   T* p = nullptr;
   const size_t bytes = sizeof(T) * (size_t)(count > 0 ? count : 1);
-  const mipcu_ctx* ctx = g_alloc_ctx;
-  if (ctx && ctx->pool_alloc) MIPCU_CK(cudaMallocAsync(&p, bytes, ctx->stream));
-  else MIPCU_CK(cudaMalloc(&p, bytes));
+  mipcu_ctx* ctx = const_cast<mipcu_ctx*>(g_alloc_ctx);
+  if (ctx && ctx->pool_alloc && !g_alloc_exported) {
+    MIPCU_CK(cudaMallocAsync(&p, bytes, ctx->stream));
+  } else {
+    MIPCU_CK(cudaMalloc(&p, bytes));
+    if (ctx && ctx->pool_alloc) ctx->raw_allocs.push_back(p);
+  }
   return p;
 }
 
 template <class T>
 void dfree(T*& p) {
   if (p) {
-    const mipcu_ctx* ctx = g_alloc_ctx;
-    if (ctx && ctx->pool_alloc) cudaFreeAsync(p, ctx->stream);
-    else cudaFree(p);
+    mipcu_ctx* ctx = const_cast<mipcu_ctx*>(g_alloc_ctx);
+    bool raw = !(ctx && ctx->pool_alloc);
+    if (!raw) {
+      auto it = std::find(ctx->raw_allocs.begin(), ctx->raw_allocs.end(), (void*)p);
+      if (it != ctx->raw_allocs.end()) { raw = true; ctx->raw_allocs.erase(it); }
+    }
+    if (raw) cudaFree(p);
+    else cudaFreeAsync(p, ctx->stream);
   }
   p = nullptr;
 }
@@ -535,7 +547,12 @@ void load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* r
   double** nvecs[] = {&ctx->cs, &ctx->ls, &ctx->us, &ctx->d2, &ctx->xbar, &ctx->x0, &ctx->aty,
                       &ctx->aty0, &ctx->xhat_first, &ctx->xhat_chk, &ctx->aty_cand, &ctx->tmp_n,
                       &ctx->x_sol};
-  for (double** p : nvecs) *p = dalloc<double>(n + 2);   // +2: TMA reads an even number of doubles
+  for (double** p : nvecs) {
+    // row-sharded: the exchange buffers are mapped by the peers (p2p.cu)
+    g_alloc_exported = ctx->world > 1 && (p == &ctx->xbar || p == &ctx->xhat_chk || p == &ctx->tmp_n || p == &ctx->x_sol);
+    *p = dalloc<double>(n + 2);   // +2: TMA reads an even number of doubles
+    g_alloc_exported = false;
+  }
   double** mvecs[] = {&ctx->los, &ctx->his, &ctx->d1, &ctx->y, &ctx->y0, &ctx->yhat, &ctx->tmp_m,
                       &ctx->y_sol};
   for (double** p : mvecs) *p = dalloc<double>(m + 2);

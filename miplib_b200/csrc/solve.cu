@@ -390,6 +390,7 @@ void col_step(mipcu_ctx* ctx, int i, bool check, const double* xhat_in, double* 
     // row-sharded, fused exchange: local partial K_g' yhat_g, then ONE kernel that pulls this rank's
     // slice of every partial over NVLink, runs the primal step on it and pushes xbar to the peers
     spmv_plain(ctx, ctx->cols, ctx->yhat, ctx->tmp_n);
+    if (ctx->split_event) MIPCU_CK(cudaEventRecord(ctx->split_event, ctx->stream));
     p2p_primal_step(ctx, a, check, xhat_out != nullptr);
     if (xhat_out == ctx->xhat_chk) p2p_allgather(ctx, 1);   // gathered by the KKT pass: must be whole
     return;
@@ -398,6 +399,7 @@ void col_step(mipcu_ctx* ctx, int i, bool check, const double* xhat_in, double* 
     // row-sharded, NCCL variant: local partial -> all-reduce over NVLink -> elementwise primal step
     // (replicated: every rank computes the same xbar from the same summed vector)
     spmv_plain(ctx, ctx->cols, ctx->yhat, ctx->tmp_n);
+    if (ctx->split_event) MIPCU_CK(cudaEventRecord(ctx->split_event, ctx->stream));
     dist_allreduce(ctx, ctx->tmp_n, (size_t)ctx->n, false);
     const int g = grid_for(ctx->n, kRowsPerCta);
     const bool store = xhat_out != nullptr;
@@ -450,7 +452,7 @@ void restart_apply(mipcu_ctx* ctx) {
 // survives as the candidate solution / restart anchor; xhat of the next block's iteration 0 is
 // stored into xhat_first by the last col step (or by k_restart_apply).
 // time_events != null: record events around the row and col kernels of iteration 1.
-void enqueue_block(mipcu_ctx* ctx, int period, cudaEvent_t* time_events) {
+void enqueue_block(mipcu_ctx* ctx, int period, cudaEvent_t* time_events, cudaEvent_t split = nullptr) {
   cudaStream_t st = ctx->stream;
   for (int i = 0; i < period; ++i) {
     const bool first = (i == 0), last = (i == period - 1);
@@ -462,7 +464,9 @@ void enqueue_block(mipcu_ctx* ctx, int period, cudaEvent_t* time_events) {
     const double* xin = first ? ctx->xhat_first : ctx->xhat_chk;
     double* xout = last ? ctx->xhat_first : (i == period - 2 ? ctx->xhat_chk : nullptr);
     // period == 2: iteration 0 is both "first" (reads xhat_first) and period-2 (stores xhat_chk)
+    ctx->split_event = (timed && ctx->world > 1) ? split : nullptr;
     col_step(ctx, i, first || last, xin, xout);
+    ctx->split_event = nullptr;
     if (timed) MIPCU_CK(cudaEventRecord(time_events[2], st));
     if (first) {
       k_ctrl_first<<<1, kThreads, 0, st>>>(ctx->d_sc, ctx->partials, global_row_sums(ctx),
@@ -604,7 +608,7 @@ void solve_lp(mipcu_ctx* ctx, mipcu_stats* out) {
 
   int status = -1;
   int64_t blocks_enqueued = 0, blocks_seen = 0;
-  double row_us = 0.0, col_us = 0.0;
+  double row_us = 0.0, col_us = 0.0, partial_us = 0.0;
   int64_t timed_samples = 0;
   Scalars last = h;
   auto can_enqueue = [&]() { return blocks_enqueued * (int64_t)period < iter_limit; };
@@ -614,7 +618,7 @@ void solve_lp(mipcu_ctx* ctx, mipcu_stats* out) {
       MIPCU_CK(cudaGraphLaunch(ctx->graph_exec, st));
       ctx->launches += launches_per_block;
     } else {
-      enqueue_block(ctx, period, ev_time[slot]);
+      enqueue_block(ctx, period, ev_time[slot], ctx->ev[10 + slot]);
     }
     MIPCU_CK(cudaMemcpyAsync(ctx->h_sc + slot, ctx->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
     MIPCU_CK(cudaEventRecord(ev_slot[slot], st));
@@ -634,6 +638,11 @@ void solve_lp(mipcu_ctx* ctx, mipcu_stats* out) {
       MIPCU_CK(cudaEventElapsedTime(&a, ev_time[slot][0], ev_time[slot][1]));
       MIPCU_CK(cudaEventElapsedTime(&b, ev_time[slot][1], ev_time[slot][2]));
       row_us += 1e3 * a; col_us += 1e3 * b; ++timed_samples;
+      if (ctx->world > 1) {
+        float c = 0.f;
+        MIPCU_CK(cudaEventElapsedTime(&c, ev_time[slot][1], ctx->ev[10 + slot]));
+        partial_us += 1e3 * c;
+      }
     }
     if (verbose)
       fprintf(stderr,
@@ -688,6 +697,8 @@ void solve_lp(mipcu_ctx* ctx, mipcu_stats* out) {
   out->col_kernel_us = timed_samples ? col_us / timed_samples : 0.0;
   out->row_kernel_bytes = row_kernel_bytes(ctx);
   out->col_kernel_bytes = col_kernel_bytes(ctx);
+  out->col_partial_us = (timed_samples && ctx->world > 1) ? partial_us / timed_samples : 0.0;
+  out->col_exchange_us = (timed_samples && ctx->world > 1) ? out->col_kernel_us - out->col_partial_us : 0.0;
   out->solve_seconds =
       std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }

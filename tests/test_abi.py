@@ -31,7 +31,7 @@ def test_library_is_sm100a_only(built):
 def test_stats_struct_layout_matches_header(built):
     from miplib_b200 import capi
     # 2 x int32 + 2 x int64 + 12 x double + 2 x int64
-    assert ctypes.sizeof(capi._Stats) == 8 + 16 + 12 * 8 + 16
+    assert ctypes.sizeof(capi._Stats) == 8 + 16 + 12 * 8 + 16 + 16   # + col_partial_us, col_exchange_us
 
 
 def test_no_cpu_fallback_without_gpu(built):

@@ -182,6 +182,29 @@ def test_mip_tier_relaxations(engine, golden):
         assert_certificate(L, engine)
 
 
+@pytest.mark.parametrize("cfg", [4, 5])
+def test_mip_configs_full_size_root_relaxation_certificate(engine, cfg):
+    """BASELINE.json configs 4 (set cover 20k x 50k) and 5 (knapsack 500 x 100k + 100 big-M switch
+    rows) at FULL size: no exact solver finishes these here, so parity is the size-independent
+    property - the independent FP64 certificate of the returned primal-dual pair (1e-6 relative
+    KKT), weak duality, binaries inside their box.  Config 5 exercises both kernel families at once:
+    rows of ~1 600 nonzeros (CSR, 32 lanes per row) and columns of ~9 (SELL, one lane per row)."""
+    L = gen.config(cfg)
+    engine.load_lp(L)
+    st = engine.solve()
+    assert_optimal(st)
+    cert = assert_certificate(L, engine)
+    assert rel(st.primal_obj, cert["primal_obj"]) <= 1e-9
+    sgn = -1.0 if L.maximize else 1.0
+    assert sgn * cert["dual_obj"] <= sgn * cert["primal_obj"] + 3e-6 * (1 + abs(cert["primal_obj"]))
+    x = engine.x()
+    assert x.min() >= -1e-12 and x.max() <= 1 + 1e-12
+    if cfg == 4:
+        # the criterion is the 2-norm of the residual relative to 1 + ||b|| = 1 + sqrt(20 000):
+        # no single cover row can be short by more than 1e-6 * 142.4
+        assert (L.A @ x).min() >= 1 - 1.5e-4
+
+
 def test_c2_full_size_certificate(engine):
     """BASELINE config 2 (100k x 200k): no exact CPU solver finishes, so parity is the
     independently verified optimality certificate."""
