@@ -289,8 +289,11 @@ def run_cuda(args, rank, world, local_rank):
         "config": {"workload": workload_name(args.config), "m": m, "n": n, "nnz": int(A.nnz),
                    "l2": "inputs larger than L2 (no flush)" if A.nnz > 8e6 else "L2-resident working set",
                    "parallelism": "single GPU" if world == 1 else
-                   f"row-sharded x{world}, " + ("fused P2P reduce-scatter + primal step + all-gather kernel over NVLink"
-                                                 if eng.get_param("shard_exchange") == 1 else "NCCL all-reduce of K'y")},
+                   f"row-sharded x{world}, " + {
+                       2: "block-owner exchange: each rank streams its row block of K and its column block of K', "
+                          "yhat / xbar slices pushed into peer memory over NVLink from the kernels' epilogues",
+                       1: "fused P2P reduce-scatter + primal step + all-gather kernel over NVLink",
+                       0: "NCCL all-reduce of K'y"}[int(eng.get_param("shard_exchange"))]},
         "time_to_tol_s": resident_s / args.steps,
         "iterations_per_solve": iters / args.steps,
         "device_iter_seconds_per_solve": dev_iter_s / args.steps,
@@ -409,8 +412,9 @@ def main():
     ap.add_argument("--workload", default="lp", choices=["lp", "nodes"])
     ap.add_argument("--nodes-per-gpu", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--shard-exchange", type=int, default=1, choices=[0, 1],
-                    help="N > 1: 1 = fused P2P exchange kernel (default), 0 = ncclAllReduce")
+    ap.add_argument("--shard-exchange", type=int, default=2, choices=[0, 1, 2],
+                    help="N > 1: 2 = block-owner exchange (row block of K + column block of K' per rank), "
+                         "1 = fused P2P reduce-scatter / primal step / all-gather kernel, 0 = ncclAllReduce")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

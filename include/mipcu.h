@@ -62,9 +62,14 @@ enum {
                                      better than this objective value (model's own sense); NaN = off */
   MIPCU_PARAM_USE_TMA = 10,       /* kernel variant: -1 auto (default), 0: sub-warp per row, 1: TMA-streamed tiles,
                                      2: CSR-stream (products staged in shared memory) */
-  MIPCU_PARAM_SHARD_EXCHANGE = 11,/* row-sharded contexts: 1 (default) fused reduce-scatter + primal step +
+  MIPCU_PARAM_SHARD_EXCHANGE = 11,/* row-sharded contexts: 2 (default) block-owner exchange - every rank streams its row
+                                     block of K and its column block of K', slices of yhat / xbar pushed into peer
+                                     memory from the kernels' epilogues; 1: fused reduce-scatter + primal step +
                                      all-gather kernel over NVLink peer memory; 0: ncclAllReduce. Set before load */
-  MIPCU_PARAM_COUNT_ = 12
+  MIPCU_PARAM_USE_PDL = 12,       /* 1: the two iteration kernels are launched as programmatic dependents of each
+                                     other (the head of the nonzero stream is fetched while the previous kernel drains);
+                                     0: plain stream order.  Ignored when the block is replayed as a CUDA graph */
+  MIPCU_PARAM_COUNT_ = 13
 };
 
 typedef struct mipcu_stats {

@@ -61,7 +61,8 @@ void set_default_params(mipcu_ctx* ctx) {
   ctx->params[MIPCU_PARAM_THREADS_PER_ROW] = 0;
   ctx->params[MIPCU_PARAM_OBJ_CUTOFF] = NAN;
   ctx->params[MIPCU_PARAM_USE_TMA] = -1;
-  ctx->params[MIPCU_PARAM_SHARD_EXCHANGE] = 1;
+  ctx->params[MIPCU_PARAM_SHARD_EXCHANGE] = 2;
+  ctx->params[MIPCU_PARAM_USE_PDL] = 0;
 }
 
 mipcu_ctx* create_on(int device) {
@@ -187,6 +188,7 @@ int mipcu_load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64
     p2p_teardown(ctx);
     load_lp(ctx, m, n, nnz, row_ptr, col_idx, val, c, lb, ub, row_lo, row_hi, maximize);
     p2p_setup(ctx);   // collective on sharded contexts: maps the peers' exchange buffers
+    own_setup(ctx);   // block-owner exchange (MIPCU_PARAM_SHARD_EXCHANGE = 2): column block of the whole matrix
   });
 }
 

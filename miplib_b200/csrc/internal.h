@@ -101,6 +101,10 @@ struct Scalars {
 
 // Row-sharded contexts: the peers' copies of the exchange buffers, mapped with CUDA IPC (p2p.cu)
 constexpr int kMaxPeers = 16;
+// flag block of a rank (u64 each): [0, W) ready, [W, 2W) done, [2W] CTA counter, [2W+1] epoch of the
+// fused-exchange kernels; [kOwnFlagBase, kOwnFlagBase + W) arrival flags of the block-owner kernels
+constexpr int kOwnFlagBase = 2 * kMaxPeers + 2;
+constexpr int kFlagCount = 3 * kMaxPeers + 2;
 struct PeerTable {
   int world = 0, rank = 0;
   int j0[kMaxPeers + 1] = {};               // column slice of rank g: [j0[g], j0[g+1])
@@ -109,6 +113,10 @@ struct PeerTable {
   double* xhat_chk[kMaxPeers] = {};
   double* x_sol[kMaxPeers] = {};
   unsigned long long* flags[kMaxPeers] = {};
+  // block-owner exchange (MIPCU_PARAM_SHARD_EXCHANGE = 2): every rank keeps the WHOLE yhat, each
+  // rank's row kernel pushes its slice [i0[g], i0[g+1]) into all of them
+  int i0[kMaxPeers + 1] = {};
+  double* yhat_full[kMaxPeers] = {};
 };
 
 }  // namespace mipcu
@@ -128,12 +136,22 @@ struct mipcu_ctx {
   mipcu::PeerTable peers;         // world == peers.world: the fused P2P exchange is usable
   std::vector<void*> peer_mappings;
   unsigned long long* p2p_flags = nullptr;
+  bool own_ready = false;             // block-owner exchange: column block built, yhat_full mapped
+  bool use_pdl = false;               // iteration kernels launched as programmatic dependents (MIPCU_PDL)
+  int own_variant = 0;                // laboratory switches (p2p.cu), 0 = shipped protocol
+  unsigned long long own_epoch = 0;   // barrier generation of the block-owner kernels (same on all ranks)
 
   // model as loaded (unscaled), device resident
   int m = 0, n = 0;
   int64_t nnz = 0;
   bool loaded = false, maximize = false;
   mipcu::Csr rows, cols;                 // scaled IN PLACE by prepare()
+  // row-sharded, block-owner exchange: columns [j0, j1) of the WHOLE matrix (CSR of K'[j0:j1, :],
+  // global row indices), assembled from all ranks' blocks at load; yhat_full: m_glob doubles
+  mipcu::Csr colblk;
+  double* yhat_full = nullptr;
+  int m_glob = 0;
+  int row_off[mipcu::kMaxPeers + 1] = {};
   double *c = nullptr, *lb = nullptr, *ub = nullptr, *lo = nullptr, *hi = nullptr;
   // scaled copies + diagonal scalings
   double *cs = nullptr, *ls = nullptr, *us = nullptr, *los = nullptr, *his = nullptr;
@@ -188,14 +206,21 @@ int kernel_format(const mipcu_ctx* ctx, const Csr& A);   // 0: SELL lane-per-row
 void set_bounds(mipcu_ctx* ctx, int64_t n_changed, const int64_t* cols, const double* lb,
                 const double* ub);
 void spmv_host(mipcu_ctx* ctx, int transpose, const double* v, double* out);
+void build_col_block(mipcu_ctx* ctx);   // collective: the column block of the block-owner exchange
 
 // ---- dist.cu --------------------------------------------------------------------------------
 void dist_allreduce(mipcu_ctx* ctx, double* buf, size_t count, bool max_instead_of_sum);
 double dist_sum_scalar(mipcu_ctx* ctx, double v);
+void dist_allgather_bytes(mipcu_ctx* ctx, const void* send_dev, void* recv_dev, size_t bytes_per_rank);
 
 // ---- p2p.cu ---------------------------------------------------------------------------------
 struct ColStepArgs;
 bool p2p_active(const mipcu_ctx* ctx);
+bool own_active(const mipcu_ctx* ctx);   // block-owner exchange in use
+struct RowStepArgs;
+void own_setup(mipcu_ctx* ctx);          // collective, after p2p_setup: builds the column block
+void own_row_step(mipcu_ctx* ctx, const RowStepArgs& a, bool check);
+void own_col_step(mipcu_ctx* ctx, int iter_in_block, bool check, const double* xhat_in, double* xhat_out);
 void p2p_setup(mipcu_ctx* ctx);
 void p2p_teardown(mipcu_ctx* ctx);
 void p2p_primal_step(mipcu_ctx* ctx, const ColStepArgs& a, bool check, bool store);

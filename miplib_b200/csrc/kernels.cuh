@@ -30,6 +30,36 @@ __device__ __forceinline__ int ld_stream(const int* p) {
   return v;
 }
 
+// Programmatic dependent launch (both no-ops in a kernel launched without the attribute).
+// pdl_trigger: the next kernel of the stream may start filling SM slots this grid no longer needs;
+// pdl_wait: everything the previous kernels wrote is visible from here on.  The iteration kernels
+// read only the (constant) matrix before pdl_wait, so the head of their nonzero stream is in
+// flight while the previous kernel drains.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Host side: launch `kernel` on kThreads-wide CTAs, optionally as a programmatic dependent of the
+// previous kernel in the stream.
+template <class... Params, class... Args>
+inline void launch_kernel(void (*kernel)(Params...), int grid, cudaStream_t stream, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  MIPCU_CK(cudaLaunchKernelEx(&cfg, kernel, Params(args)...));
+}
+
+// `pre` hook of cta_row_sums for kernels with nothing to wait for
+struct NoWait {
+  __device__ __forceinline__ bool operator()() const { return true; }
+};
+
 __device__ __forceinline__ double clampd(double v, double lo, double hi) {
   return fmin(fmax(v, lo), hi);
 }
@@ -53,37 +83,54 @@ __device__ __forceinline__ double clampd(double v, double lo, double hi) {
 //    independent chains per lane.
 constexpr int kSellUnroll = 8;
 
-template <int TPR>
-__device__ __forceinline__ void cta_row_sums(const int* __restrict__ ptr,
+//
+// `pre()` is called by every thread exactly once, after the first loads of the matrix stream have
+// been issued and before anything of `vec` is read: the place to wait for the producer of `vec`
+// (programmatic dependent launch, a cross-GPU barrier).  It returns false when the kernel has
+// nothing to do (solve finished); the function then returns false with s_sum undefined.
+template <int TPR, class Pre>
+__device__ __forceinline__ bool cta_row_sums(const int* __restrict__ ptr,
                                              const int* __restrict__ idx,
                                              const double* __restrict__ val,
                                              const unsigned char* __restrict__ perm,
                                              const double* __restrict__ vec, int nrows,
-                                             double* s_sum) {
+                                             double* s_sum, Pre pre) {
   if constexpr (TPR == 0) {
     constexpr int U = kSellUnroll;
     const int lane = threadIdx.x & 31;
     const int slice = blockIdx.x * (kRowsPerCta / 32) + (threadIdx.x >> 5);
     const int beg = ptr[slice], end = ptr[slice + 1];
+    const int slot = perm[blockIdx.x * kRowsPerCta + threadIdx.x];
     double acc0 = 0.0, acc1 = 0.0;
-    for (int p = beg + lane; p < end; p += 32 * U) {
-      double v[U];
-      int c[U];
+    double v[U];
+    int c[U];
+    int p = beg + lane;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool ok = p + 32 * u < end;     // warp-uniform: a slice is padded to whole lanes
-        v[u] = ok ? ld_stream(val + p + 32 * u) : 0.0;
-        c[u] = ok ? ld_stream(idx + p + 32 * u) : -1;
-      }
+    for (int u = 0; u < U; ++u) {
+      const bool ok = p + 32 * u < end;       // warp-uniform: a slice is padded to whole lanes
+      v[u] = ok ? ld_stream(val + p + 32 * u) : 0.0;
+      c[u] = ok ? ld_stream(idx + p + 32 * u) : -1;
+    }
+    if (!pre()) return false;
+    while (true) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const double x = c[u] >= 0 ? __ldg(vec + c[u]) : 0.0;
         if (u & 1) acc1 = fma(v[u], x, acc1); else acc0 = fma(v[u], x, acc0);
       }
+      p += 32 * U;
+      if (p - lane >= end) break;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool ok = p + 32 * u < end;
+        v[u] = ok ? ld_stream(val + p + 32 * u) : 0.0;
+        c[u] = ok ? ld_stream(idx + p + 32 * u) : -1;
+      }
     }
-    s_sum[perm[blockIdx.x * kRowsPerCta + threadIdx.x]] = acc0 + acc1;
+    s_sum[slot] = acc0 + acc1;
     __syncthreads();
   } else {
+    if (!pre()) return false;
     constexpr int SUBS = kThreads / TPR;        // rows in flight per pass
     const int lane = threadIdx.x % TPR;
     const int sub = threadIdx.x / TPR;
@@ -112,6 +159,15 @@ __device__ __forceinline__ void cta_row_sums(const int* __restrict__ ptr,
     }
     __syncthreads();
   }
+  return true;
+}
+
+template <int TPR>
+__device__ __forceinline__ void cta_row_sums(const int* __restrict__ ptr, const int* __restrict__ idx,
+                                             const double* __restrict__ val,
+                                             const unsigned char* __restrict__ perm,
+                                             const double* __restrict__ vec, int nrows, double* s_sum) {
+  cta_row_sums<TPR>(ptr, idx, val, perm, vec, nrows, s_sum, NoWait());
 }
 
 // Deterministic CTA reduction of NQ running sums; thread 0 stores them to
@@ -148,39 +204,48 @@ struct RowStepArgs {
   double* kx_save;   // CHECK, last iteration of a block: K xbar kept for the primal-ray test (or null)
 };
 
+// The per-row part of the row step, given (K xbar)_i: dual proximal step, Halpern / reflection
+// update of y; on CHECK iterations the five partial sums of the restart / certificate tests.
+// Returns yhat_i.  Shared by the single-GPU kernel and the block-owner kernel of p2p.cu.
+template <bool CHECK>
+__device__ __forceinline__ double row_epilogue(const RowStepArgs& a, const int i, const double kx,
+                                               const double sigma, const double w_new, double (&red)[5]) {
+  const double yi = a.y[i], y0i = a.y0[i], lo = a.lo[i], hi = a.hi[i];
+  const double t = kx - yi / sigma;
+  const double yh = sigma * (clampd(t, lo, hi) - t);
+  a.yhat[i] = yh;
+  a.y[i] = w_new * (2.0 * yh - yi) + (1.0 - w_new) * y0i;
+  if (CHECK) {
+    const double dy = yh - yi, d0 = yh - y0i;
+    red[0] = dy * dy;
+    red[1] = d0 * d0;
+    const double yp = fmax(yh, 0.0), ym = fmax(-yh, 0.0);
+    red[2] = (isfinite(lo) ? lo * yp : 0.0) - (isfinite(hi) ? hi * ym : 0.0);
+    // dy as a candidate Farkas ray
+    const double dp = fmax(dy, 0.0), dm = fmax(-dy, 0.0);
+    red[3] = (isfinite(lo) ? lo * dp : 0.0) - (isfinite(hi) ? hi * dm : 0.0);
+    const double rv = (isfinite(lo) ? 0.0 : dp) + (isfinite(hi) ? 0.0 : dm);
+    red[4] = rv * rv;
+    if (a.kx_save) a.kx_save[i] = kx;
+  }
+  return yh;
+}
+
 template <int TPR, bool CHECK>
 __global__ void __launch_bounds__(kThreads)
 k_row_step(const RowStepArgs a) {
   __shared__ double s_sum[kRowsPerCta];
   const Scalars* sc = a.sc;
-  if (sc->done) return;
-  cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.perm, a.xbar, a.m, s_sum);
+  pdl_trigger();
+  if (!cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.perm, a.xbar, a.m, s_sum,
+                         [&] { pdl_wait(); return !sc->done; }))
+    return;
   const double sigma = sc->sigma;
   const double k = (double)(sc->k_base + a.iter_in_block);
   const double w_new = (k + 1.0) / (k + 2.0);
   const int i = blockIdx.x * kRowsPerCta + threadIdx.x;
   double red[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  if (i < a.m) {
-    const double kx = s_sum[threadIdx.x];
-    const double yi = a.y[i], y0i = a.y0[i], lo = a.lo[i], hi = a.hi[i];
-    const double t = kx - yi / sigma;
-    const double yh = sigma * (clampd(t, lo, hi) - t);
-    a.yhat[i] = yh;
-    a.y[i] = w_new * (2.0 * yh - yi) + (1.0 - w_new) * y0i;
-    if (CHECK) {
-      const double dy = yh - yi, d0 = yh - y0i;
-      red[0] = dy * dy;
-      red[1] = d0 * d0;
-      const double yp = fmax(yh, 0.0), ym = fmax(-yh, 0.0);
-      red[2] = (isfinite(lo) ? lo * yp : 0.0) - (isfinite(hi) ? hi * ym : 0.0);
-      // dy as a candidate Farkas ray
-      const double dp = fmax(dy, 0.0), dm = fmax(-dy, 0.0);
-      red[3] = (isfinite(lo) ? lo * dp : 0.0) - (isfinite(hi) ? hi * dm : 0.0);
-      const double rv = (isfinite(lo) ? 0.0 : dp) + (isfinite(hi) ? 0.0 : dm);
-      red[4] = rv * rv;
-      if (a.kx_save) a.kx_save[i] = kx;
-    }
-  }
+  if (i < a.m) row_epilogue<CHECK>(a, i, s_sum[threadIdx.x], sigma, w_new, red);
   if (CHECK) {
     const int q[5] = {Q_DY2, Q_DY0, Q_DOBJ_ROW, Q_RAYD_ROW, Q_RAYD_ROWV};
     cta_reduce_store<5>(red, q, a.partials, sc->max_blocks);
@@ -247,8 +312,10 @@ __global__ void __launch_bounds__(kThreads)
 k_col_step(const ColStepArgs a) {
   __shared__ double s_sum[kRowsPerCta];
   const Scalars* sc = a.sc;
-  if (sc->done) return;
-  cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.perm, a.yhat, a.n, s_sum);
+  pdl_trigger();
+  if (!cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.perm, a.yhat, a.n, s_sum,
+                         [&] { pdl_wait(); return !sc->done; }))
+    return;
   const double tau = sc->tau;
   const double k = (double)(sc->k_base + a.iter_in_block);
   const double w_new = (k + 1.0) / (k + 2.0);

@@ -18,6 +18,7 @@
 // Peer buffers are mapped with CUDA IPC (one process per GPU); handles travel through one
 // ncclAllGather at load time.  All ranks execute the same sequence of barrier kernels, so a
 // per-rank epoch counter stays in lock step.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -111,6 +112,157 @@ k_primal_step_p2p(const ColStepArgs a, const PeerTable t) {
   exit_barrier(t, epoch);
 }
 
+// ---- block-owner exchange (MIPCU_PARAM_SHARD_EXCHANGE = 2) --------------------------------------
+// Rank g owns row block g of K (whole rows) AND column block g of K' (whole columns, cut out of all
+// ranks' blocks at load: setup.cu:build_col_block).  Both kernels of an iteration then stream 1/W of
+// the nonzeros, nothing n-proportional is written besides the iterate itself, and the exchange is two
+// all-gathers issued from the kernels' epilogues straight into peer memory:
+//   k_row_step_own : K_g xbar (gathers the whole xbar), dual step on the rank's rows, yhat_i pushed
+//                    into every rank's yhat_full (m_glob doubles per rank);
+//   k_col_step_own : (K' yhat)_j for the rank's columns (gathers the whole yhat_full), primal step,
+//                    xbar_j pushed into every rank's xbar.
+// One cross-GPU barrier per kernel, at its entry: "every rank has finished the previous kernel"
+// covers both hazards (the vector about to be gathered is complete; the vector about to be pushed
+// is no longer being read).  Arrival flags carry a generation number the host counts (all ranks
+// launch the same sequence).  The pushes of kernel t-1 are complete when the grid has retired (stream
+// order), the arrival flag of kernel t is a system-scope release store issued after that, and the
+// gathers of kernel t are issued after the acquire that saw the flag.  An extra system fence per
+// CTA after its pushes is NOT needed and costs 8 us (row) / 21 us (column) per launch on config 3
+// at two GPUs (profiles/r01_block_owner_exchange.md); it stays available as a laboratory switch.
+// Laboratory switches (environment variable MIPCU_OWN_VARIANT, read at load; scripts/own_lab.py):
+// what each piece of the protocol costs.  OWN_NO_PUBLISH alone (1) is the shipped protocol.
+enum { OWN_NO_PUBLISH = 1, OWN_RELAXED_POLL = 2, OWN_NO_PUSH = 4, OWN_NO_BARRIER = 8 };
+
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void own_barrier(const PeerTable& t, const unsigned long long epoch, const int variant) {
+  if (variant & OWN_NO_BARRIER) return;
+  if (threadIdx.x < t.world) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      st_release_sys(t.flags[threadIdx.x] + kOwnFlagBase + t.rank, epoch);
+    }
+    const unsigned long long* f = t.flags[t.rank] + kOwnFlagBase + threadIdx.x;
+    int spins = 0;
+    if (variant & OWN_RELAXED_POLL) {
+      while (ld_relaxed_sys(f) < epoch)
+        if (++spins > (1 << 24)) asm volatile("trap;");
+      __threadfence_system();
+    } else {
+      while (ld_acquire_sys(f) < epoch)
+        if (++spins > (1 << 24)) asm volatile("trap;");   // a lost peer must not hang the device
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void own_publish(const int variant) {
+  if (variant & OWN_NO_PUBLISH) return;
+  __syncthreads();
+  if (threadIdx.x == 0) __threadfence_system();
+}
+
+template <int TPR, bool CHECK>
+__global__ void __launch_bounds__(kThreads)
+k_row_step_own(const RowStepArgs a, const PeerTable t, const unsigned long long epoch, const int variant) {
+  __shared__ double s_sum[kRowsPerCta];
+  const Scalars* sc = a.sc;
+  pdl_trigger();
+  // the head of the nonzero stream is requested before the wait for the peers; `done` is identical
+  // on every rank and is looked at only after the barrier has been passed by all
+  if (!cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.perm, a.xbar, a.m, s_sum, [&] {
+        pdl_wait();
+        own_barrier(t, epoch, variant);
+        return !sc->done;
+      }))
+    return;
+  const double sigma = sc->sigma;
+  const double k = (double)(sc->k_base + a.iter_in_block);
+  const double w_new = (k + 1.0) / (k + 2.0);
+  const int i = blockIdx.x * kRowsPerCta + threadIdx.x;
+  double red[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  if (i < a.m) {
+    const double yh = row_epilogue<CHECK>(a, i, s_sum[threadIdx.x], sigma, w_new, red);
+    const int gi = t.i0[t.rank] + i;
+    if (!(variant & OWN_NO_PUSH))
+      for (int p = 0; p < t.world; ++p) t.yhat_full[p][gi] = yh;      // all-gather by push (self too)
+  }
+  if (CHECK) {
+    const int q[5] = {Q_DY2, Q_DY0, Q_DOBJ_ROW, Q_RAYD_ROW, Q_RAYD_ROWV};
+    cta_reduce_store<5>(red, q, a.partials, sc->max_blocks);
+  }
+  own_publish(variant);
+}
+
+// `a` addresses the rank's column slice: every per-column pointer is already offset by j0, a.n is
+// the slice length, a.yhat is this rank's whole yhat_full.  push_xhat: the stored xhat is the KKT
+// candidate, which the row-side KKT pass of every rank gathers.
+template <int TPR, bool CHECK, bool STORE>
+__global__ void __launch_bounds__(kThreads)
+k_col_step_own(const ColStepArgs a, const PeerTable t, const unsigned long long epoch, const int push_xhat,
+               const int variant) {
+  __shared__ double s_sum[kRowsPerCta];
+  const Scalars* sc = a.sc;
+  pdl_trigger();
+  if (!cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.perm, a.yhat, a.n, s_sum, [&] {
+        pdl_wait();
+        own_barrier(t, epoch, variant);
+        return !sc->done;
+      }))
+    return;
+  const double tau = sc->tau;
+  const double k = (double)(sc->k_base + a.iter_in_block);
+  const double w_new = (k + 1.0) / (k + 2.0);
+  const int j = blockIdx.x * kRowsPerCta + threadIdx.x;
+  double red[10] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (j < a.n) {
+    col_epilogue<CHECK, STORE>(a, j, s_sum[threadIdx.x], tau, w_new, red);
+    const int gj = t.j0[t.rank] + j;
+    const double xb = a.xbar[j];
+    if (!(variant & OWN_NO_PUSH))
+      for (int p = 0; p < t.world; ++p)
+        if (p != t.rank) t.xbar[p][gj] = xb;
+    if (STORE && push_xhat) {
+      const double xh = a.xhat_out[j];
+      for (int p = 0; p < t.world; ++p)
+        if (p != t.rank) t.xhat_chk[p][gj] = xh;
+    }
+  }
+  if (CHECK) {
+    const int q[10] = {Q_DX2, Q_DXDATY, Q_DX0, Q_DRES2, Q_POBJ, Q_DOBJ_COL,
+                       Q_RAYD_COL, Q_RAYD_COLV, Q_RAYP_C, Q_RAYP_COLV};
+    cta_reduce_store<10>(red, q, a.partials, sc->max_blocks);
+  }
+  own_publish(variant);
+}
+
+template <int TPR>
+void launch_row_own(mipcu_ctx* ctx, const RowStepArgs& a, bool check) {
+  const int g = std::max(1, grid_for(ctx->m, kRowsPerCta));
+  const unsigned long long e = ++ctx->own_epoch;
+  const bool pdl = ctx->use_pdl;
+  if (check) launch_kernel(k_row_step_own<TPR, true>, g, ctx->stream, pdl, a, ctx->peers, e, ctx->own_variant);
+  else launch_kernel(k_row_step_own<TPR, false>, g, ctx->stream, pdl, a, ctx->peers, e, ctx->own_variant);
+}
+
+template <int TPR>
+void launch_col_own(mipcu_ctx* ctx, const ColStepArgs& a, bool check, bool store, int push_xhat) {
+  const int g = std::max(1, grid_for(a.n, kRowsPerCta));
+  const unsigned long long e = ++ctx->own_epoch;
+  cudaStream_t st = ctx->stream;
+  const PeerTable& t = ctx->peers;
+  const bool pdl = ctx->use_pdl;
+  const int v = ctx->own_variant;
+  if (check && store) launch_kernel(k_col_step_own<TPR, true, true>, g, st, pdl, a, t, e, push_xhat, v);
+  else if (check) launch_kernel(k_col_step_own<TPR, true, false>, g, st, pdl, a, t, e, push_xhat, v);
+  else if (store) launch_kernel(k_col_step_own<TPR, false, true>, g, st, pdl, a, t, e, push_xhat, v);
+  else launch_kernel(k_col_step_own<TPR, false, false>, g, st, pdl, a, t, e, push_xhat, v);
+}
+
 // all-gather of one replicated vector: every rank pushes its slice into all peers
 __global__ void __launch_bounds__(kThreads) k_push_slice(const PeerTable t, int which) {
   const unsigned long long epoch = barrier_epoch(t);
@@ -128,6 +280,54 @@ __global__ void __launch_bounds__(kThreads) k_push_slice(const PeerTable t, int 
 }  // namespace
 
 bool p2p_active(const mipcu_ctx* ctx) { return ctx->world > 1 && ctx->peers.world == ctx->world; }
+bool own_active(const mipcu_ctx* ctx) { return p2p_active(ctx) && ctx->own_ready; }
+
+// Collective (from mipcu_load_lp, after p2p_setup).  The block-owner exchange needs the peer table
+// of the fused exchange plus this rank's column block of the whole matrix.
+void own_setup(mipcu_ctx* ctx) {
+  ctx->own_ready = false;
+  ctx->own_epoch = 0;
+  if (!p2p_active(ctx) || (int)ctx->params[MIPCU_PARAM_SHARD_EXCHANGE] != 2) return;
+  build_col_block(ctx);
+  const char* v = std::getenv("MIPCU_OWN_VARIANT");
+  ctx->own_variant = v ? std::atoi(v) : OWN_NO_PUBLISH;
+  ctx->own_ready = true;
+}
+
+#define MIPCU_OWN_DISPATCH(fmt, CALL)                                                          \
+  switch (fmt) {                                                                               \
+    case 0: { constexpr int T = 0; CALL; } break;                                              \
+    case 2: { constexpr int T = 2; CALL; } break;                                              \
+    case 4: { constexpr int T = 4; CALL; } break;                                              \
+    case 8: { constexpr int T = 8; CALL; } break;                                              \
+    case 16: { constexpr int T = 16; CALL; } break;                                            \
+    default: { constexpr int T = 32; CALL; } break;                                            \
+  }
+
+void own_row_step(mipcu_ctx* ctx, const RowStepArgs& a, bool check) {
+  MIPCU_OWN_DISPATCH(kernel_format(ctx, ctx->rows), launch_row_own<T>(ctx, a, check));
+  ctx->launches++;
+}
+
+void own_col_step(mipcu_ctx* ctx, int iter_in_block, bool check, const double* xhat_in, double* xhat_out) {
+  const PeerTable& t = ctx->peers;
+  const int j0 = t.j0[t.rank];
+  const Csr& B = ctx->colblk;
+  ColStepArgs a;
+  if (kernel_format(ctx, B) == 0) { a.ptr = B.sptr; a.idx = B.sidx; a.val = B.sval; a.perm = B.perm; }
+  else { a.ptr = B.ptr; a.idx = B.idx; a.val = B.val; a.perm = nullptr; }
+  a.yhat = ctx->yhat_full;
+  a.x0 = ctx->x0 + j0; a.aty0 = ctx->aty0 + j0; a.c = ctx->cs + j0; a.l = ctx->ls + j0; a.u = ctx->us + j0;
+  a.d2 = ctx->d2 + j0; a.xbar = ctx->xbar + j0; a.aty = ctx->aty + j0;
+  a.xhat_in = xhat_in ? xhat_in + j0 : nullptr;
+  a.xhat_out = xhat_out ? xhat_out + j0 : nullptr;
+  a.aty_cand = ctx->aty_cand + j0;
+  a.sc = ctx->d_sc; a.partials = ctx->partials;
+  a.n = t.j0[t.rank + 1] - j0; a.iter_in_block = iter_in_block;
+  const int push_xhat = xhat_out == ctx->xhat_chk ? 1 : 0;
+  MIPCU_OWN_DISPATCH(kernel_format(ctx, B), launch_col_own<T>(ctx, a, check, xhat_out != nullptr, push_xhat));
+  ctx->launches++;
+}
 
 void p2p_teardown(mipcu_ctx* ctx) {
   for (void* p : ctx->peer_mappings) cudaIpcCloseMemHandle(p);
@@ -135,6 +335,7 @@ void p2p_teardown(mipcu_ctx* ctx) {
   if (ctx->p2p_flags) cudaFree(ctx->p2p_flags);
   ctx->p2p_flags = nullptr;
   ctx->peers = PeerTable();
+  ctx->own_ready = false;
 }
 
 // Collective (every rank calls it from mipcu_load_lp): exchange IPC handles of the four shared
@@ -145,10 +346,10 @@ void p2p_setup(mipcu_ctx* ctx) {
   if (ctx->world <= 1 || ctx->world > kMaxPeers || (int)ctx->params[MIPCU_PARAM_SHARD_EXCHANGE] == 0) return;
   const int W = ctx->world, n = ctx->n;
   cudaStream_t st = ctx->stream;
-  MIPCU_CK(cudaMalloc(&ctx->p2p_flags, sizeof(unsigned long long) * (2 * kMaxPeers + 2)));
-  MIPCU_CK(cudaMemsetAsync(ctx->p2p_flags, 0, sizeof(unsigned long long) * (2 * kMaxPeers + 2), st));
-  constexpr int kBufs = 5;
-  void* mine[kBufs] = {ctx->tmp_n, ctx->xbar, ctx->xhat_chk, ctx->x_sol, ctx->p2p_flags};
+  MIPCU_CK(cudaMalloc(&ctx->p2p_flags, sizeof(unsigned long long) * kFlagCount));
+  MIPCU_CK(cudaMemsetAsync(ctx->p2p_flags, 0, sizeof(unsigned long long) * kFlagCount, st));
+  constexpr int kBufs = 6;
+  void* mine[kBufs] = {ctx->tmp_n, ctx->xbar, ctx->xhat_chk, ctx->x_sol, ctx->p2p_flags, ctx->yhat_full};
   std::vector<cudaIpcMemHandle_t> send(kBufs), recv((size_t)kBufs * W);
   int ok = 1;
   for (int i = 0; i < kBufs; ++i)
@@ -171,6 +372,7 @@ void p2p_setup(mipcu_ctx* ctx) {
   t.world = W;
   t.rank = ctx->rank;
   for (int g = 0; g <= W; ++g) t.j0[g] = (int)(((int64_t)n * g) / W);
+  for (int g = 0; g <= W; ++g) t.i0[g] = ctx->row_off[g];
   bool all_ok = true;
   for (int p = 0; p < W && all_ok; ++p) {
     int peer_ok = 0;
@@ -199,6 +401,7 @@ void p2p_setup(mipcu_ctx* ctx) {
     t.xhat_chk[p] = (double*)ptr[2];
     t.x_sol[p] = (double*)ptr[3];
     t.flags[p] = (unsigned long long*)ptr[4];
+    t.yhat_full[p] = (double*)ptr[5];
   }
   // every rank must take the same path: agree on success
   const double agreed = dist_sum_scalar(ctx, all_ok ? 1.0 : 0.0);

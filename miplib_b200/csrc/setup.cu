@@ -418,7 +418,117 @@ void free_csr(Csr& A) {
   A = Csr();
 }
 
+// ---- column block of the block-owner exchange ---------------------------------------------------
+// ptr_all / idx_all / val_all: every rank's local transpose (CSR of K_g', n rows, LOCAL row ids),
+// all-gathered.  Column j of the whole matrix is the concatenation over g of row j of those, with
+// row ids shifted by the rank's row offset: rows come out increasing (deterministic sums).
+__global__ void k_colblk_count(const int* __restrict__ ptr_all, int W, int n1, int j0, int nloc,
+                               int* __restrict__ cnt) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nloc) return;
+  int c = 0;
+  for (int g = 0; g < W; ++g) {
+    const int* P = ptr_all + (size_t)g * n1;
+    c += P[j0 + j + 1] - P[j0 + j];
+  }
+  cnt[j] = c;
+}
+
+__global__ void k_colblk_fill(const int* __restrict__ ptr_all, const int* __restrict__ idx_all,
+                              const double* __restrict__ val_all, size_t stride, int W, int n1, int j0,
+                              int nloc, const int* __restrict__ row_off, const int* __restrict__ bptr,
+                              int* __restrict__ bidx, double* __restrict__ bval) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nloc) return;
+  int pos = bptr[j];
+  for (int g = 0; g < W; ++g) {
+    const int* P = ptr_all + (size_t)g * n1;
+    for (int k = P[j0 + j]; k < P[j0 + j + 1]; ++k) {
+      bidx[pos] = idx_all[(size_t)g * stride + k] + row_off[g];
+      bval[pos] = val_all[(size_t)g * stride + k];
+      ++pos;
+    }
+  }
+}
+
+__global__ void k_place(const double* __restrict__ src, double* __restrict__ dst, int offset, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dst[offset + i] = src[i];
+}
+
 }  // namespace
+
+// Collective.  Rank g already holds its row block and that block's transpose; the block-owner
+// exchange also needs columns [j0, j1) of the WHOLE matrix.  Every rank all-gathers the local
+// transposes (setup only: the matrix crosses NVLink once) and cuts its column range out of them.
+void build_col_block(mipcu_ctx* ctx) {
+  free_csr(ctx->colblk);
+  if (ctx->world <= 1) return;
+  cudaStream_t st = ctx->stream;
+  const int W = ctx->world, n = ctx->n, n1 = n + 1;
+  const int j0 = (int)(((int64_t)n * ctx->rank) / W), j1 = (int)(((int64_t)n * (ctx->rank + 1)) / W);
+  const int nloc = j1 - j0;
+  const Csr& T = ctx->cols;
+  // sizes of everybody's block
+  long long* d_meta = dalloc<long long>(W + 1);
+  const long long mine = T.nnz;
+  MIPCU_CK(cudaMemcpyAsync(d_meta + W, &mine, sizeof(long long), cudaMemcpyHostToDevice, st));
+  dist_allgather_bytes(ctx, d_meta + W, d_meta, sizeof(long long));
+  std::vector<long long> nnz_of(W);
+  MIPCU_CK(cudaMemcpyAsync(nnz_of.data(), d_meta, sizeof(long long) * W, cudaMemcpyDeviceToHost, st));
+  MIPCU_CK(cudaStreamSynchronize(st));
+  dfree(d_meta);
+  size_t stride = 4;
+  for (long long v : nnz_of) stride = std::max(stride, (size_t)((v + 3) & ~3ll));
+  int* send_idx = dalloc<int>(stride);
+  double* send_val = dalloc<double>(stride);
+  MIPCU_CK(cudaMemsetAsync(send_idx, 0, sizeof(int) * stride, st));
+  MIPCU_CK(cudaMemsetAsync(send_val, 0, sizeof(double) * stride, st));
+  if (T.nnz) {
+    MIPCU_CK(cudaMemcpyAsync(send_idx, T.idx, sizeof(int) * T.nnz, cudaMemcpyDeviceToDevice, st));
+    MIPCU_CK(cudaMemcpyAsync(send_val, T.val, sizeof(double) * T.nnz, cudaMemcpyDeviceToDevice, st));
+  }
+  int* ptr_all = dalloc<int>((int64_t)W * n1);
+  int* idx_all = dalloc<int>((int64_t)W * stride);
+  double* val_all = dalloc<double>((int64_t)W * stride);
+  dist_allgather_bytes(ctx, T.ptr, ptr_all, sizeof(int) * (size_t)n1);
+  dist_allgather_bytes(ctx, send_idx, idx_all, sizeof(int) * stride);
+  dist_allgather_bytes(ctx, send_val, val_all, sizeof(double) * stride);
+  int* d_off = dalloc<int>(W + 1);
+  MIPCU_CK(cudaMemcpyAsync(d_off, ctx->row_off, sizeof(int) * (W + 1), cudaMemcpyHostToDevice, st));
+
+  Csr& B = ctx->colblk;
+  B.nrows = nloc;
+  B.ncols = ctx->m_glob;
+  B.ptr = dalloc<int>(nloc + 1);
+  int* cnt = dalloc<int>(nloc + 1);
+  MIPCU_CK(cudaMemsetAsync(cnt, 0, sizeof(int) * (nloc + 1), st));
+  if (nloc) {
+    k_colblk_count<<<grid_for(nloc), kThreads, 0, st>>>(ptr_all, W, n1, j0, nloc, cnt);
+    ctx->launches++;
+  }
+  size_t tmp_bytes = 0;
+  MIPCU_CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, B.ptr, nloc + 1, st));
+  char* tmp = dalloc<char>((int64_t)tmp_bytes + 16);
+  MIPCU_CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, B.ptr, nloc + 1, st));
+  int total = 0;
+  MIPCU_CK(cudaMemcpyAsync(&total, B.ptr + nloc, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MIPCU_CK(cudaStreamSynchronize(st));
+  B.nnz = total;
+  B.idx = dalloc<int>((int64_t)total + 4);
+  B.val = dalloc<double>((int64_t)total + 4);
+  MIPCU_CK(cudaMemsetAsync(B.idx + total, 0, sizeof(int) * 4, st));
+  MIPCU_CK(cudaMemsetAsync(B.val + total, 0, sizeof(double) * 4, st));
+  if (nloc) {
+    k_colblk_fill<<<grid_for(nloc), kThreads, 0, st>>>(ptr_all, idx_all, val_all, stride, W, n1, j0, nloc,
+                                                      d_off, B.ptr, B.idx, B.val);
+    ctx->launches++;
+  }
+  B.tpr = choose_tpr(nloc ? (double)total / (double)nloc : 0.0, (int)ctx->params[MIPCU_PARAM_THREADS_PER_ROW]);
+  MIPCU_CK(cudaStreamSynchronize(st));
+  dfree(tmp); dfree(cnt); dfree(d_off); dfree(send_idx); dfree(send_val);
+  dfree(ptr_all); dfree(idx_all); dfree(val_all);
+}
 
 int choose_tpr(double avg, int override_tpr) {
   if (override_tpr == 2 || override_tpr == 4 || override_tpr == 8 || override_tpr == 16 ||
@@ -458,6 +568,8 @@ double device_norm2(mipcu_ctx* ctx, const double* v, int64_t len) {
 void free_model(mipcu_ctx* ctx) {
   free_csr(ctx->rows);
   free_csr(ctx->cols);
+  free_csr(ctx->colblk);
+  dfree(ctx->yhat_full);
   double** vecs[] = {&ctx->c, &ctx->lb, &ctx->ub, &ctx->lo, &ctx->hi, &ctx->cs, &ctx->ls, &ctx->us,
                      &ctx->los, &ctx->his, &ctx->d1, &ctx->d2, &ctx->xbar, &ctx->x0, &ctx->aty,
                      &ctx->aty0, &ctx->xhat_first, &ctx->xhat_chk, &ctx->aty_cand, &ctx->y,
@@ -556,6 +668,30 @@ void load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* r
   double** mvecs[] = {&ctx->los, &ctx->his, &ctx->d1, &ctx->y, &ctx->y0, &ctx->yhat, &ctx->tmp_m,
                       &ctx->y_sol};
   for (double** p : mvecs) *p = dalloc<double>(m + 2);
+  ctx->m_glob = (int)m;
+  for (int& v : ctx->row_off) v = 0;
+  ctx->row_off[1] = (int)m;
+  if (ctx->world > 1) {
+    // every rank's row count -> row offsets of the blocks (collective, like the rest of a sharded load)
+    const int W = ctx->world;
+    long long* d_rows = dalloc<long long>(W + 1);
+    const long long mine = m;
+    MIPCU_CK(cudaMemcpyAsync(d_rows + W, &mine, sizeof(long long), cudaMemcpyHostToDevice, st));
+    dist_allgather_bytes(ctx, d_rows + W, d_rows, sizeof(long long));
+    std::vector<long long> rows_of(W);
+    MIPCU_CK(cudaMemcpyAsync(rows_of.data(), d_rows, sizeof(long long) * W, cudaMemcpyDeviceToHost, st));
+    MIPCU_CK(cudaStreamSynchronize(st));
+    dfree(d_rows);
+    long long acc = 0;
+    for (int g = 0; g < W; ++g) { ctx->row_off[g] = (int)acc; acc += rows_of[g]; }
+    MIPCU_REQUIRE(acc < (1ll << 31) - 1024, "mipcu_load_lp: total row count beyond int32 indexing");
+    ctx->row_off[W] = (int)acc;
+    ctx->m_glob = (int)acc;
+    g_alloc_exported = true;
+    ctx->yhat_full = dalloc<double>(acc + 2);
+    g_alloc_exported = false;
+    MIPCU_CK(cudaMemsetAsync(ctx->yhat_full, 0, sizeof(double) * (acc + 2), st));
+  }
   ctx->max_blocks = std::max(1024, std::max(grid_for(m, 64), grid_for(n, 64)));   // 64 = TMA tile rows
   A.tile_cap = tile_capacity(ctx, A);
   ctx->cols.tile_cap = tile_capacity(ctx, ctx->cols);
@@ -600,6 +736,20 @@ void prepare(mipcu_ctx* ctx) {
       k_scale_matrix<true><<<gr, kThreads, 0, st>>>(R.ptr, R.idx, R.val, rf, cf, m);
       k_scale_matrix<false><<<gc, kThreads, 0, st>>>(C.ptr, C.idx, C.val, rf, cf, n);
       ctx->launches += 6;
+      if (ctx->colblk.nrows > 0 && ctx->yhat_full) {
+        // block-owner exchange: the column block holds entries of every rank's rows, so it needs
+        // all row factors; each row is owned by exactly one rank: place + sum assembles them
+        // (yhat_full is free until the first iteration).  Same (val * r_i) * c_j as the row copy.
+        Csr& B = ctx->colblk;
+        double* rf_all = ctx->yhat_full;
+        MIPCU_CK(cudaMemsetAsync(rf_all, 0, sizeof(double) * (size_t)ctx->m_glob, st));
+        if (m) k_place<<<grid_for(m), kThreads, 0, st>>>(rf, rf_all, ctx->row_off[ctx->rank], m);
+        dist_allreduce(ctx, rf_all, (size_t)ctx->m_glob, false);
+        const int j0 = (int)(((int64_t)n * ctx->rank) / ctx->world);
+        k_scale_matrix<false><<<grid_for((int64_t)B.nrows * 8), kThreads, 0, st>>>(B.ptr, B.idx, B.val, rf_all,
+                                                                                cf + j0, B.nrows);
+        ctx->launches += 2;
+      }
     }
   }
   const bool verbose = ctx->params[MIPCU_PARAM_VERBOSE] != 0.0;
@@ -613,6 +763,7 @@ void prepare(mipcu_ctx* ctx) {
   // lane-per-row copies of the scaled matrix for the iteration kernels
   build_sell(ctx, R);
   build_sell(ctx, C);
+  if (ctx->colblk.nrows > 0) build_sell(ctx, ctx->colblk);
   lap("sell copies");
   // step size
   double step = ctx->params[MIPCU_PARAM_STEP_SIZE];

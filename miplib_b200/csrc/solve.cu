@@ -351,17 +351,18 @@ void launch_kkt(mipcu_ctx* ctx) {
 // SELL (lane per row) launches: no TMA / CSR-stream variants exist for this format
 void launch_row_sell(mipcu_ctx* ctx, const RowStepArgs& a, bool check) {
   const int g = grid_for(ctx->m, kRowsPerCta);
-  if (check) k_row_step<0, true><<<g, kThreads, 0, ctx->stream>>>(a);
-  else k_row_step<0, false><<<g, kThreads, 0, ctx->stream>>>(a);
+  if (check) launch_kernel(k_row_step<0, true>, g, ctx->stream, ctx->use_pdl, a);
+  else launch_kernel(k_row_step<0, false>, g, ctx->stream, ctx->use_pdl, a);
 }
 
 void launch_col_sell(mipcu_ctx* ctx, const ColStepArgs& a, bool check, bool store) {
   const int g = grid_for(ctx->n, kRowsPerCta);
   cudaStream_t st = ctx->stream;
-  if (check && store) k_col_step<0, true, true><<<g, kThreads, 0, st>>>(a);
-  else if (check) k_col_step<0, true, false><<<g, kThreads, 0, st>>>(a);
-  else if (store) k_col_step<0, false, true><<<g, kThreads, 0, st>>>(a);
-  else k_col_step<0, false, false><<<g, kThreads, 0, st>>>(a);
+  const bool pdl = ctx->use_pdl;
+  if (check && store) launch_kernel(k_col_step<0, true, true>, g, st, pdl, a);
+  else if (check) launch_kernel(k_col_step<0, true, false>, g, st, pdl, a);
+  else if (store) launch_kernel(k_col_step<0, false, true>, g, st, pdl, a);
+  else launch_kernel(k_col_step<0, false, false>, g, st, pdl, a);
 }
 
 #define MIPCU_DISPATCH_TPR(tpr, CALL)                                                          \
@@ -377,6 +378,7 @@ void row_step(mipcu_ctx* ctx, int i, bool check, bool keep_kx = false) {
   if (ctx->m == 0) return;
   RowStepArgs a = row_args(ctx, i);
   if (keep_kx) a.kx_save = ctx->tmp_m;
+  if (own_active(ctx)) { own_row_step(ctx, a, check); return; }
   const int fmt = kernel_format(ctx, ctx->rows);
   if (fmt == 0) launch_row_sell(ctx, a, check);
   else MIPCU_DISPATCH_TPR(fmt, launch_row<T>(ctx, a, check));
@@ -385,6 +387,12 @@ void row_step(mipcu_ctx* ctx, int i, bool check, bool keep_kx = false) {
 
 void col_step(mipcu_ctx* ctx, int i, bool check, const double* xhat_in, double* xhat_out) {
   if (ctx->n == 0) return;
+  if (own_active(ctx)) {
+    // row-sharded, block-owner exchange: this rank's columns of the WHOLE matrix against the whole
+    // yhat the row kernels pushed together; xbar (and the KKT candidate) pushed to the peers
+    own_col_step(ctx, i, check, xhat_in, xhat_out);
+    return;
+  }
   ColStepArgs a = col_args(ctx, i, xhat_in, xhat_out);
   if (p2p_active(ctx)) {
     // row-sharded, fused exchange: local partial K_g' yhat_g, then ONE kernel that pulls this rank's
@@ -481,6 +489,7 @@ void enqueue_block(mipcu_ctx* ctx, int period, cudaEvent_t* time_events, cudaEve
 }
 
 void ensure_aux(mipcu_ctx* ctx) {
+  ctx->use_pdl = ctx->params[MIPCU_PARAM_USE_PDL] != 0.0;
   if (!ctx->d_sc) MIPCU_CK(cudaMalloc(&ctx->d_sc, sizeof(Scalars)));
   if (!ctx->h_sc) MIPCU_CK(cudaMallocHost(&ctx->h_sc, sizeof(Scalars) * 2));
   for (auto& e : ctx->ev)
@@ -548,6 +557,12 @@ int64_t row_kernel_bytes(const mipcu_ctx* ctx) {
 }
 
 int64_t col_kernel_bytes(const mipcu_ctx* ctx) {
+  if (own_active(ctx)) {
+    // block-owner exchange: the rank's columns of the whole matrix, the whole yhat gathered once,
+    // the primal vectors of the slice only
+    const Csr& B = ctx->colblk;
+    return 12 * B.nnz + index_bytes(ctx, B) + 8 * (int64_t)ctx->m_glob + 72 * (int64_t)B.nrows;
+  }
   // CSC stream 12/nnz + col ptr 4(n+1) + gathered yhat once 8m + reads xbar,x0,aty,aty0,c,l,u
   // + writes xbar,aty
   return 12 * ctx->nnz + index_bytes(ctx, ctx->cols) + 8 * (int64_t)ctx->m + 72 * (int64_t)ctx->n;
@@ -578,6 +593,7 @@ void solve_lp(mipcu_ctx* ctx, mipcu_stats* out) {
   MIPCU_REQUIRE(ctx->world <= 1 || time_limit <= 0.0,
                 "a time limit is not supported on row-sharded contexts (use the iteration limit)");
 
+  if (use_graph) ctx->use_pdl = false;
   Scalars h;
   init_iterate(ctx, h);
 
@@ -638,7 +654,7 @@ void solve_lp(mipcu_ctx* ctx, mipcu_stats* out) {
       MIPCU_CK(cudaEventElapsedTime(&a, ev_time[slot][0], ev_time[slot][1]));
       MIPCU_CK(cudaEventElapsedTime(&b, ev_time[slot][1], ev_time[slot][2]));
       row_us += 1e3 * a; col_us += 1e3 * b; ++timed_samples;
-      if (ctx->world > 1) {
+      if (ctx->world > 1 && !own_active(ctx)) {
         float c = 0.f;
         MIPCU_CK(cudaEventElapsedTime(&c, ev_time[slot][1], ctx->ev[10 + slot]));
         partial_us += 1e3 * c;
@@ -697,8 +713,10 @@ void solve_lp(mipcu_ctx* ctx, mipcu_stats* out) {
   out->col_kernel_us = timed_samples ? col_us / timed_samples : 0.0;
   out->row_kernel_bytes = row_kernel_bytes(ctx);
   out->col_kernel_bytes = col_kernel_bytes(ctx);
-  out->col_partial_us = (timed_samples && ctx->world > 1) ? partial_us / timed_samples : 0.0;
-  out->col_exchange_us = (timed_samples && ctx->world > 1) ? out->col_kernel_us - out->col_partial_us : 0.0;
+  // the block-owner exchange has no separate partial product: the split is reported as 0 / 0
+  const bool split = timed_samples && ctx->world > 1 && !own_active(ctx);
+  out->col_partial_us = split ? partial_us / timed_samples : 0.0;
+  out->col_exchange_us = split ? out->col_kernel_us - out->col_partial_us : 0.0;
   out->solve_seconds =
       std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }

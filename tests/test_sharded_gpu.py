@@ -15,7 +15,7 @@ def _worker(rank, world, uid, which, exchange, out):
     L = gen.lp(3000, 5000, 8, 21) if which == "small" else gen.config(2)
     ptr, idx, val, lo, hi = sharding.shard_csr(L.A, L.row_lo, L.row_hi, rank, world)
     with Engine(rank, rank, world, uid) as e:
-        e.set_param("shard_exchange", exchange)       # 1: fused P2P kernel, 0: ncclAllReduce
+        e.set_param("shard_exchange", exchange)       # 2: block-owner, 1: fused P2P kernel, 0: ncclAllReduce
         e.load(ptr, idx, val, L.c, L.lb, L.ub, lo, hi, L.maximize, n=L.n)
         assert e.get_param("shard_exchange") == exchange      # no silent fall-back to NCCL
         st = e.solve()
@@ -23,7 +23,7 @@ def _worker(rank, world, uid, which, exchange, out):
                      st.rel_primal_res, st.rel_gap)
 
 
-@pytest.mark.parametrize("exchange", [1, 0])
+@pytest.mark.parametrize("exchange", [2, 1, 0])
 @pytest.mark.parametrize("which", ["small", "C2"])
 def test_two_rank_solve_matches_single_gpu(built, which, exchange):
     from miplib_b200 import Engine
