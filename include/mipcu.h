@@ -69,7 +69,10 @@ enum {
   MIPCU_PARAM_USE_PDL = 12,       /* 1: the two iteration kernels are launched as programmatic dependents of each
                                      other (the head of the nonzero stream is fetched while the previous kernel drains);
                                      0: plain stream order.  Ignored when the block is replayed as a CUDA graph */
-  MIPCU_PARAM_COUNT_ = 13
+  MIPCU_PARAM_MULTICAST = 13,     /* block-owner exchange: 1 (default) push slices through an NVSwitch multicast window
+                                     when the box supports it; 0: unicast stores into every peer.  Set before load;
+                                     after load it reads back 1 only if the window is in use on every rank */
+  MIPCU_PARAM_COUNT_ = 14
 };
 
 typedef struct mipcu_stats {

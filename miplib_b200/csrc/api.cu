@@ -63,6 +63,7 @@ void set_default_params(mipcu_ctx* ctx) {
   ctx->params[MIPCU_PARAM_USE_TMA] = -1;
   ctx->params[MIPCU_PARAM_SHARD_EXCHANGE] = 2;
   ctx->params[MIPCU_PARAM_USE_PDL] = 0;
+  ctx->params[MIPCU_PARAM_MULTICAST] = 1;
 }
 
 mipcu_ctx* create_on(int device) {

@@ -117,6 +117,21 @@ struct PeerTable {
   // rank's row kernel pushes its slice [i0[g], i0[g+1]) into all of them
   int i0[kMaxPeers + 1] = {};
   double* yhat_full[kMaxPeers] = {};
+  // NVSwitch multicast mappings of xbar / yhat_full (mc.cu): one store reaches every rank's copy,
+  // this rank's included; null = unicast pushes through the arrays above
+  double* mc_xbar = nullptr;
+  double* mc_yhat_full = nullptr;
+};
+
+// mc.cu: the window [xbar | yhat_full] of this rank, bound to the job's multicast object
+struct McWindow {
+  bool active = false, bound = false;
+  size_t size = 0;
+  unsigned long long mc_handle = 0, mem_handle = 0;   // CUmemGenericAllocationHandle
+  void* uc_va = nullptr;                              // this rank's window (ordinary mapping)
+  void* mc_va = nullptr;                              // multicast mapping of all ranks' windows
+  double* saved_xbar = nullptr;                       // the cudaMalloc'd vectors the window replaces
+  double* saved_yhat_full = nullptr;
 };
 
 }  // namespace mipcu
@@ -136,6 +151,7 @@ struct mipcu_ctx {
   mipcu::PeerTable peers;         // world == peers.world: the fused P2P exchange is usable
   std::vector<void*> peer_mappings;
   unsigned long long* p2p_flags = nullptr;
+  mipcu::McWindow mc;
   bool own_ready = false;             // block-owner exchange: column block built, yhat_full mapped
   bool use_pdl = false;               // iteration kernels launched as programmatic dependents (MIPCU_PDL)
   int own_variant = 0;                // laboratory switches (p2p.cu), 0 = shipped protocol
@@ -225,6 +241,10 @@ void p2p_setup(mipcu_ctx* ctx);
 void p2p_teardown(mipcu_ctx* ctx);
 void p2p_primal_step(mipcu_ctx* ctx, const ColStepArgs& a, bool check, bool store);
 void p2p_allgather(mipcu_ctx* ctx, int which);   // 0 xbar, 1 xhat_chk, 2 x_sol
+
+// ---- mc.cu ----------------------------------------------------------------------------------
+bool mc_setup(mipcu_ctx* ctx);      // collective: xbar / yhat_full moved into an NVSwitch multicast window
+void mc_teardown(mipcu_ctx* ctx);
 
 // ---- solve.cu -------------------------------------------------------------------------------
 void solve_lp(mipcu_ctx* ctx, mipcu_stats* out);

@@ -188,8 +188,10 @@ k_row_step_own(const RowStepArgs a, const PeerTable t, const unsigned long long 
   if (i < a.m) {
     const double yh = row_epilogue<CHECK>(a, i, s_sum[threadIdx.x], sigma, w_new, red);
     const int gi = t.i0[t.rank] + i;
-    if (!(variant & OWN_NO_PUSH))
-      for (int p = 0; p < t.world; ++p) t.yhat_full[p][gi] = yh;      // all-gather by push (self too)
+    if (!(variant & OWN_NO_PUSH)) {
+      if (t.mc_yhat_full) t.mc_yhat_full[gi] = yh;                      // one store, replicated by the switch
+      else for (int p = 0; p < t.world; ++p) t.yhat_full[p][gi] = yh;   // all-gather by push (self too)
+    }
   }
   if (CHECK) {
     const int q[5] = {Q_DY2, Q_DY0, Q_DOBJ_ROW, Q_RAYD_ROW, Q_RAYD_ROWV};
@@ -223,9 +225,12 @@ k_col_step_own(const ColStepArgs a, const PeerTable t, const unsigned long long 
     col_epilogue<CHECK, STORE>(a, j, s_sum[threadIdx.x], tau, w_new, red);
     const int gj = t.j0[t.rank] + j;
     const double xb = a.xbar[j];
-    if (!(variant & OWN_NO_PUSH))
-      for (int p = 0; p < t.world; ++p)
-        if (p != t.rank) t.xbar[p][gj] = xb;
+    if (!(variant & OWN_NO_PUSH)) {
+      if (t.mc_xbar) t.mc_xbar[gj] = xb;
+      else
+        for (int p = 0; p < t.world; ++p)
+          if (p != t.rank) t.xbar[p][gj] = xb;
+    }
     if (STORE && push_xhat) {
       const double xh = a.xhat_out[j];
       for (int p = 0; p < t.world; ++p)
@@ -271,8 +276,10 @@ __global__ void __launch_bounds__(kThreads) k_push_slice(const PeerTable t, int 
   if (j < t.j0[t.rank + 1]) {
     double* const* dst = which == 0 ? t.xbar : which == 1 ? t.xhat_chk : t.x_sol;
     const double v = dst[t.rank][j];
-    for (int p = 0; p < t.world; ++p)
-      if (p != t.rank) dst[p][j] = v;
+    if (which == 0 && t.mc_xbar) t.mc_xbar[j] = v;
+    else
+      for (int p = 0; p < t.world; ++p)
+        if (p != t.rank) dst[p][j] = v;
   }
   exit_barrier(t, epoch);
 }
@@ -289,6 +296,9 @@ void own_setup(mipcu_ctx* ctx) {
   ctx->own_epoch = 0;
   if (!p2p_active(ctx) || (int)ctx->params[MIPCU_PARAM_SHARD_EXCHANGE] != 2) return;
   build_col_block(ctx);
+  // optional: pushes through the NVSwitch multicast window when the box has one; the parameter
+  // reads back whether it is in use
+  ctx->params[MIPCU_PARAM_MULTICAST] = mc_setup(ctx) ? 1.0 : 0.0;
   const char* v = std::getenv("MIPCU_OWN_VARIANT");
   ctx->own_variant = v ? std::atoi(v) : OWN_NO_PUBLISH;
   ctx->own_ready = true;
@@ -330,6 +340,7 @@ void own_col_step(mipcu_ctx* ctx, int iter_in_block, bool check, const double* x
 }
 
 void p2p_teardown(mipcu_ctx* ctx) {
+  mc_teardown(ctx);
   for (void* p : ctx->peer_mappings) cudaIpcCloseMemHandle(p);
   ctx->peer_mappings.clear();
   if (ctx->p2p_flags) cudaFree(ctx->p2p_flags);
