@@ -72,7 +72,10 @@ enum {
   MIPCU_PARAM_MULTICAST = 13,     /* block-owner exchange: 1 (default) push slices through an NVSwitch multicast window
                                      when the box supports it; 0: unicast stores into every peer.  Set before load;
                                      after load it reads back 1 only if the window is in use on every rank */
-  MIPCU_PARAM_COUNT_ = 14
+  MIPCU_PARAM_ROW_SORT = 14,      /* 1 (default): rows are stored sorted by decreasing length on the device (no padding in
+                                     the sliced-ELL copy); invisible through this ABI.  0: rows keep the caller's order.
+                                     Set before load */
+  MIPCU_PARAM_COUNT_ = 15
 };
 
 typedef struct mipcu_stats {

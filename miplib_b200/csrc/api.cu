@@ -64,6 +64,7 @@ void set_default_params(mipcu_ctx* ctx) {
   ctx->params[MIPCU_PARAM_SHARD_EXCHANGE] = 2;
   ctx->params[MIPCU_PARAM_USE_PDL] = 0;
   ctx->params[MIPCU_PARAM_MULTICAST] = 1;
+  ctx->params[MIPCU_PARAM_ROW_SORT] = 1;
 }
 
 mipcu_ctx* create_on(int device) {
@@ -305,7 +306,10 @@ int mipcu_get_scaling(mipcu_ctx* ctx, double* d1, double* d2) {
   return guarded(ctx, [&] {
     MIPCU_REQUIRE(ctx->loaded, "mipcu_get_scaling: no model loaded");
     MIPCU_CK(cudaSetDevice(ctx->device));
-    if (d1 && ctx->m) MIPCU_CK(cudaMemcpy(d1, ctx->d1, sizeof(double) * ctx->m, cudaMemcpyDeviceToHost));
+    if (d1 && ctx->m) {
+      MIPCU_CK(cudaMemcpy(d1, ctx->d1, sizeof(double) * ctx->m, cudaMemcpyDeviceToHost));
+      rows_to_caller_order(ctx, d1);
+    }
     if (d2 && ctx->n) MIPCU_CK(cudaMemcpy(d2, ctx->d2, sizeof(double) * ctx->n, cudaMemcpyDeviceToHost));
   });
 }

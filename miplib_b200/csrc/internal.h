@@ -168,6 +168,11 @@ struct mipcu_ctx {
   double* yhat_full = nullptr;
   int m_glob = 0;
   int row_off[mipcu::kMaxPeers + 1] = {};
+  // rows are kept sorted by decreasing length on the device (setup.cu:sort_rows_by_length): internal
+  // row i is the caller's row row_perm[i].  Null = identity.  Every m-vector that crosses the ABI
+  // (row sides, warm-start / solution duals, the test hooks) is permuted at the boundary.
+  int* row_perm = nullptr;
+  std::vector<int> h_row_perm;   // host copy, fetched on first use by the test hooks
   double *c = nullptr, *lb = nullptr, *ub = nullptr, *lo = nullptr, *hi = nullptr;
   // scaled copies + diagonal scalings
   double *cs = nullptr, *ls = nullptr, *us = nullptr, *los = nullptr, *his = nullptr;
@@ -223,6 +228,9 @@ void set_bounds(mipcu_ctx* ctx, int64_t n_changed, const int64_t* cols, const do
                 const double* ub);
 void spmv_host(mipcu_ctx* ctx, int transpose, const double* v, double* out);
 void build_col_block(mipcu_ctx* ctx);   // collective: the column block of the block-owner exchange
+const std::vector<int>& host_row_perm(mipcu_ctx* ctx);   // empty = identity
+void rows_to_caller_order(mipcu_ctx* ctx, double* v);    // host m-vector, internal -> caller's row order
+void rows_to_internal_order(mipcu_ctx* ctx, double* v);  // host m-vector, caller's -> internal row order
 
 // ---- dist.cu --------------------------------------------------------------------------------
 void dist_allreduce(mipcu_ctx* ctx, double* buf, size_t count, bool max_instead_of_sum);
