@@ -154,6 +154,7 @@ struct mipcu_ctx {
   mipcu::McWindow mc;
   bool own_ready = false;             // block-owner exchange: column block built, yhat_full mapped
   bool use_pdl = false;               // iteration kernels launched as programmatic dependents (MIPCU_PDL)
+  int own_blocks_per_cta = 0;         // block-owner kernels: 256-row blocks one CTA works through (0 = automatic)
   int own_variant = 0;                // laboratory switches (p2p.cu), 0 = shipped protocol
   unsigned long long own_epoch = 0;   // barrier generation of the block-owner kernels (same on all ranks)
 

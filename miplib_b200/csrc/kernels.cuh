@@ -94,13 +94,13 @@ __device__ __forceinline__ bool cta_row_sums(const int* __restrict__ ptr,
                                              const double* __restrict__ val,
                                              const unsigned char* __restrict__ perm,
                                              const double* __restrict__ vec, int nrows,
-                                             double* s_sum, Pre pre) {
+                                             double* s_sum, Pre pre, const int blk) {
   if constexpr (TPR == 0) {
     constexpr int U = kSellUnroll;
     const int lane = threadIdx.x & 31;
-    const int slice = blockIdx.x * (kRowsPerCta / 32) + (threadIdx.x >> 5);
+    const int slice = blk * (kRowsPerCta / 32) + (threadIdx.x >> 5);
     const int beg = ptr[slice], end = ptr[slice + 1];
-    const int slot = perm[blockIdx.x * kRowsPerCta + threadIdx.x];
+    const int slot = perm[blk * kRowsPerCta + threadIdx.x];
     double acc0 = 0.0, acc1 = 0.0;
     double v[U];
     int c[U];
@@ -134,7 +134,7 @@ __device__ __forceinline__ bool cta_row_sums(const int* __restrict__ ptr,
     constexpr int SUBS = kThreads / TPR;        // rows in flight per pass
     const int lane = threadIdx.x % TPR;
     const int sub = threadIdx.x / TPR;
-    const int row0 = blockIdx.x * kRowsPerCta;
+    const int row0 = blk * kRowsPerCta;
 #pragma unroll 2
     for (int r = sub; r < kRowsPerCta; r += SUBS) {
       const int row = row0 + r;
@@ -162,6 +162,14 @@ __device__ __forceinline__ bool cta_row_sums(const int* __restrict__ ptr,
   return true;
 }
 
+template <int TPR, class Pre>
+__device__ __forceinline__ bool cta_row_sums(const int* __restrict__ ptr, const int* __restrict__ idx,
+                                             const double* __restrict__ val,
+                                             const unsigned char* __restrict__ perm,
+                                             const double* __restrict__ vec, int nrows, double* s_sum, Pre pre) {
+  return cta_row_sums<TPR>(ptr, idx, val, perm, vec, nrows, s_sum, pre, (int)blockIdx.x);
+}
+
 template <int TPR>
 __device__ __forceinline__ void cta_row_sums(const int* __restrict__ ptr, const int* __restrict__ idx,
                                              const double* __restrict__ val,
@@ -174,7 +182,7 @@ __device__ __forceinline__ void cta_row_sums(const int* __restrict__ ptr, const 
 // partials[(q0 + q) * max_blocks + blockIdx.x].
 template <int NQ>
 __device__ __forceinline__ void cta_reduce_store(double (&v)[NQ], const int (&q)[NQ],
-                                                 double* partials, int max_blocks) {
+                                                 double* partials, int max_blocks, const int blk) {
   __shared__ double s_red[NQ][kThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -189,8 +197,14 @@ __device__ __forceinline__ void cta_reduce_store(double (&v)[NQ], const int (&q)
     double a = 0.0;
 #pragma unroll
     for (int w = 0; w < kThreads / 32; ++w) a += s_red[threadIdx.x][w];
-    partials[(size_t)q[threadIdx.x] * max_blocks + blockIdx.x] = a;
+    partials[(size_t)q[threadIdx.x] * max_blocks + blk] = a;
   }
+}
+
+template <int NQ>
+__device__ __forceinline__ void cta_reduce_store(double (&v)[NQ], const int (&q)[NQ],
+                                                 double* partials, int max_blocks) {
+  cta_reduce_store<NQ>(v, q, partials, max_blocks, (int)blockIdx.x);
 }
 
 struct RowStepArgs {

@@ -166,36 +166,47 @@ __device__ __forceinline__ void own_publish(const int variant) {
   if (threadIdx.x == 0) __threadfence_system();
 }
 
-template <int TPR, bool CHECK>
+// A CTA owns the blocks blockIdx.x, blockIdx.x + gridDim.x, ... (nblk in all): with more than one
+// block per CTA the pushes of block k travel while block k + 1 is multiplied.
+template <int TPR, bool CHECK, bool MULTI>
 __global__ void __launch_bounds__(kThreads)
-k_row_step_own(const RowStepArgs a, const PeerTable t, const unsigned long long epoch, const int variant) {
+k_row_step_own(const RowStepArgs a, const PeerTable t, const unsigned long long epoch, const int variant,
+               const int nblk) {
   __shared__ double s_sum[kRowsPerCta];
   const Scalars* sc = a.sc;
   pdl_trigger();
-  // the head of the nonzero stream is requested before the wait for the peers; `done` is identical
-  // on every rank and is looked at only after the barrier has been passed by all
-  if (!cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.perm, a.xbar, a.m, s_sum, [&] {
-        pdl_wait();
-        own_barrier(t, epoch, variant);
-        return !sc->done;
-      }))
-    return;
-  const double sigma = sc->sigma;
-  const double k = (double)(sc->k_base + a.iter_in_block);
-  const double w_new = (k + 1.0) / (k + 2.0);
-  const int i = blockIdx.x * kRowsPerCta + threadIdx.x;
-  double red[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  if (i < a.m) {
-    const double yh = row_epilogue<CHECK>(a, i, s_sum[threadIdx.x], sigma, w_new, red);
-    const int gi = t.i0[t.rank] + i;
-    if (!(variant & OWN_NO_PUSH)) {
-      if (t.mc_yhat_full) t.mc_yhat_full[gi] = yh;                      // one store, replicated by the switch
-      else for (int p = 0; p < t.world; ++p) t.yhat_full[p][gi] = yh;   // all-gather by push (self too)
+  double sigma = 0.0, w_new = 0.0;
+  for (int blk = blockIdx.x; MULTI ? blk < nblk : blk == (int)blockIdx.x; blk += MULTI ? gridDim.x : 1) {
+    // first block: the head of the nonzero stream is requested before the wait for the peers;
+    // `done` is identical on every rank and is looked at only after the barrier has been passed
+    const bool first = !MULTI || blk == (int)blockIdx.x;
+    if (!cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.perm, a.xbar, a.m, s_sum, [&] {
+          if (!first) return true;
+          pdl_wait();
+          own_barrier(t, epoch, variant);
+          return !sc->done;
+        }, blk))
+      return;
+    if (first) {
+      sigma = sc->sigma;
+      const double k = (double)(sc->k_base + a.iter_in_block);
+      w_new = (k + 1.0) / (k + 2.0);
     }
-  }
-  if (CHECK) {
-    const int q[5] = {Q_DY2, Q_DY0, Q_DOBJ_ROW, Q_RAYD_ROW, Q_RAYD_ROWV};
-    cta_reduce_store<5>(red, q, a.partials, sc->max_blocks);
+    const int i = blk * kRowsPerCta + threadIdx.x;
+    double red[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (i < a.m) {
+      const double yh = row_epilogue<CHECK>(a, i, s_sum[threadIdx.x], sigma, w_new, red);
+      const int gi = t.i0[t.rank] + i;
+      if (!(variant & OWN_NO_PUSH)) {
+        if (t.mc_yhat_full) t.mc_yhat_full[gi] = yh;                      // one store, replicated by the switch
+        else for (int p = 0; p < t.world; ++p) t.yhat_full[p][gi] = yh;   // all-gather by push (self too)
+      }
+    }
+    if (CHECK) {
+      const int q[5] = {Q_DY2, Q_DY0, Q_DOBJ_ROW, Q_RAYD_ROW, Q_RAYD_ROWV};
+      cta_reduce_store<5>(red, q, a.partials, sc->max_blocks, blk);
+    }
+    if (MULTI) __syncthreads();      // s_sum (and the reduction scratch) are reused by the next block
   }
   own_publish(variant);
 }
@@ -203,69 +214,115 @@ k_row_step_own(const RowStepArgs a, const PeerTable t, const unsigned long long 
 // `a` addresses the rank's column slice: every per-column pointer is already offset by j0, a.n is
 // the slice length, a.yhat is this rank's whole yhat_full.  push_xhat: the stored xhat is the KKT
 // candidate, which the row-side KKT pass of every rank gathers.
-template <int TPR, bool CHECK, bool STORE>
+template <int TPR, bool CHECK, bool STORE, bool MULTI>
 __global__ void __launch_bounds__(kThreads)
 k_col_step_own(const ColStepArgs a, const PeerTable t, const unsigned long long epoch, const int push_xhat,
-               const int variant) {
+               const int variant, const int nblk) {
   __shared__ double s_sum[kRowsPerCta];
   const Scalars* sc = a.sc;
   pdl_trigger();
-  if (!cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.perm, a.yhat, a.n, s_sum, [&] {
-        pdl_wait();
-        own_barrier(t, epoch, variant);
-        return !sc->done;
-      }))
-    return;
-  const double tau = sc->tau;
-  const double k = (double)(sc->k_base + a.iter_in_block);
-  const double w_new = (k + 1.0) / (k + 2.0);
-  const int j = blockIdx.x * kRowsPerCta + threadIdx.x;
-  double red[10] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  if (j < a.n) {
-    col_epilogue<CHECK, STORE>(a, j, s_sum[threadIdx.x], tau, w_new, red);
-    const int gj = t.j0[t.rank] + j;
-    const double xb = a.xbar[j];
-    if (!(variant & OWN_NO_PUSH)) {
-      if (t.mc_xbar) t.mc_xbar[gj] = xb;
-      else
+  double tau = 0.0, w_new = 0.0;
+  for (int blk = blockIdx.x; MULTI ? blk < nblk : blk == (int)blockIdx.x; blk += MULTI ? gridDim.x : 1) {
+    const bool first = !MULTI || blk == (int)blockIdx.x;
+    if (!cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.perm, a.yhat, a.n, s_sum, [&] {
+          if (!first) return true;
+          pdl_wait();
+          own_barrier(t, epoch, variant);
+          return !sc->done;
+        }, blk))
+      return;
+    if (first) {
+      tau = sc->tau;
+      const double k = (double)(sc->k_base + a.iter_in_block);
+      w_new = (k + 1.0) / (k + 2.0);
+    }
+    const int j = blk * kRowsPerCta + threadIdx.x;
+    double red[10] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (j < a.n) {
+      col_epilogue<CHECK, STORE>(a, j, s_sum[threadIdx.x], tau, w_new, red);
+      const int gj = t.j0[t.rank] + j;
+      const double xb = a.xbar[j];
+      if (!(variant & OWN_NO_PUSH)) {
+        if (t.mc_xbar) t.mc_xbar[gj] = xb;
+        else
+          for (int p = 0; p < t.world; ++p)
+            if (p != t.rank) t.xbar[p][gj] = xb;
+      }
+      if (STORE && push_xhat) {
+        const double xh = a.xhat_out[j];
         for (int p = 0; p < t.world; ++p)
-          if (p != t.rank) t.xbar[p][gj] = xb;
+          if (p != t.rank) t.xhat_chk[p][gj] = xh;
+      }
     }
-    if (STORE && push_xhat) {
-      const double xh = a.xhat_out[j];
-      for (int p = 0; p < t.world; ++p)
-        if (p != t.rank) t.xhat_chk[p][gj] = xh;
+    if (CHECK) {
+      const int q[10] = {Q_DX2, Q_DXDATY, Q_DX0, Q_DRES2, Q_POBJ, Q_DOBJ_COL,
+                         Q_RAYD_COL, Q_RAYD_COLV, Q_RAYP_C, Q_RAYP_COLV};
+      cta_reduce_store<10>(red, q, a.partials, sc->max_blocks, blk);
     }
-  }
-  if (CHECK) {
-    const int q[10] = {Q_DX2, Q_DXDATY, Q_DX0, Q_DRES2, Q_POBJ, Q_DOBJ_COL,
-                       Q_RAYD_COL, Q_RAYD_COLV, Q_RAYP_C, Q_RAYP_COLV};
-    cta_reduce_store<10>(red, q, a.partials, sc->max_blocks);
+    if (MULTI) __syncthreads();
   }
   own_publish(variant);
 }
 
+// Blocks per CTA.  One while a grid of one block per CTA is longer than about a wave (the waves
+// already stagger the pushes over the kernel).  Around one wave or less - the 4 and 8 GPU shards of
+// config 3 - every CTA would finish, and push, at the same moment at the end of the kernel; a CTA
+// that works through about 14k nonzeros in 2 - 4 blocks pushes block k while it multiplies block
+// k + 1.  Measured on config 3 (profiles/r01_block_owner_exchange.md): 8 GPUs, row step (488
+// blocks of 8k nonzeros) 36.1 / 35.0 / 44.5 us and column step (977 blocks of 4k) 45.0 / 40.4 /
+// 38.1 us for 1 / 2 / 3 blocks per CTA; 4 GPUs, row step (977 blocks) 57.3 / 51.6 / 56.3 us.
+// MIPCU_OWN_BLOCKS overrides (laboratory).
+int own_grid(const mipcu_ctx* ctx, int nblk, int64_t nnz) {
+  int per_cta = ctx->own_blocks_per_cta;
+  if (per_cta <= 0) {
+    per_cta = 1;
+    const int slots = 6 * ctx->sm_count;                 // resident CTAs of these kernels (40 registers)
+    if (nblk > 1 && nblk <= slots + slots / 4) {
+      const double per_block = (double)nnz / nblk;
+      per_cta = (int)(14000.0 / std::max(per_block, 1.0) + 0.5);
+      per_cta = std::max(1, std::min(per_cta, 4));
+      while (per_cta > 1 && (nblk + per_cta - 1) / per_cta < ctx->sm_count + ctx->sm_count / 2) --per_cta;
+    }
+  }
+  return std::max(1, (nblk + per_cta - 1) / per_cta);
+}
+
 template <int TPR>
 void launch_row_own(mipcu_ctx* ctx, const RowStepArgs& a, bool check) {
-  const int g = std::max(1, grid_for(ctx->m, kRowsPerCta));
+  const int nblk = std::max(1, grid_for(ctx->m, kRowsPerCta)), g = own_grid(ctx, nblk, ctx->rows.nnz);
   const unsigned long long e = ++ctx->own_epoch;
   const bool pdl = ctx->use_pdl;
-  if (check) launch_kernel(k_row_step_own<TPR, true>, g, ctx->stream, pdl, a, ctx->peers, e, ctx->own_variant);
-  else launch_kernel(k_row_step_own<TPR, false>, g, ctx->stream, pdl, a, ctx->peers, e, ctx->own_variant);
+  const int v = ctx->own_variant;
+  cudaStream_t st = ctx->stream;
+  const PeerTable& t = ctx->peers;
+  if (g < nblk) {
+    if (check) launch_kernel(k_row_step_own<TPR, true, true>, g, st, pdl, a, t, e, v, nblk);
+    else launch_kernel(k_row_step_own<TPR, false, true>, g, st, pdl, a, t, e, v, nblk);
+  } else {
+    if (check) launch_kernel(k_row_step_own<TPR, true, false>, g, st, pdl, a, t, e, v, nblk);
+    else launch_kernel(k_row_step_own<TPR, false, false>, g, st, pdl, a, t, e, v, nblk);
+  }
 }
 
 template <int TPR>
 void launch_col_own(mipcu_ctx* ctx, const ColStepArgs& a, bool check, bool store, int push_xhat) {
-  const int g = std::max(1, grid_for(a.n, kRowsPerCta));
+  const int nblk = std::max(1, grid_for(a.n, kRowsPerCta)), g = own_grid(ctx, nblk, ctx->colblk.nnz);
   const unsigned long long e = ++ctx->own_epoch;
   cudaStream_t st = ctx->stream;
   const PeerTable& t = ctx->peers;
   const bool pdl = ctx->use_pdl;
   const int v = ctx->own_variant;
-  if (check && store) launch_kernel(k_col_step_own<TPR, true, true>, g, st, pdl, a, t, e, push_xhat, v);
-  else if (check) launch_kernel(k_col_step_own<TPR, true, false>, g, st, pdl, a, t, e, push_xhat, v);
-  else if (store) launch_kernel(k_col_step_own<TPR, false, true>, g, st, pdl, a, t, e, push_xhat, v);
-  else launch_kernel(k_col_step_own<TPR, false, false>, g, st, pdl, a, t, e, push_xhat, v);
+  if (g < nblk) {
+    if (check && store) launch_kernel(k_col_step_own<TPR, true, true, true>, g, st, pdl, a, t, e, push_xhat, v, nblk);
+    else if (check) launch_kernel(k_col_step_own<TPR, true, false, true>, g, st, pdl, a, t, e, push_xhat, v, nblk);
+    else if (store) launch_kernel(k_col_step_own<TPR, false, true, true>, g, st, pdl, a, t, e, push_xhat, v, nblk);
+    else launch_kernel(k_col_step_own<TPR, false, false, true>, g, st, pdl, a, t, e, push_xhat, v, nblk);
+  } else {
+    if (check && store) launch_kernel(k_col_step_own<TPR, true, true, false>, g, st, pdl, a, t, e, push_xhat, v, nblk);
+    else if (check) launch_kernel(k_col_step_own<TPR, true, false, false>, g, st, pdl, a, t, e, push_xhat, v, nblk);
+    else if (store) launch_kernel(k_col_step_own<TPR, false, true, false>, g, st, pdl, a, t, e, push_xhat, v, nblk);
+    else launch_kernel(k_col_step_own<TPR, false, false, false>, g, st, pdl, a, t, e, push_xhat, v, nblk);
+  }
 }
 
 // all-gather of one replicated vector: every rank pushes its slice into all peers
@@ -301,6 +358,8 @@ void own_setup(mipcu_ctx* ctx) {
   ctx->params[MIPCU_PARAM_MULTICAST] = mc_setup(ctx) ? 1.0 : 0.0;
   const char* v = std::getenv("MIPCU_OWN_VARIANT");
   ctx->own_variant = v ? std::atoi(v) : OWN_NO_PUBLISH;
+  const char* b = std::getenv("MIPCU_OWN_BLOCKS");
+  ctx->own_blocks_per_cta = b ? std::atoi(b) : 0;     // 0: chosen per kernel (own_grid)
   ctx->own_ready = true;
 }
 

@@ -20,12 +20,13 @@ def worker(rank, world, uid, cfg, out):
     L = gen.config(cfg)
     ptr, idx, val, lo, hi = sharding.shard_csr(L.A, L.row_lo, L.row_hi, rank, world)
     res = {}
-    cases = [(1, 0, 0, 0), (2, 1, 0, 0), (2, 1, 0, 1), (2, 0, 0, 1), (2, 5, 0, 0), (2, 13, 0, 0)]
+    cases = [(1, 0, 0, 0, 1), (2, 1, 0, 1, 1), (2, 1, 0, 1, 2), (2, 1, 0, 1, 3), (2, 1, 0, 1, 4), (2, 13, 0, 0, 1), (2, 13, 0, 0, 2)]
     if os.environ.get("OWN_LAB_CASES"):
         cases = [tuple(int(v) for v in c.split(",")) for c in os.environ["OWN_LAB_CASES"].split(";")]
     with Engine(rank, rank, world, uid) as e:
-        for ex, var, pdl, mc in cases:
+        for ex, var, pdl, mc, blocks in cases:
             os.environ["MIPCU_OWN_VARIANT"] = str(var)
+            os.environ["MIPCU_OWN_BLOCKS"] = str(blocks)
             e.set_param("shard_exchange", ex)
             e.set_param("use_pdl", pdl)
             e.set_param("multicast", mc)
@@ -39,7 +40,7 @@ def worker(rank, world, uid, cfg, out):
                 e.solve()
                 st = e.solve()
                 its = st.iterations / st.iter_seconds
-            res[(ex, var, pdl, mc)] = (row, col, its)
+            res[(ex, var, pdl, mc, blocks)] = (row, col, its)
     out[rank] = res
 
 
@@ -53,7 +54,7 @@ if __name__ == "__main__":
         out = mgr.dict()
         mp.spawn(worker, args=(world, uid, cfg, out), nprocs=world, join=True)
         res = dict(out)
-    print("exchange variant pdl multicast(in use) | row us (rank 0 / last) | col us (rank 0 / last) | solve it/s")
+    print("exchange variant pdl multicast(in use) blocks/CTA | row us (rank 0 / last) | col us (rank 0 / last) | solve it/s")
     for key in res[0]:
         r0, r1 = res[0][key], res[world - 1][key]
-        print(f"{key[0]:8d} {key[1]:7d} {key[2]:3d} {key[3]:3d} | {r0[0]:8.1f} {r1[0]:8.1f} | {r0[1]:8.1f} {r1[1]:8.1f} | {r0[2]:8.0f}")
+        print(f"{key[0]:8d} {key[1]:7d} {key[2]:3d} {key[3]:3d} {key[4]:3d} | {r0[0]:8.1f} {r1[0]:8.1f} | {r0[1]:8.1f} {r1[1]:8.1f} | {r0[2]:8.0f}")
