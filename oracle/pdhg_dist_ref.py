@@ -4,7 +4,9 @@ Each rank holds a row block of A; the only data-path exchange is the sum over ra
 products K_g' yhat_g, plus a few scalars on check iterations and the column norms during the
 equilibration - exactly what miplib_b200/csrc/dist.cu does with NCCL.  Here the collectives go
 through a tiny `comm` object (torch.distributed over gloo in tests/test_sharded_cpu.py), so the
-N > 1 host logic is covered on CPU with world_size 2."""
+N > 1 host logic is covered on CPU with world_size 2.  `solve_block_owner` restates the default
+exchange of miplib_b200/csrc/p2p.cu (row block of K + column block of K' per rank, two all-gathers
+per iteration) the same way."""
 from __future__ import annotations
 
 import numpy as np
@@ -17,6 +19,7 @@ class LocalComm:
     """world_size 1: every collective is the identity."""
     def sum(self, a): return a
     def max(self, a): return a
+    def gather(self, a): return [a]
 
 
 def _segment(uf, values, ptr):
@@ -129,4 +132,104 @@ def solve_sharded(Ag, c, lb, ub, lo_g, hi_g, comm, maximize=False, eps=1e-6, max
             x0 = xh_k.copy(); y0 = yhat.copy(); aty0 = atyh.copy(); y = y0.copy(); aty = aty0.copy()
             xhat_first, xbar = seed(x0, aty0, w); k = 0
     return dict(status=status, x=xh_k * d2, y_local=sgn * yhat * d1, obj=sgn * pobj, iters=total,
+                restarts=restarts, rel_pres=rel_p, rel_dres=rel_d, rel_gap=rel_g)
+
+
+def solve_block_owner(Ag, c, lb, ub, lo_g, hi_g, comm, rank, world, maximize=False, eps=1e-6,
+                      max_iter=200000, period=64):
+    """The block-owner exchange of miplib_b200/csrc/p2p.cu (MIPCU_PARAM_SHARD_EXCHANGE = 2): rank g
+    owns row block g of K (row step on its rows, yhat slices all-gathered) AND column block g of K'
+    (whole columns cut out of all ranks' blocks at load; primal step on its column slice, xbar
+    slices all-gathered).  No partial-sum vector, no reduction on the data path: every column sum
+    runs over the whole column in global row order, as in the single-process oracle.
+    `comm.gather(a)` returns the list of every rank's array, in rank order."""
+    sgn = -1.0 if maximize else 1.0
+    c0 = sgn * np.asarray(c, float)
+    K, d1, d2 = scale_sharded(Ag, comm)
+    KT = K.T.tocsr(); KT.sort_indices()
+    n, mg = K.shape[1], K.shape[0]
+    j0, j1 = (n * rank) // world, (n * (rank + 1)) // world
+    # column block of the WHOLE scaled matrix: all ranks' blocks stacked, columns [j0, j1)
+    blocks = comm.gather((K.indptr, K.indices, K.data, mg))
+    Kfull = sp.vstack([sp.csr_matrix((d, i, p), shape=(r, n)) for p, i, d, r in blocks]).tocsr()
+    KcT = Kfull[:, j0:j1].T.tocsr(); KcT.sort_indices()           # (j1 - j0) x m_glob
+    cs = c0 * d2; l = lb / d2; u = ub / d2; lo = lo_g * d1; hi = hi_g * d1
+    bnorm = float(np.sqrt(comm.sum(np.array([np.sum(R.finite_abs_max(lo_g, hi_g) ** 2)]))[0]))
+    cnorm = float(np.linalg.norm(c0))
+    bs = float(np.sqrt(comm.sum(np.array([np.sum(R.finite_abs_max(lo, hi) ** 2)]))[0]))
+    csn = float(np.linalg.norm(cs))
+    w = csn / bs if (csn > 0 and bs > 0) else 1.0
+    v = R.hash_unit_vector(n); v /= np.linalg.norm(v)
+    prev = s = 0.0; it = 0
+    while it < R.POWER_MAX:
+        for _ in range(R.POWER_BATCH):
+            v = comm.sum(KT @ (K @ v)); s2 = np.linalg.norm(v); v /= s2; it += 1
+        s = np.sqrt(s2)
+        if abs(s - prev) <= R.POWER_TOL * s: break
+        prev = s
+    eta = R.STEP_SAFETY / s
+    sl = slice(j0, j1)                                   # column-side state lives on the slice only
+    cs_s, l_s, u_s, d2_s = cs[sl], l[sl], u[sl], d2[sl]
+    x0 = np.clip(np.zeros(j1 - j0), l_s, u_s); y0 = np.zeros(mg)
+    aty0 = KcT @ np.concatenate(comm.gather(y0))
+
+    def seed(x0, aty0, w):
+        xh = np.clip(x0 - (eta / w) * (cs_s - aty0), l_s, u_s)
+        return xh, np.concatenate(comm.gather(2.0 * xh - x0))        # xbar is kept whole
+    xhat_first, xbar = seed(x0, aty0, w)
+    y = y0.copy(); aty = aty0.copy(); k = total = restarts = 0
+    fp0 = fp_prev = None; xhat_chk = xhat_first
+    status = "iteration_limit"
+    while total < max_iter:
+        tau, sigma = eta / w, eta * w
+        for i in range(period):
+            a = (k + 1.0) / (k + 2.0)
+            first, last = i == 0, i == period - 1
+            y_k = y
+            kx = K @ xbar                                             # row step: this rank's rows
+            t = kx - y / sigma
+            yhat = sigma * (np.clip(t, lo, hi) - t)
+            y = a * (2.0 * yhat - y) + (1.0 - a) * y0
+            yhat_full = np.concatenate(comm.gather(yhat))             # exchange 1: yhat slices
+            if first or last:
+                xh_k = xhat_first if first else xhat_chk              # slice
+                dx = xbar[sl] - xh_k
+                if last:
+                    kxh = K @ np.concatenate(comm.gather(xh_k))       # KKT pass gathers the whole candidate
+            atyh = KcT @ yhat_full                                    # col step: this rank's columns
+            x = a * xbar[sl] + (1.0 - a) * x0
+            aty_new = a * (2.0 * atyh - aty) + (1.0 - a) * aty0
+            xhat_next = np.clip(x - tau * (cs_s - aty_new), l_s, u_s)
+            if first or last:
+                dy2, dx2, dxd = comm.sum(np.array([np.sum((yhat - y_k) ** 2), dx @ dx, dx @ (atyh - aty)]))
+                fp = np.sqrt(max((w / eta) * dx2 - 2.0 * dxd + dy2 / (eta * w), 0.0))
+            aty = aty_new
+            xbar = np.concatenate(comm.gather(2.0 * xhat_next - x))   # exchange 2: xbar slices
+            if i == period - 2: xhat_chk = xhat_next
+            if last: xhat_first = xhat_next
+            k += 1; total += 1
+            if first and k == 1: fp0 = fp_prev = fp
+        r = cs_s - atyh; rp = np.maximum(r, 0); rm = np.maximum(-r, 0)
+        viol = (np.where(np.isfinite(l_s), 0, rp) + np.where(np.isfinite(u_s), 0, rm)) / d2_s
+        pres2, dy0, dobj, dres2, pobj, dx0 = comm.sum(np.array([
+            np.sum(((kxh - np.clip(kxh, lo, hi)) / d1) ** 2), np.sum((yhat - y0) ** 2),
+            np.where(np.isfinite(lo), lo, 0.0) @ np.maximum(yhat, 0) - np.where(np.isfinite(hi), hi, 0.0) @ np.maximum(-yhat, 0)
+            + np.where(np.isfinite(l_s), l_s, 0) @ rp - np.where(np.isfinite(u_s), u_s, 0) @ rm,
+            viol @ viol, cs_s @ xh_k, np.sum((xh_k - x0) ** 2)]))
+        rel_p = np.sqrt(pres2) / (1 + bnorm); rel_d = np.sqrt(dres2) / (1 + cnorm)
+        rel_g = abs(pobj - dobj) / (1 + abs(pobj) + abs(dobj))
+        if max(rel_p, rel_d, rel_g) <= eps:
+            status = "optimal"; break
+        restart = fp <= R.BETA_SUFFICIENT * fp0 or (fp <= R.BETA_NECESSARY * fp0 and fp > fp_prev) \
+            or k >= R.BETA_ARTIFICIAL * total
+        fp_prev = fp
+        if restart:
+            restarts += 1
+            dxn = np.sqrt(dx0); dyn = np.sqrt(dy0)
+            if dxn > R.WEIGHT_EPS and dyn > R.WEIGHT_EPS:
+                w = np.exp(R.WEIGHT_SMOOTHING * np.log(dyn / dxn) + (1 - R.WEIGHT_SMOOTHING) * np.log(w))
+            x0 = xh_k.copy(); y0 = yhat.copy(); aty0 = atyh.copy(); y = y0.copy(); aty = aty0.copy()
+            xhat_first, xbar = seed(x0, aty0, w); k = 0
+    x_full = np.concatenate(comm.gather(xh_k * d2_s))
+    return dict(status=status, x=x_full, y_local=sgn * yhat * d1, obj=sgn * pobj, iters=total,
                 restarts=restarts, rel_pres=rel_p, rel_dres=rel_d, rel_gap=rel_g)

@@ -33,27 +33,37 @@ class GlooComm:
         return t.numpy()
     def sum(self, a): return self._all(a, dist.ReduceOp.SUM)
     def max(self, a): return self._all(a, dist.ReduceOp.MAX)
+    def gather(self, a):
+        out = [None] * dist.get_world_size()
+        dist.all_gather_object(out, a)
+        return out
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, exchange="allreduce"):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
         import scipy.sparse as sp
         L = gen.lp(300, 500, 6, 7)
         ptr, idx, val, lo, hi = sharding.shard_csr(L.A, L.row_lo, L.row_hi, rank, world)
         Ag = sp.csr_matrix((val, idx, ptr), shape=(ptr.size - 1, L.n))
-        r = pdhg_dist_ref.solve_sharded(Ag, L.c, L.lb, L.ub, lo, hi, GlooComm())
+        if exchange == "owner":
+            r = pdhg_dist_ref.solve_block_owner(Ag, L.c, L.lb, L.ub, lo, hi, GlooComm(), rank, world)
+        else:
+            r = pdhg_dist_ref.solve_sharded(Ag, L.c, L.lb, L.ub, lo, hi, GlooComm())
         out[rank] = (r["status"], r["obj"], r["iters"], r["restarts"], r["x"].copy(), r["y_local"].copy())
     finally:
         dist.destroy_process_group()
 
 
-def test_sharded_oracle_world2_gloo_matches_single_process():
+@pytest.mark.parametrize("exchange", ["allreduce", "owner"])
+def test_sharded_oracle_world2_gloo_matches_single_process(exchange):
+    """allreduce: partial K_g' yhat_g summed over the ranks (dist.cu); owner: the block-owner exchange
+    of p2p.cu - row block + column block per rank, two all-gathers per iteration."""
     world = 2
     port = 29500 + np.random.default_rng().integers(0, 2000)
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(world, int(port), out), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, int(port), out, exchange), nprocs=world, join=True)
         res = dict(out)
     ref = pdhg_ref.solve(gen.lp(300, 500, 6, 7))
     L = gen.lp(300, 500, 6, 7)
@@ -68,6 +78,14 @@ def test_sharded_oracle_world2_gloo_matches_single_process():
     from oracle import kkt_verify
     cert = kkt_verify.certificate(L, res[0][4], y)
     assert max(cert["rel_primal_res"], cert["rel_dual_res"], cert["rel_gap"]) <= 1.05e-6
+
+
+def test_block_owner_oracle_world1_is_the_plain_oracle():
+    L = gen.lp(300, 500, 6, 8)
+    r = pdhg_dist_ref.solve_block_owner(L.A, L.c, L.lb, L.ub, L.row_lo, L.row_hi, pdhg_dist_ref.LocalComm(), 0, 1)
+    ref = pdhg_ref.solve(L)
+    assert r["iters"] == ref["iters"] and abs(r["obj"] - ref["obj"]) <= 1e-12 * (1 + abs(ref["obj"]))
+    assert np.abs(r["x"] - ref["x"]).max() <= 1e-12
 
 
 def test_sharded_oracle_world1_is_the_plain_oracle():
