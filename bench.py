@@ -315,6 +315,15 @@ def run_cuda(args, rank, world, local_rank):
         line["roofline"]["col_step_split_us"] = {
             "partial_spmv": float(np.mean([s.col_partial_us for s in stats])),
             "exchange_and_primal": float(np.mean([s.col_exchange_us for s in stats]))}
+    if world == 1:
+        # the two plain products (B_Ax / B_ATy over >= 100 repetitions, CUDA events on
+        # the library's stream through the mipcu_time_kernel hook); after the timed solves
+        spmv = {}
+        for which, name in ((0, "Ax"), (1, "ATy")):
+            us, nbytes = eng.time_kernel(which, 100, False)
+            spmv[name] = {"launch_us": us, "bytes": int(nbytes), "GBps": nbytes / us / 1e3,
+                          "frac_of_peak": nbytes / us / 1e3 / peak}
+        line["spmv"] = spmv
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(L)
     print(json.dumps(line), flush=True)

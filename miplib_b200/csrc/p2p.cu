@@ -150,11 +150,11 @@ __device__ __forceinline__ void own_barrier(const PeerTable& t, const unsigned l
     int spins = 0;
     if (variant & OWN_RELAXED_POLL) {
       while (ld_relaxed_sys(f) < epoch)
-        if (++spins > (1 << 24)) asm volatile("trap;");
+        if (++spins > (1 << 27)) asm volatile("trap;");
       __threadfence_system();
     } else {
       while (ld_acquire_sys(f) < epoch)
-        if (++spins > (1 << 24)) asm volatile("trap;");   // a lost peer must not hang the device
+        if (++spins > (1 << 27)) asm volatile("trap;");   // a lost peer must not hang the device (~1 min)
     }
   }
   __syncthreads();
