@@ -1,7 +1,9 @@
 """Regenerates tests/golden/objectives.json and tests/golden/pdhg_trace_c1.npz.
 
 Run in the build container (needs SciPy's HiGHS; minutes, because of the 10k x 20k IPM solve):
-    python tests/golden/make_golden.py [--with-mid]
+    python tests/golden/make_golden.py [--with-mid] [--with-c2] [--with-c3]
+--with-c2 / --with-c3: configs 2 / 3 by HiGHS' own PDLP (2 minutes / hours on one core), the only
+independent solver that finishes them here.
 The values are the independent exact-solver optima the parity tests compare the CUDA backend
 against (HiGHS stand-in for the reference's SCIP / lp_solve backends).
 """
@@ -43,6 +45,17 @@ else:
     old = json.loads((HERE / "objectives.json").read_text()) if (HERE / "objectives.json").exists() else {}
     if "mid_lp" in old:
         out["mid_lp"] = old["mid_lp"]
+old = json.loads((HERE / "objectives.json").read_text()) if (HERE / "objectives.json").exists() else {}
+for cfg in (2, 3):
+    key = f"C{cfg}_lp"
+    if f"--with-c{cfg}" in sys.argv:
+        r = highs_ref.solve_lp_pdlp(gen.config(cfg), 1e-6)
+        assert r["status"] == "kOptimal", r["status"]
+        put(key, f"config({cfg})", "highs-pdlp 1e-6", r["obj"],
+            {"iterations": r["iters"], "seconds": round(r["secs"], 1),
+             "max_primal_infeasibility": r["max_primal_infeas"], "max_dual_infeasibility": r["max_dual_infeas"]})
+    elif key in old:
+        out[key] = old[key]
 (HERE / "objectives.json").write_text(json.dumps(out, indent=1) + "\n")
 
 # iterate-level golden vectors of the oracle on C1: scaled (xbar, y) after 10 and 64 iterations,

@@ -102,6 +102,16 @@ def test_scaling_equilibrates():
     assert 0.9 < s <= 1.0 + 1e-9                          # Pock-Chambolle alpha=1 bounds ||K||_2 by 1
 
 
+def test_highs_pdlp_stand_in_agrees_with_highs_simplex(golden):
+    """The second independent solver used to pin configs 2 and 3 (HiGHS' own PDLP) against the exact
+    one on config 1, and the committed config-2 value is the kind it claims to be."""
+    from oracle import highs_ref
+    r = highs_ref.solve_lp_pdlp(gen.config(1), 1e-6)
+    assert r["status"] == "kOptimal"
+    assert rel(r["obj"], golden["C1_lp"]["objective"]) <= 1e-6
+    assert golden["C2_lp"]["kind"].startswith("highs-pdlp") and golden["C2_lp"]["objective"] < 0
+
+
 def test_golden_trace_reproduces():
     from pathlib import Path
     z = np.load(Path(__file__).parent / "golden" / "pdhg_trace_c1.npz")
