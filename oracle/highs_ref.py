@@ -93,7 +93,8 @@ def solve_lp_pdlp(lpm: LP, eps: float = 1e-6, time_limit: float | None = None):
     h.setOptionValue("presolve", "off")
     if time_limit is not None:
         h.setOptionValue("time_limit", float(time_limit))
-    for key in ("pdlp_d_gap_tol", "primal_feasibility_tolerance", "dual_feasibility_tolerance"):
+    # pdlp_optimality_tolerance (relative duality gap) keeps its default 1e-7: tighter than eps
+    for key in ("primal_feasibility_tolerance", "dual_feasibility_tolerance"):
         h.setOptionValue(key, float(eps))
     h.passModel(lp)
     t0 = time.time()
