@@ -379,7 +379,8 @@ void launch_col_sell(mipcu_ctx* ctx, const ColStepArgs& a, bool check, bool stor
   }
 
 void row_step(mipcu_ctx* ctx, int i, bool check, bool keep_kx = false) {
-  if (ctx->m == 0) return;
+  // block-owner exchange: a rank that owns no rows still has to pass the kernel's barrier
+  if (ctx->m == 0 && !own_active(ctx)) return;
   RowStepArgs a = row_args(ctx, i);
   if (keep_kx) a.kx_save = ctx->tmp_m;
   if (own_active(ctx)) { own_row_step(ctx, a, check); return; }
