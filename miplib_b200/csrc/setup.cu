@@ -189,6 +189,11 @@ __global__ void k_div(const double* __restrict__ a, const double* __restrict__ b
   if (i < count) out[i] = a[i] / b[i];
 }
 
+__global__ void k_div_inplace(double* v, const double* __restrict__ b, int count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) v[i] /= b[i];
+}
+
 __global__ void k_scale_inplace(double* v, double s, int count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) v[i] *= s;
@@ -983,14 +988,14 @@ void spmv_host(mipcu_ctx* ctx, int transpose, const double* v, double* out) {
   }
   if (n_in) MIPCU_CK(cudaMemcpyAsync(d_in, v, sizeof(double) * n_in, cudaMemcpyHostToDevice, st));
   if (ctx->prepared && n_in) {
-    k_div<<<grid_for(n_in), kThreads, 0, st>>>(d_in, din_scale, d_in, n_in);
+    k_div_inplace<<<grid_for(n_in), kThreads, 0, st>>>(d_in, din_scale, n_in);
     ctx->launches++;
   }
   if (n_out) {
     if (n_in && ctx->nnz) spmv_plain(ctx, transpose ? ctx->cols : ctx->rows, d_in, d_out);
     else MIPCU_CK(cudaMemsetAsync(d_out, 0, sizeof(double) * n_out, st));
     if (ctx->prepared) {
-      k_div<<<grid_for(n_out), kThreads, 0, st>>>(d_out, dout_scale, d_out, n_out);
+      k_div_inplace<<<grid_for(n_out), kThreads, 0, st>>>(d_out, dout_scale, n_out);
       ctx->launches++;
     }
     MIPCU_CK(cudaMemcpyAsync(out, d_out, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
