@@ -323,13 +323,13 @@ void CudaSolver::dump(std::string const& filename) const
       bool const is_int = m_columns[j].type != Var::Type::Continuous;
       if (is_int != in_int)
       {
-        out << " MARKER MARKER " << (is_int ? "INTORG" : "INTEND") << "\n";
+        out << " MARKER 'MARKER' " << (is_int ? "'INTORG'" : "'INTEND'") << "\n";   // quoted: the MPS convention
         in_int = is_int;
       }
       out << " " << col_name(j) << " obj " << obj(j) << "\n";
       for (auto const& [r, v] : by_col[j]) out << " " << col_name(j) << " r" << r << " " << v << "\n";
     }
-    if (in_int) out << " MARKER MARKER INTEND\n";
+    if (in_int) out << " MARKER 'MARKER' 'INTEND'\n";
     out << "RHS\n";
     for (std::size_t r : rows)
     {

@@ -303,6 +303,81 @@ GPU_TEST("Bulk CSR ingress: LP and MIP without Var / Expr objects (miplib/cuda/c
 // Replays oracle/gen.py's recipes through Var / Expr / Constr from a text fixture written by the
 // pytest wrapper (tests/test_frontend.py): "n m" / per column "type lb ub cost" / per row
 // "lo hi k (col val)*k" / "maximize expected_objective kind".
+namespace {
+
+struct FixtureModel
+{
+  std::string label;
+  std::vector<Var> vars;
+  Expr objective;
+  int maximize = 0;
+  double expected = 0, tol = 0;
+};
+
+// one model of the fixture, built into `solver` through the public modelling API only
+FixtureModel read_fixture_model(std::istream& in, Solver& solver)
+{
+  FixtureModel f;
+  std::size_t n, m;
+  in >> f.label >> n >> m;
+  for (std::size_t j = 0; j < n; ++j)
+  {
+    int type;
+    double lb, ub, cost;
+    in >> type >> lb >> ub >> cost;
+    f.vars.emplace_back(solver, static_cast<Var::Type>(type), lb, ub);
+    if (cost != 0) f.objective += cost * f.vars.back();
+  }
+  for (std::size_t i = 0; i < m; ++i)
+  {
+    std::string lo_s, hi_s;
+    std::size_t k;
+    in >> lo_s >> hi_s >> k;
+    Expr row;
+    for (std::size_t e = 0; e < k; ++e)
+    {
+      std::size_t col;
+      double val;
+      in >> col >> val;
+      row += val * f.vars[col];
+    }
+    bool const has_lo = lo_s != "-inf", has_hi = hi_s != "inf";
+    if (has_lo && has_hi && lo_s == hi_s) solver.add(row == std::stod(hi_s));
+    else
+    {
+      if (has_hi) solver.add(row <= std::stod(hi_s));
+      if (has_lo) solver.add(row >= std::stod(lo_s));
+    }
+  }
+  in >> f.maximize >> f.expected >> f.tol;
+  return f;
+}
+
+}  // namespace
+
+// No device needed: the model is lowered by CudaSolver::add / set_objective (the code that replaces
+// reference miplib/lpsolve/solver.cpp:66-131, miplib/scip/solver.cpp:69-178) and written with
+// dump(); tests/test_frontend.py reads the MPS files back with an independent reader (HiGHS),
+// compares them entry for entry with the generator's arrays and solves them exactly.
+CPU_TEST("Generated models lowered through the expression API are dumped as MPS")
+{
+  char const* path = std::getenv("MIPLIB_TEST_MODELS");
+  char const* dir = std::getenv("MIPLIB_TEST_DUMP_DIR");
+  if (!path || !dir) return;
+  std::ifstream in(path);
+  REQUIRE(in.good());
+  int count;
+  in >> count;
+  for (int t = 0; t < count; ++t)
+  {
+    Solver solver(B, false);
+    FixtureModel f = read_fixture_model(in, solver);
+    solver.set_objective(f.maximize ? Solver::Sense::Maximize : Solver::Sense::Minimize, f.objective);
+    solver.dump(std::string(dir) + "/" + f.label + ".mps");
+    solver.dump(std::string(dir) + "/" + f.label + ".lp");
+  }
+}
+
 GPU_TEST("Generated models through the expression API match the exact-solver goldens")
 {
   char const* path = std::getenv("MIPLIB_TEST_MODELS");
@@ -313,44 +388,12 @@ GPU_TEST("Generated models through the expression API match the exact-solver gol
   in >> count;
   for (int t = 0; t < count; ++t)
   {
-    std::string label;
-    std::size_t n, m;
-    in >> label >> n >> m;
     Solver solver(B, false);
-    std::vector<Var> vars;
-    Expr objective;
-    for (std::size_t j = 0; j < n; ++j)
-    {
-      int type;
-      double lb, ub, cost;
-      in >> type >> lb >> ub >> cost;
-      vars.emplace_back(solver, static_cast<Var::Type>(type), lb, ub);
-      if (cost != 0) objective += cost * vars.back();
-    }
-    for (std::size_t i = 0; i < m; ++i)
-    {
-      std::string lo_s, hi_s;
-      std::size_t k;
-      in >> lo_s >> hi_s >> k;
-      Expr row;
-      for (std::size_t e = 0; e < k; ++e)
-      {
-        std::size_t col;
-        double val;
-        in >> col >> val;
-        row += val * vars[col];
-      }
-      bool const has_lo = lo_s != "-inf", has_hi = hi_s != "inf";
-      if (has_lo && has_hi && lo_s == hi_s) solver.add(row == std::stod(hi_s));
-      else
-      {
-        if (has_hi) solver.add(row <= std::stod(hi_s));
-        if (has_lo) solver.add(row >= std::stod(lo_s));
-      }
-    }
-    int maximize;
-    double expected, tol;
-    in >> maximize >> expected >> tol;
+    FixtureModel f = read_fixture_model(in, solver);
+    std::string const& label = f.label;
+    Expr const& objective = f.objective;
+    int const maximize = f.maximize;
+    double const expected = f.expected, tol = f.tol;
     double limit = 150;           // a runaway tree must fail the test, not hang it
     if (char const* t = std::getenv("MIPLIB_TEST_TIME_LIMIT")) limit = std::atof(t);
     solver.set_time_limit(limit);

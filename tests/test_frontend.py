@@ -61,6 +61,83 @@ def write_models(path, models):
             fh.write(f"{int(L.maximize)} {f(expected)} {tol}\n")
 
 
+def _read_mps_with_highs(path):
+    """The dumped model as HiGHS (an independent MPS reader) sees it."""
+    import scipy.optimize._highspy._core as core
+    import scipy.sparse as sp
+    h = core._Highs()
+    h.setOptionValue("output_flag", False)
+    assert h.readModel(str(path)) == core.HighsStatus.kOk
+    lp = h.getLp()
+    a = lp.a_matrix_
+    shape = (lp.num_row_, lp.num_col_)
+    if a.format_ == core.MatrixFormat.kColwise:
+        A = sp.csc_matrix((np.array(a.value_), np.array(a.index_), np.array(a.start_)), shape=shape).tocsr()
+    else:
+        A = sp.csr_matrix((np.array(a.value_), np.array(a.index_), np.array(a.start_)), shape=shape)
+    A.sort_indices()
+    inf = core.kHighsInf
+    clean = lambda v: np.where(np.array(v) >= inf, np.inf, np.where(np.array(v) <= -inf, -np.inf, np.array(v)))
+    integ = np.array([int(t) != 0 for t in lp.integrality_], bool) if len(lp.integrality_) else np.zeros(shape[1], bool)
+    return dict(h=h, A=A, c=np.array(lp.col_cost_), lb=clean(lp.col_lower_), ub=clean(lp.col_upper_),
+                lo=clean(lp.row_lower_), hi=clean(lp.row_upper_), integer=integ,
+                maximize=lp.sense_ == core.ObjSense.kMaximize)
+
+
+def test_lowering_through_the_expression_api_equals_the_generator(built, golden, tmp_path):
+    """Rows a5 - a10 of SURVEY.md section 8 without a device: the fixture models are built through
+    Var / Expr / Constr, lowered by the Cuda adapter and written with Solver::dump(); HiGHS reads
+    the MPS files back.  The lowered model must be the generator's model entry for entry (a `>=`
+    row may come back as the negated `<=` row, the reference's own convention,
+    miplib/constr.cpp:117-143), and HiGHS must find the golden optimum on it."""
+    models = [
+        ("C1_lp", gen.config(1), golden["C1_lp"]["objective"], 1e-6),
+        ("lp_300x500_s7", gen.lp(300, 500, 6, 7), golden["lp_300x500_s7"]["objective"], 1e-6),
+        ("setcover_200x500_mip", gen.set_cover(200, 500, 8, 20264), golden["setcover_200x500_mip"]["objective"], 1e-9),
+        ("mkp_5x60_mip", gen.mkp(5, 60, 4, 4, 20265), golden["mkp_5x60_mip"]["objective"], 1e-9),
+    ]
+    path = tmp_path / "models.txt"
+    write_models(path, models)
+    rc, out = run_unit_test(built, "--cpu-only", "--filter", "dumped as MPS",
+                            env={"MIPLIB_TEST_MODELS": str(path), "MIPLIB_TEST_DUMP_DIR": str(tmp_path)})
+    assert rc == 0 and "1 passed" in out, out
+
+    def upper_form(A, lo, hi):
+        """every one-sided row as `a x <= b` (a `>=` row negated), two-sided rows untouched"""
+        A = A.tocsr().copy()
+        flip = np.isfinite(lo) & ~np.isfinite(hi)
+        sign = np.where(flip, -1.0, 1.0)
+        A = A.multiply(sign[:, None]).tocsr()
+        A.sort_indices()
+        return A, np.where(flip, -hi, lo), np.where(flip, -lo, hi)
+
+    for label, L, expected, tol in models:
+        M = _read_mps_with_highs(tmp_path / f"{label}.mps")
+        assert M["A"].shape == (L.m, L.n), label
+        A0, lo0, hi0 = upper_form(L.A, L.row_lo, L.row_hi)
+        A1, lo1, hi1 = upper_form(M["A"], M["lo"], M["hi"])
+        assert np.array_equal(A0.indptr, A1.indptr) and np.array_equal(A0.indices, A1.indices), label
+        assert np.array_equal(A0.data, A1.data), label                  # 17 significant digits: exact
+        assert np.array_equal(lo0, lo1) and np.array_equal(hi0, hi1), label
+        assert np.array_equal(M["c"], L.c) and M["maximize"] == bool(L.maximize), label
+        assert np.array_equal(M["lb"], L.lb) and np.array_equal(M["ub"], L.ub), label
+        integer = L.integer if L.integer is not None else np.zeros(L.n, bool)
+        assert np.array_equal(M["integer"], integer), label
+        # and an exact solver finds the golden optimum on the dumped file
+        h = M["h"]
+        h.run()
+        obj = h.getInfo().objective_function_value
+        assert abs(obj - expected) <= max(tol, 1e-9) * (1 + abs(expected)), (label, obj, expected)
+        # the LP-format writer describes the same model
+        import scipy.optimize._highspy._core as core
+        h2 = core._Highs()
+        h2.setOptionValue("output_flag", False)
+        assert h2.readModel(str(tmp_path / f"{label}.lp")) == core.HighsStatus.kOk
+        h2.run()
+        obj2 = h2.getInfo().objective_function_value
+        assert abs(obj2 - expected) <= max(tol, 1e-9) * (1 + abs(expected)), (label, obj2, expected)
+
+
 @pytest.mark.gpu
 def test_kats_and_generated_models_on_gpu(built, golden, tmp_path):
     models = [
