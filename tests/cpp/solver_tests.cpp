@@ -302,7 +302,8 @@ GPU_TEST("Bulk CSR ingress: LP and MIP without Var / Expr objects (miplib/cuda/c
 
 // Replays oracle/gen.py's recipes through Var / Expr / Constr from a text fixture written by the
 // pytest wrapper (tests/test_frontend.py): "n m" / per column "type lb ub cost" / per row
-// "lo hi k (col val)*k" / "maximize expected_objective kind".
+// "lo hi k (col val)*k" / per indicator "zcol k col*k" = (z == 0) >> (sum of the k columns <= 0),
+// posted through Solver::add(IndicatorConstr) / "maximize expected_objective kind".
 namespace {
 
 struct FixtureModel
@@ -318,8 +319,8 @@ struct FixtureModel
 FixtureModel read_fixture_model(std::istream& in, Solver& solver)
 {
   FixtureModel f;
-  std::size_t n, m;
-  in >> f.label >> n >> m;
+  std::size_t n, m, indicators;
+  in >> f.label >> n >> m >> indicators;
   for (std::size_t j = 0; j < n; ++j)
   {
     int type;
@@ -348,6 +349,19 @@ FixtureModel read_fixture_model(std::istream& in, Solver& solver)
       if (has_hi) solver.add(row <= std::stod(hi_s));
       if (has_lo) solver.add(row >= std::stod(lo_s));
     }
+  }
+  for (std::size_t g = 0; g < indicators; ++g)
+  {
+    std::size_t zcol, k;
+    in >> zcol >> k;
+    Expr members;
+    for (std::size_t e = 0; e < k; ++e)
+    {
+      std::size_t col;
+      in >> col;
+      members += f.vars[col];
+    }
+    solver.add((f.vars[zcol] == 0) >> (members <= 0));   // reformulated by IndicatorConstr::reformulation()
   }
   in >> f.maximize >> f.expected >> f.tol;
   return f;

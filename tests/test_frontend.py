@@ -40,8 +40,12 @@ def test_libmiplib_exports_reference_capi(built):
         assert f" T {sym}" in out, sym
 
 
-def write_models(path, models):
-    """Text fixture read by tests/cpp/solver_tests.cpp ('Generated models ...')."""
+def write_models(path, models, indicator_rows=None):
+    """Text fixture read by tests/cpp/solver_tests.cpp ('Generated models ...').
+    indicator_rows: {label: G} - the LAST G rows of that model are big-M switch rows
+    `sum_{j in g} x_j - |g| z_g <= 0` (oracle/gen.py: mkp); they are written as indicator
+    constraints `(z_g == 0) >> (sum_{j in g} x_j <= 0)` instead, so that the C++ side posts them
+    through Solver::add(IndicatorConstr) and the adapter's reformulation has to recreate the rows."""
     def f(v):
         return "inf" if v == np.inf else "-inf" if v == -np.inf else repr(float(v))
     with open(path, "w") as fh:
@@ -49,15 +53,27 @@ def write_models(path, models):
         for label, L, expected, tol in models:
             A = L.A.tocsr()
             integer = L.integer if L.integer is not None else np.zeros(L.n, bool)
-            fh.write(f"{label} {L.n} {L.m}\n")
+            G = (indicator_rows or {}).get(label, 0)
+            switches = []
+            for i in range(L.m - G, L.m):
+                s, e = A.indptr[i], A.indptr[i + 1]
+                cols, vals = A.indices[s:e], A.data[s:e]
+                z = cols[vals < 0]
+                assert z.size == 1 and np.all(vals[vals > 0] == 1.0) and L.row_hi[i] == 0.0
+                assert -vals[vals < 0][0] == (vals > 0).sum()            # big-M = |group|
+                switches.append((int(z[0]), [int(c) for c in cols[vals > 0]]))
+            m_lin = L.m - G
+            fh.write(f"{label} {L.n} {m_lin} {G}\n")
             for j in range(L.n):
                 binary = integer[j] and L.lb[j] == 0 and L.ub[j] == 1
                 t = 1 if binary else 2 if integer[j] else 0
                 fh.write(f"{t} {f(L.lb[j])} {f(L.ub[j])} {f(L.c[j])}\n")
-            for i in range(L.m):
+            for i in range(m_lin):
                 s, e = A.indptr[i], A.indptr[i + 1]
                 terms = " ".join(f"{c} {f(v)}" for c, v in zip(A.indices[s:e], A.data[s:e]))
                 fh.write(f"{f(L.row_lo[i])} {f(L.row_hi[i])} {e - s} {terms}\n")
+            for z, members in switches:
+                fh.write(f"{z} {len(members)} " + " ".join(map(str, members)) + "\n")
             fh.write(f"{int(L.maximize)} {f(expected)} {tol}\n")
 
 
@@ -95,9 +111,14 @@ def test_lowering_through_the_expression_api_equals_the_generator(built, golden,
         ("lp_300x500_s7", gen.lp(300, 500, 6, 7), golden["lp_300x500_s7"]["objective"], 1e-6),
         ("setcover_200x500_mip", gen.set_cover(200, 500, 8, 20264), golden["setcover_200x500_mip"]["objective"], 1e-9),
         ("mkp_5x60_mip", gen.mkp(5, 60, 4, 4, 20265), golden["mkp_5x60_mip"]["objective"], 1e-9),
+        # the same recipe with its 4 switch rows posted as indicator constraints
+        # (z == 0) >> (sum x <= 0): IndicatorConstr::reformulation (reference miplib/constr.cpp:225-271)
+        # must give back exactly the generator's big-M rows
+        ("mkp_5x60_indicator", gen.mkp(5, 60, 4, 4, 20265), golden["mkp_5x60_mip"]["objective"], 1e-9),
+        ("mkp_8x80_indicator", gen.mkp(8, 80, 4, 4, 20265), golden["mkp_8x80_mip"]["objective"], 1e-9),
     ]
     path = tmp_path / "models.txt"
-    write_models(path, models)
+    write_models(path, models, indicator_rows={"mkp_5x60_indicator": 4, "mkp_8x80_indicator": 4})
     rc, out = run_unit_test(built, "--cpu-only", "--filter", "dumped as MPS",
                             env={"MIPLIB_TEST_MODELS": str(path), "MIPLIB_TEST_DUMP_DIR": str(tmp_path)})
     assert rc == 0 and "1 passed" in out, out
