@@ -85,7 +85,10 @@ void ExprImpl::add_scaled(ExprImpl const& other, double factor)
   }
   constant += factor * other.constant;
   if (factor == 0) return;
-  linear.reserve(linear.size() + other.linear.size());
+  // grow geometrically: an exact reserve here would reallocate on EVERY `objective += c * x`
+  // (2 M columns: quadratic; measured 7.7 s for 80 k terms)
+  if (linear.capacity() < linear.size() + other.linear.size())
+    linear.reserve(std::max(linear.size() + other.linear.size(), 2 * linear.capacity()));
   for (LinTerm const& t : other.linear) linear.push_back({t.var, factor * t.coef});
   for (QuadTerm const& t : other.quad) quad.push_back({t.first, t.second, factor * t.coef});
   if (!other.linear.empty() || !other.quad.empty()) canonical = false;
