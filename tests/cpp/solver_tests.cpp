@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <iostream>
 #include <fstream>
+#include <optional>
 #include <random>
 #include <string>
 
@@ -324,8 +325,12 @@ FixtureModel read_fixture_model(std::istream& in, Solver& solver)
   for (std::size_t j = 0; j < n; ++j)
   {
     int type;
-    double lb, ub, cost;
-    in >> type >> lb >> ub >> cost;
+    std::string lb_s, ub_s;       // "inf" / "-inf": no bound given, the API's std::nullopt
+    double cost;
+    in >> type >> lb_s >> ub_s >> cost;
+    std::optional<double> lb, ub;
+    if (lb_s != "-inf") lb = std::stod(lb_s);
+    if (ub_s != "inf") ub = std::stod(ub_s);
     f.vars.emplace_back(solver, static_cast<Var::Type>(type), lb, ub);
     if (cost != 0) f.objective += cost * f.vars.back();
   }

@@ -95,8 +95,14 @@ def _read_mps_with_highs(path):
     inf = core.kHighsInf
     clean = lambda v: np.where(np.array(v) >= inf, np.inf, np.where(np.array(v) <= -inf, -np.inf, np.array(v)))
     integ = np.array([int(t) != 0 for t in lp.integrality_], bool) if len(lp.integrality_) else np.zeros(shape[1], bool)
-    return dict(h=h, A=A, c=np.array(lp.col_cost_), lb=clean(lp.col_lower_), ub=clean(lp.col_upper_),
-                lo=clean(lp.row_lower_), hi=clean(lp.row_upper_), integer=integ,
+    # LP files order the columns by first appearance: put them back in creation order x0, x1, ...
+    names = list(lp.col_names_)
+    order = np.argsort([int(nm[1:]) for nm in names]) if names and all(nm[:1] == "x" and nm[1:].isdigit() for nm in names) \
+        else np.arange(shape[1])
+    A = A[:, order].tocsr()
+    A.sort_indices()
+    return dict(h=h, A=A, c=np.array(lp.col_cost_)[order], lb=clean(lp.col_lower_)[order], ub=clean(lp.col_upper_)[order],
+                lo=clean(lp.row_lower_), hi=clean(lp.row_upper_), integer=integ[order],
                 maximize=lp.sense_ == core.ObjSense.kMaximize)
 
 
@@ -157,6 +163,50 @@ def test_lowering_through_the_expression_api_equals_the_generator(built, golden,
         h2.run()
         obj2 = h2.getInfo().objective_function_value
         assert abs(obj2 - expected) <= max(tol, 1e-9) * (1 + abs(expected)), (label, obj2, expected)
+
+
+def test_dump_writers_keep_every_kind_of_bound_and_row(built, tmp_path):
+    """A small model with every column kind the API can express (free, one-sided, boxed, fixed,
+    negative bounds, integer, binary) and every row sense, lowered and dumped; both files, read by
+    HiGHS, must give back the model - and the same optimum from either file."""
+    import scipy.sparse as sp
+    inf = np.inf
+    lb = np.array([-inf, -inf, -3.0, 2.0, 0.0, 1.5, -4.0, 0.0])
+    ub = np.array([inf, 5.0, inf, 7.0, 1.0, 1.5, -1.0, 10.0])
+    integer = np.array([False, False, False, True, True, False, True, False])
+    c = np.array([1.0, -2.0, 0.5, 3.0, -1.0, 0.0, 2.0, -0.25])
+    A = sp.csr_matrix(np.array([
+        [1.0, 1.0, 0.0, 0.0, 2.0, 0.0, 0.0, 1.0],      # <=
+        [1.0, -1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0],     # >=
+        [0.0, 0.0, 1.0, 1.0, 0.0, 1.0, 1.0, 0.0],      # ==
+        [-1.0, 0.0, 0.0, 0.5, 0.0, 0.0, 0.0, 2.0],     # <= with a negative right-hand side
+        [0.0, 2.0, 0.0, 0.0, 0.0, 0.0, 1.0, 1.0],      # >= 0: no RHS line in the MPS file
+    ]))
+    row_lo = np.array([-inf, -2.0, 3.5, -inf, 0.0])
+    row_hi = np.array([8.0, inf, 3.5, -1.25, inf])
+    L = gen.LP(A, c, lb, ub, row_lo, row_hi, False, integer, "mixed")
+    path = tmp_path / "models.txt"
+    write_models(path, [("mixed", L, 0.0, 1e-9)])
+    rc, out = run_unit_test(built, "--cpu-only", "--filter", "dumped as MPS",
+                            env={"MIPLIB_TEST_MODELS": str(path), "MIPLIB_TEST_DUMP_DIR": str(tmp_path)})
+    assert rc == 0 and "1 passed" in out, out
+    objs = []
+    for ext in ("mps", "lp"):
+        M = _read_mps_with_highs(tmp_path / f"mixed.{ext}")
+        assert M["A"].shape == (L.m, L.n), ext
+        flip = np.isfinite(M["lo"]) & ~np.isfinite(M["hi"])            # `>=` rows may come back negated
+        dense = M["A"].toarray() * np.where(flip, -1.0, 1.0)[:, None]
+        lo = np.where(flip, -M["hi"], M["lo"]); hi = np.where(flip, -M["lo"], M["hi"])
+        flip0 = np.isfinite(row_lo) & ~np.isfinite(row_hi)
+        dense0 = A.toarray() * np.where(flip0, -1.0, 1.0)[:, None]
+        lo0 = np.where(flip0, -row_hi, row_lo); hi0 = np.where(flip0, -row_lo, row_hi)
+        assert np.array_equal(dense, dense0), ext
+        assert np.array_equal(lo, lo0) and np.array_equal(hi, hi0), ext
+        assert np.array_equal(M["c"], c) and np.array_equal(M["lb"], lb) and np.array_equal(M["ub"], ub), ext
+        assert np.array_equal(M["integer"], integer), ext
+        M["h"].run()
+        objs.append(M["h"].getInfo().objective_function_value)
+    assert abs(objs[0] - objs[1]) <= 1e-9 * (1 + abs(objs[0])), objs
 
 
 @pytest.mark.gpu
