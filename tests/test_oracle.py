@@ -109,7 +109,10 @@ def test_highs_pdlp_stand_in_agrees_with_highs_simplex(golden):
     r = highs_ref.solve_lp_pdlp(gen.config(1), 1e-6)
     assert r["status"] == "kOptimal"
     assert rel(r["obj"], golden["C1_lp"]["objective"]) <= 1e-6
-    assert golden["C2_lp"]["kind"].startswith("highs-pdlp") and golden["C2_lp"]["objective"] < 0
+    for key in ("C2_lp", "C3_lp"):
+        assert golden[key]["kind"].startswith("highs-pdlp") and golden[key]["objective"] < 0
+    # the value every B200 run of config 3 in this round printed (bench logs, all GPU counts)
+    assert rel(-692346.1453006756, golden["C3_lp"]["objective"]) <= 2e-6
 
 
 def test_golden_trace_reproduces():
