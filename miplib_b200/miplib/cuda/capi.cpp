@@ -39,6 +39,22 @@ int miplib_cuda_load_csr(miplib::Solver* p_solver, std::int64_t m, std::int64_t 
   });
 }
 
+int miplib_cuda_read_mps(miplib::Solver* p_solver, char const* path)
+{
+  return guarded([&] {
+    if (!path) throw std::logic_error("miplib_cuda_read_mps: null path");
+    miplib::CudaSolver::of(*p_solver).read_mps(*p_solver, path);
+  });
+}
+
+int miplib_cuda_dump(miplib::Solver* p_solver, char const* path)
+{
+  return guarded([&] {
+    if (!path) throw std::logic_error("miplib_cuda_dump: null path");
+    p_solver->dump(path);
+  });
+}
+
 int miplib_cuda_solve(miplib::Solver* p_solver, int* result, int* has_solution)
 {
   return guarded([&] {

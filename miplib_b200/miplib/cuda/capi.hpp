@@ -23,6 +23,13 @@ int miplib_cuda_load_csr(miplib::Solver* p_solver, std::int64_t m, std::int64_t 
                          std::int32_t const* var_type, double const* row_lo, double const* row_hi,
                          int maximize);
 
+// Reads a free-format MPS file into a Cuda-backend solver (appends its columns and rows, replaces
+// the objective): N / L / G / E rows, integer markers, RHS, RANGES, every BOUNDS type, OBJSENSE.
+int miplib_cuda_read_mps(miplib::Solver* p_solver, char const* path);
+
+// Solver::dump(): the lowered model as free-format MPS (*.mps) or CPLEX-LP text (*.lp).
+int miplib_cuda_dump(miplib::Solver* p_solver, char const* path);
+
 // Solver::solve(); *result receives Solver::Result as int, *has_solution 0 / 1.
 int miplib_cuda_solve(miplib::Solver* p_solver, int* result, int* has_solution);
 

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
@@ -290,9 +291,16 @@ void CudaSolver::dump(std::string const& filename) const
   };
   bool const as_mps = ends_with(".mps"), as_lp = ends_with(".lp");
   if (!as_mps && !as_lp) fail("Dumping Cuda backend models to this file type is not supported (use .mps or .lp).");
-  std::ofstream out(filename);
-  if (!out) fail("Cuda backend: cannot open " + filename + " for writing.");
-  out << std::setprecision(17);
+  // The text is assembled with snprintf and written with stdio: iostream NUMBER formatting
+  // (std::num_put) crashes inside CPython hosts that have loaded an extension with its own copy
+  // of the C++ runtime's locale tables (SciPy's does) - the reason bnb.cpp logs through stdio too.
+  std::string out;
+  auto num = [&](double v) {
+    char buf[40];
+    std::snprintf(buf, sizeof(buf), "%.17g", v);
+    out += buf;
+  };
+  auto idx = [&](std::size_t v) { out += std::to_string(v); };
   std::size_t const n = m_columns.size();
   auto col_name = [&](std::size_t j) {
     if (m_columns[j].name && m_columns[j].name->find(' ') == std::string::npos) return *m_columns[j].name;
@@ -306,97 +314,127 @@ void CudaSolver::dump(std::string const& filename) const
 
   if (as_mps)
   {
-    out << "NAME miplib_cuda\n";
-    if (m_sense == Solver::Sense::Maximize) out << "OBJSENSE\n    MAX\n";
-    out << "ROWS\n N obj\n";
+    out += "NAME miplib_cuda\n";
+    if (m_sense == Solver::Sense::Maximize) out += "OBJSENSE\n    MAX\n";
+    out += "ROWS\n N obj\n";
     for (std::size_t r : rows)
-      out << (m_row_lo[r] == m_row_hi[r] ? " E " : (m_row_hi[r] < inf ? " L " : " G ")) << "r" << r << "\n";
+    {
+      out += m_row_lo[r] == m_row_hi[r] ? " E r" : (m_row_hi[r] < inf ? " L r" : " G r");
+      idx(r);
+      out += "\n";
+    }
     // column-major pass over the row store
     std::vector<std::vector<std::pair<std::size_t, double>>> by_col(n);
     for (std::size_t r : rows)
       for (std::int64_t k = m_row_start[r]; k < m_row_start[r + 1]; ++k)
         by_col[m_row_idx[k]].push_back({r, m_row_val[k]});
-    out << "COLUMNS\n";
+    out += "COLUMNS\n";
     bool in_int = false;
     for (std::size_t j = 0; j < n; ++j)
     {
       bool const is_int = m_columns[j].type != Var::Type::Continuous;
       if (is_int != in_int)
       {
-        out << " MARKER 'MARKER' " << (is_int ? "'INTORG'" : "'INTEND'") << "\n";   // quoted: the MPS convention
+        out += is_int ? " MARKER 'MARKER' 'INTORG'\n" : " MARKER 'MARKER' 'INTEND'\n";   // quoted: the MPS convention
         in_int = is_int;
       }
-      out << " " << col_name(j) << " obj " << obj(j) << "\n";
-      for (auto const& [r, v] : by_col[j]) out << " " << col_name(j) << " r" << r << " " << v << "\n";
+      std::string const name = col_name(j);
+      out += " " + name + " obj ";
+      num(obj(j));
+      out += "\n";
+      for (auto const& [r, v] : by_col[j])
+      {
+        out += " " + name + " r";
+        idx(r);
+        out += " ";
+        num(v);
+        out += "\n";
+      }
     }
-    if (in_int) out << " MARKER 'MARKER' 'INTEND'\n";
-    out << "RHS\n";
+    if (in_int) out += " MARKER 'MARKER' 'INTEND'\n";
+    out += "RHS\n";
     for (std::size_t r : rows)
     {
       double const rhs = m_row_hi[r] < inf ? m_row_hi[r] : m_row_lo[r];
-      if (rhs != 0) out << " rhs r" << r << " " << rhs << "\n";
+      if (rhs != 0) { out += " rhs r"; idx(r); out += " "; num(rhs); out += "\n"; }
     }
-    out << "BOUNDS\n";
+    // two-sided rows (bulk ingress, read_mps): written as L rows with a range
+    bool ranges = false;
+    for (std::size_t r : rows)
+      if (m_row_lo[r] != m_row_hi[r] && m_row_hi[r] < inf && m_row_lo[r] > -inf)
+      {
+        if (!ranges) { out += "RANGES\n"; ranges = true; }
+        out += " rng r"; idx(r); out += " "; num(m_row_hi[r] - m_row_lo[r]); out += "\n";
+      }
+    out += "BOUNDS\n";
     for (std::size_t j = 0; j < n; ++j)
     {
       Column const& c = m_columns[j];
+      std::string const name = col_name(j);
       bool const lo_inf = c.lb <= -inf, hi_inf = c.ub >= inf;
-      if (lo_inf && hi_inf) out << " FR bnd " << col_name(j) << "\n";
+      if (lo_inf && hi_inf) out += " FR bnd " + name + "\n";
       else
       {
-        if (lo_inf) out << " MI bnd " << col_name(j) << "\n";
-        else if (c.lb != 0 || c.type != Var::Type::Continuous) out << " LO bnd " << col_name(j) << " " << c.lb << "\n";
-        if (!hi_inf) out << " UP bnd " << col_name(j) << " " << c.ub << "\n";
-        else if (c.type != Var::Type::Continuous) out << " PL bnd " << col_name(j) << "\n";
+        if (lo_inf) out += " MI bnd " + name + "\n";
+        else if (c.lb != 0 || c.type != Var::Type::Continuous) { out += " LO bnd " + name + " "; num(c.lb); out += "\n"; }
+        if (!hi_inf) { out += " UP bnd " + name + " "; num(c.ub); out += "\n"; }
+        else if (c.type != Var::Type::Continuous) out += " PL bnd " + name + "\n";
       }
     }
-    out << "ENDATA\n";
-    return;
+    out += "ENDATA\n";
   }
-
-  auto term = [&](double v, std::size_t j) {
-    out << (v < 0 ? " - " : " + ") << std::abs(v) << " " << col_name(j);
-  };
-  out << (m_sense == Solver::Sense::Maximize ? "Maximize\n obj:" : "Minimize\n obj:");
-  bool any = false;
-  for (std::size_t j = 0; j < n; ++j)
-    if (obj(j) != 0) { term(obj(j), j); any = true; }
-  if (!any && n) out << " 0 " << col_name(0);
-  out << "\nSubject To\n";
-  for (std::size_t r : rows)
+  else
   {
-    auto body = [&]() {
-      for (std::int64_t k = m_row_start[r]; k < m_row_start[r + 1]; ++k) term(m_row_val[k], m_row_idx[k]);
+    auto term = [&](double v, std::size_t j) {
+      out += v < 0 ? " - " : " + ";
+      num(std::abs(v));
+      out += " " + col_name(j);
     };
-    if (m_row_lo[r] == m_row_hi[r]) { out << " r" << r << ":"; body(); out << " = " << m_row_hi[r] << "\n"; }
-    else
+    out += m_sense == Solver::Sense::Maximize ? "Maximize\n obj:" : "Minimize\n obj:";
+    bool any = false;
+    for (std::size_t j = 0; j < n; ++j)
+      if (obj(j) != 0) { term(obj(j), j); any = true; }
+    if (!any && n) out += " 0 " + col_name(0);
+    out += "\nSubject To\n";
+    for (std::size_t r : rows)
     {
-      if (m_row_hi[r] < inf) { out << " r" << r << ":"; body(); out << " <= " << m_row_hi[r] << "\n"; }
-      if (m_row_lo[r] > -inf) { out << " r" << r << "_lo:"; body(); out << " >= " << m_row_lo[r] << "\n"; }
+      auto body = [&]() {
+        for (std::int64_t k = m_row_start[r]; k < m_row_start[r + 1]; ++k) term(m_row_val[k], m_row_idx[k]);
+      };
+      if (m_row_lo[r] == m_row_hi[r]) { out += " r"; idx(r); out += ":"; body(); out += " = "; num(m_row_hi[r]); out += "\n"; }
+      else
+      {
+        if (m_row_hi[r] < inf) { out += " r"; idx(r); out += ":"; body(); out += " <= "; num(m_row_hi[r]); out += "\n"; }
+        if (m_row_lo[r] > -inf) { out += " r"; idx(r); out += "_lo:"; body(); out += " >= "; num(m_row_lo[r]); out += "\n"; }
+      }
     }
+    out += "Bounds\n";
+    for (std::size_t j = 0; j < n; ++j)
+    {
+      Column const& c = m_columns[j];
+      if (c.lb <= -inf && c.ub >= inf) out += " " + col_name(j) + " free\n";
+      else
+      {
+        out += " ";
+        if (c.lb <= -inf) out += "-inf"; else num(c.lb);
+        out += " <= " + col_name(j) + " <= ";
+        if (c.ub >= inf) out += "+inf"; else num(c.ub);
+        out += "\n";
+      }
+    }
+    bool header = false;
+    for (std::size_t j = 0; j < n; ++j)
+      if (m_columns[j].type != Var::Type::Continuous)
+      {
+        if (!header) { out += "General\n"; header = true; }
+        out += " " + col_name(j) + "\n";
+      }
+    out += "End\n";
   }
-  out << "Bounds\n";
-  for (std::size_t j = 0; j < n; ++j)
-  {
-    Column const& c = m_columns[j];
-    if (c.lb <= -inf && c.ub >= inf) out << " " << col_name(j) << " free\n";
-    else
-    {
-      out << " ";
-      if (c.lb <= -inf) out << "-inf"; else out << c.lb;
-      out << " <= " << col_name(j) << " <= ";
-      if (c.ub >= inf) out << "+inf"; else out << c.ub;
-      out << "\n";
-    }
-  }
-  bool header = false;
-  for (std::size_t j = 0; j < n; ++j)
-    if (m_columns[j].type != Var::Type::Continuous)
-    {
-      if (!header) { out << "General\n"; header = true; }
-      out << " " << col_name(j) << "\n";
-    }
-  out << "End\n";
+  std::FILE* file = std::fopen(filename.c_str(), "w");
+  if (!file) fail("Cuda backend: cannot open " + filename + " for writing.");
+  bool const ok = std::fwrite(out.data(), 1, out.size(), file) == out.size();
+  if (std::fclose(file) != 0 || !ok) fail("Cuda backend: error writing " + filename + ".");
 }
 
 // ---- device side ---------------------------------------------------------------------------------

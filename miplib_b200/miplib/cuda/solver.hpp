@@ -84,6 +84,10 @@ struct CudaSolver : detail::ISolver
                 double const* ub, std::int32_t const* var_type, double const* row_lo,
                 double const* row_hi, bool maximize);
 
+  // Free-format MPS file -> n new columns and m new rows (mps.cpp); the counterpart of dump().
+  // Column names are kept (dump() writes them back), row names are not.
+  void read_mps(Solver const& solver, std::string const& path);
+
   // ---- model store (host) --------------------------------------------------------------------
   struct Column
   {

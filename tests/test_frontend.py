@@ -278,6 +278,146 @@ def test_bulk_ingress_builds_the_same_row_store(built):
     assert lib.miplib_destroy_solver(solver) == 0 and lib.miplib_destroy_solver(s2) == 0
 
 
+HAND_MPS = """NAME hand
+OBJSENSE
+    MAX
+ROWS
+ N cost
+ N ignored
+ L lim1
+ G lim2
+ E eq1
+ L rng1
+ G rng2
+ E rng3
+ E rng4
+COLUMNS
+ a cost 1.5 lim1 1
+ a lim2 2 eq1 1
+ a ignored 7
+ b cost -2 lim1 3
+ b rng1 1 rng2 -1
+ MARKER 'MARKER' 'INTORG'
+ i1 cost 1 eq1 2
+ i1 rng3 1
+ i2 lim2 1 rng4 4
+ MARKER 'MARKER' 'INTEND'
+ c lim1 -1 rng1 2.5
+ d cost 0.25 rng2 1
+ e rng3 -3 rng4 1
+ f lim2 1
+ g eq1 1 rng1 1
+ h cost -1 lim1 1
+RHS
+ rhs lim1 10 lim2 -4
+ rhs eq1 3 cost 99
+ rhs rng1 8 rng2 1
+ rhs rng3 2 rng4 -2
+RANGES
+ rng rng1 3 rng2 2.5
+ rng rng3 4 rng4 -1.5
+BOUNDS
+ UP bnd a 4
+ MI bnd b
+ UP bnd b -1
+ LO bnd c -2.5
+ UP bnd c 6
+ FX bnd d 1.25
+ FR bnd e
+ MI bnd f
+ UP bnd f 9
+ PL bnd g
+ BV bnd h
+ LI bnd i1 -3
+ UI bnd i1 5
+ UP bnd i2 12
+ENDATA
+"""
+
+
+def test_mps_reader_agrees_with_highs_reader(built, golden, tmp_path):
+    """miplib_cuda_read_mps (miplib/cuda/mps.cpp) against HiGHS' reader on a file with every
+    section and bound type, then a byte-for-byte dump -> read -> dump round trip of generated
+    models.  No device needed: reader, row store and writers are host code."""
+    lib, C = _front(built)
+    lib.miplib_cuda_read_mps.argtypes = [C.c_void_p, C.c_char_p]
+    lib.miplib_cuda_dump.argtypes = [C.c_void_p, C.c_char_p]
+    src = tmp_path / "hand.mps"
+    src.write_text(HAND_MPS)
+    solver = C.c_void_p()
+    assert lib.miplib_create_solver(C.byref(solver), 5) == 0
+    assert lib.miplib_cuda_read_mps(solver, str(src).encode()) == 0, lib.miplib_get_last_error()
+    n, m = C.c_int64(), C.c_int64()
+    assert lib.miplib_cuda_get_shape(solver, C.byref(n), C.byref(m)) == 0
+    assert (n.value, m.value) == (10, 7)
+    out = tmp_path / "hand_out.mps"
+    assert lib.miplib_cuda_dump(solver, str(out).encode()) == 0, lib.miplib_get_last_error()
+    assert lib.miplib_destroy_solver(solver) == 0
+    want, got = _read_mps_with_highs(src), _read_mps_with_highs(out)
+    assert got["maximize"] and want["maximize"]
+    assert np.array_equal(got["A"].toarray(), want["A"].toarray())
+    assert np.array_equal(got["c"], want["c"])
+    assert np.array_equal(got["lb"], want["lb"]) and np.array_equal(got["ub"], want["ub"])
+    assert np.array_equal(got["integer"], want["integer"])
+    assert np.array_equal(np.isfinite(got["lo"]), np.isfinite(want["lo"]))
+    assert np.array_equal(np.isfinite(got["hi"]), np.isfinite(want["hi"]))
+    fin = np.isfinite(want["lo"])
+    assert np.abs(got["lo"][fin] - want["lo"][fin]).max() <= 1e-12          # ranges are written as hi - lo
+    assert np.array_equal(got["hi"][np.isfinite(want["hi"])], want["hi"][np.isfinite(want["hi"])])
+    # what the file says, spelled out for the cases readers disagree on most often
+    assert want["lb"][1] == -np.inf and want["ub"][1] == -1
+    assert (want["lo"][3], want["hi"][3]) == (5.0, 8.0)               # L row with a range
+    assert (want["lo"][4], want["hi"][4]) == (1.0, 3.5)               # G row with a range
+    assert (want["lo"][5], want["hi"][5]) == (2.0, 6.0)               # E row, positive range
+    assert (want["lo"][6], want["hi"][6]) == (-3.5, -2.0)             # E row, negative range
+    for M in (want, got):                                             # and both describe the same optimum
+        M["h"].run()
+    # ... up to the objective constant (RHS of the objective row, -99 here), which the backend drops
+    # like the constant of set_objective (reference miplib/lpsolve/solver.cpp:70-73)
+    assert abs(want["h"].getInfo().objective_function_value + 99.0 - got["h"].getInfo().objective_function_value) <= 1e-9
+
+    # A negative UP bound on a column whose lower bound is still the default 0: lp_solve, SCIP,
+    # CPLEX and Gurobi (the reference's backends) move the lower bound to -inf; HiGHS keeps [0, -1]
+    # and warns.  The reader follows the reference's backends.
+    quirk = tmp_path / "quirk.mps"
+    quirk.write_text("NAME q\nROWS\n N obj\n L r0\nCOLUMNS\n x obj 1 r0 1\n y obj 1 r0 1\nRHS\n rhs r0 5\n"
+                     "BOUNDS\n UP bnd x -2\n LO bnd y 1\n UP bnd y 3\nENDATA\n")
+    s3 = C.c_void_p()
+    assert lib.miplib_create_solver(C.byref(s3), 5) == 0
+    assert lib.miplib_cuda_read_mps(s3, str(quirk).encode()) == 0, lib.miplib_get_last_error()
+    assert lib.miplib_cuda_dump(s3, str(tmp_path / "quirk_out.mps").encode()) == 0
+    assert lib.miplib_destroy_solver(s3) == 0
+    Q = _read_mps_with_highs(tmp_path / "quirk_out.mps")
+    assert list(Q["lb"]) == [-np.inf, 1.0] and list(Q["ub"]) == [-2.0, 3.0]
+    # malformed input is an error with the file position, not a crash
+    broken = tmp_path / "broken.mps"
+    broken.write_text("NAME b\nROWS\n N obj\n L r0\nCOLUMNS\n x obj 1 nosuchrow 1\nENDATA\n")
+    s4 = C.c_void_p()
+    assert lib.miplib_create_solver(C.byref(s4), 5) == 0
+    assert lib.miplib_cuda_read_mps(s4, str(broken).encode()) == 1
+    assert b"broken.mps:6" in lib.miplib_get_last_error() and b"nosuchrow" in lib.miplib_get_last_error()
+    assert lib.miplib_cuda_read_mps(s4, str(tmp_path / "missing.mps").encode()) == 1
+    assert lib.miplib_destroy_solver(s4) == 0
+
+    # generated models: expression API -> dump -> read_mps -> dump must reproduce the file
+    models = [("C1_lp", gen.config(1), 0.0, 1e-6),
+              ("setcover_200x500_mip", gen.set_cover(200, 500, 8, 20264), 0.0, 1e-9),
+              ("mkp_5x60_mip", gen.mkp(5, 60, 4, 4, 20265), 0.0, 1e-9)]
+    path = tmp_path / "models.txt"
+    write_models(path, models)
+    rc, text = run_unit_test(built, "--cpu-only", "--filter", "dumped as MPS",
+                             env={"MIPLIB_TEST_MODELS": str(path), "MIPLIB_TEST_DUMP_DIR": str(tmp_path)})
+    assert rc == 0 and "1 passed" in text, text
+    for label, L, _, _ in models:
+        s2 = C.c_void_p()
+        assert lib.miplib_create_solver(C.byref(s2), 5) == 0
+        assert lib.miplib_cuda_read_mps(s2, str(tmp_path / f"{label}.mps").encode()) == 0, lib.miplib_get_last_error()
+        again = tmp_path / f"{label}_again.mps"
+        assert lib.miplib_cuda_dump(s2, str(again).encode()) == 0
+        assert lib.miplib_destroy_solver(s2) == 0
+        assert again.read_text() == (tmp_path / f"{label}.mps").read_text(), label
+
+
 @pytest.mark.gpu
 def test_bulk_ingress_solves_lp_and_mip(built, golden):
     lib, C = _front(built)
