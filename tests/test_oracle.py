@@ -115,6 +115,43 @@ def test_highs_pdlp_stand_in_agrees_with_highs_simplex(golden):
     assert rel(-692346.1453006756, golden["C3_lp"]["objective"]) <= 2e-6
 
 
+def test_c_port_iterates_match_the_numpy_oracle_and_the_golden_trace():
+    """oracle/pdhg_port.c is what bench.py times as the CPU baseline / reference arm: its 10 and 64
+    raw iterations on config 1 must be the NumPy oracle's (and the committed golden trace's), for
+    one thread and for all of them (row / column sums are sequential per row: thread count must
+    not change a bit)."""
+    from pathlib import Path
+    from oracle import port
+    z = np.load(Path(__file__).parent / "golden" / "pdhg_trace_c1.npz")
+    L = gen.config(1)
+    S = pdhg_ref.prepare(L)
+    results = []
+    for threads in (1, 0):
+        if threads:
+            port.lib().port_set_threads(threads)
+        else:
+            port.use_all_threads()
+        st = port.PortState(S)
+        st.iterate(10)
+        x10, y10 = st.xbar.copy(), st.y.copy()
+        st.iterate(54)
+        results.append((x10, y10, st.xbar.copy(), st.y.copy()))
+        assert np.abs(x10 - z["xbar10"]).max() <= 1e-11 and np.abs(y10 - z["y10"]).max() <= 1e-11
+        assert np.abs(st.xbar - z["xbar64"]).max() <= 1e-10 and np.abs(st.y - z["y64"]).max() <= 1e-10
+    for a, b in zip(*results):
+        assert np.array_equal(a, b)
+    # and step by step against the NumPy restatement
+    st = port.PortState(S)
+    xbar, y, aty = st.xbar.copy(), st.y.copy(), st.aty.copy()
+    tau, sigma = S.eta / S.w0, S.eta * S.w0
+    for k in range(5):
+        a = (k + 1.0) / (k + 2.0)
+        yhat, y, _ = pdhg_ref.row_step(S, xbar, y, st.y0, sigma, a)
+        _, aty, _, xbar = pdhg_ref.col_step(S, yhat, xbar, st.x0, aty, st.aty0, tau, a)
+        st.iterate(1)
+        assert np.abs(st.xbar - xbar).max() <= 1e-13 and np.abs(st.y - y).max() <= 1e-13
+
+
 def test_golden_trace_reproduces():
     from pathlib import Path
     z = np.load(Path(__file__).parent / "golden" / "pdhg_trace_c1.npz")
