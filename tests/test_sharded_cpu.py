@@ -93,3 +93,101 @@ def test_sharded_oracle_world1_is_the_plain_oracle():
     r = pdhg_dist_ref.solve_sharded(L.A, L.c, L.lb, L.ub, L.row_lo, L.row_hi, pdhg_dist_ref.LocalComm())
     ref = pdhg_ref.solve(L)
     assert r["iters"] == ref["iters"] and abs(r["obj"] - ref["obj"]) <= 1e-12 * (1 + abs(ref["obj"]))
+
+
+# ---- 2-D (R x C) block partition: the layout DESIGN.md section 5.1 names next for 8 GPUs ---------
+class _ThreadWorld:
+    """In-process stand-in for all_gather_object: W threads meet at a barrier."""
+    def __init__(self, W):
+        import threading
+        self.slots = [None] * W
+        self.barrier = threading.Barrier(W)
+
+    def gather(self, rank, obj):
+        self.slots[rank] = obj
+        self.barrier.wait()
+        out = list(self.slots)
+        self.barrier.wait()
+        return out
+
+
+def _grid_shares(L, R, C, rank):
+    A = L.A.tocsr()
+    m, n = A.shape
+    r, c = divmod(rank, C)
+    r0, r1 = (m * r) // R, (m * (r + 1)) // R
+    c0, c1 = (n * c) // C, (n * (c + 1)) // C
+    return A[r0:r1, c0:c1], L.c[c0:c1], L.lb[c0:c1], L.ub[c0:c1], L.row_lo[r0:r1], L.row_hi[r0:r1]
+
+
+@pytest.mark.parametrize("R,C", [(2, 2), (2, 4)])
+def test_grid_partition_oracle_matches_single_process(R, C):
+    """Row step = partial product + reduce-scatter inside the row group + all-gather of yhat; column
+    step = the mirror image inside the column group.  Same decisions as the single-process oracle,
+    and the ingress per rank is the formula DESIGN.md quotes (half the block-owner exchange's at
+    2 x 4)."""
+    import threading
+    from oracle import kkt_verify
+    L = gen.lp(300, 500, 6, 7)
+    W = R * C
+    world = _ThreadWorld(W)
+    res = [None] * W
+
+    def work(rank):
+        comm = pdhg_dist_ref.GridComm(rank, R, C, lambda obj: world.gather(rank, obj))
+        try:
+            res[rank] = pdhg_dist_ref.solve_grid(*_grid_shares(L, R, C, rank), comm)
+        except BaseException as e:          # let the other threads out of the barrier
+            res[rank] = e
+            world.barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(W)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert all(isinstance(v, dict) for v in res), res
+    ref = pdhg_ref.solve(L)
+    assert {v["status"] for v in res} == {"optimal"}
+    assert {v["iters"] for v in res} == {ref["iters"]} and {v["restarts"] for v in res} == {ref["restarts"]}
+    assert abs(res[0]["obj"] - ref["obj"]) <= 1e-12 * (1 + abs(ref["obj"]))
+    for c in range(C):                       # the R ranks of a column group hold the same x, bit for bit
+        assert all(np.array_equal(res[c]["x_group"], res[r * C + c]["x_group"]) for r in range(R))
+    x = np.concatenate([res[c]["x_group"] for c in range(C)])
+    y = np.concatenate([res[r * C]["y_group"] for r in range(R)])
+    cert = kkt_verify.certificate(L, x, y)
+    assert max(cert["rel_primal_res"], cert["rel_dual_res"], cert["rel_gap"]) <= 1.05e-6
+    formula = 16 * ((C - 1) * L.m + (R - 1) * L.n) / (R * C)
+    owner = 8 * (L.m + L.n) * (W - 1) / W
+    assert formula <= res[0]["ingress_bytes_per_iter"] <= 1.03 * formula       # + the KKT pass, 1 in 64
+    if (R, C) == (2, 4):
+        assert res[0]["ingress_bytes_per_iter"] < 0.52 * owner
+
+
+def _grid_worker(rank, world, port, out):
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        L = gen.lp(300, 500, 6, 7)
+
+        def gather_world(obj):
+            got = [None] * world
+            dist.all_gather_object(got, obj)
+            return got
+        comm = pdhg_dist_ref.GridComm(rank, 1, world, gather_world)          # 1 x 2: column groups
+        r = pdhg_dist_ref.solve_grid(*_grid_shares(L, 1, world, rank), comm)
+        out[rank] = (r["status"], r["obj"], r["iters"], r["x_group"].copy(), r["y_group"].copy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grid_partition_oracle_world2_gloo():
+    world = 2
+    port = 29500 + np.random.default_rng().integers(0, 2000)
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_grid_worker, args=(world, int(port), out), nprocs=world, join=True)
+        res = dict(out)
+    ref = pdhg_ref.solve(gen.lp(300, 500, 6, 7))
+    assert res[0][0] == res[1][0] == "optimal" and res[0][2] == res[1][2] == ref["iters"]
+    assert abs(res[0][1] - ref["obj"]) <= 1e-12 * (1 + abs(ref["obj"]))
+    assert np.array_equal(res[0][4], res[1][4])                   # one row group: both hold the whole y
+    x = np.concatenate([res[0][3], res[1][3]])
+    assert np.abs(x - ref["x"]).max() <= 1e-9
