@@ -19,6 +19,14 @@ A "step" is ONE COMPLETE SOLVE of that LP from a zero start to 1e-6 relative KKT
   cpu_baseline   : the multi-core C/OpenMP port of the same iteration (oracle/pdhg_port.c) on the
                    same LP, a bounded number of iterations, on this box's host cores
 
+  parity         : the (x, y) of the last timed solve, y gathered across the ranks, checked on rank 0
+                   by the independent FP64 certificate verifier (oracle/kkt_verify.py) and against
+                   the golden objective; a failed check makes the run exit non-zero
+  nodes          : bounded secondary block (config 4): rounds of 128 branch-and-bound node LPs per
+                   GPU, dealt to the ranks with no collective; root LP certificate-checked
+  cpu_baseline_highs : N = 1 only - SciPy-HiGHS (the stand-in for the reference's SCIP / lp_solve
+                   backends) on config 1 to optimality and on the bench config under a time cap
+
 N > 1 (torchrun, one process per GPU): the same LP row-sharded across the ranks (strong scaling):
 every rank owns m/N rows of A; the K'y partial sums are combined by one NCCL all-reduce per
 iteration.  --impl reference: rank 0 times the CPU port; other ranks exit 0.
@@ -47,6 +55,72 @@ def workload_name(cfg: int) -> str:
     return {1: "C1: synthetic sparse LP 1k x 2k, 8 nnz/col",
             2: "C2: synthetic sparse LP 100k x 200k, 8 nnz/col",
             3: "C3: synthetic sparse LP 1M x 2M, 16 nnz/col (32M nnz), solved to 1e-6 rel. KKT"}[cfg]
+
+
+def config_dict(cfg: int, m: int, n: int, nnz: int) -> dict:
+    """Identical in the CUDA arm and the reference arm (the driver compares them)."""
+    return {"workload": workload_name(cfg), "m": int(m), "n": int(n), "nnz": int(nnz),
+            "l2": "inputs larger than L2 (no flush)" if nnz > 8e6 else "L2-resident working set"}
+
+
+GOLDEN_KEY = {1: "C1_lp", 2: "C2_lp", 3: "C3_lp"}
+
+
+def parity_block(L, cfg: int, x, y, reported_obj: float) -> dict:
+    """Independent certificate of the returned point (oracle/kkt_verify.py shares no code with the
+    CUDA path) + relative objective distance to the golden optimum of tests/golden/objectives.json
+    (C1: HiGHS simplex; C2 / C3: HiGHS' own PDLP at 1e-6, so 2e-6 is the agreement one can ask)."""
+    from oracle import kkt_verify
+    cert = kkt_verify.certificate(L, x, y)
+    golden = json.loads((ROOT / "tests" / "golden" / "objectives.json").read_text())[GOLDEN_KEY[cfg]]
+    rel_obj = abs(cert["primal_obj"] - golden["objective"]) / (1.0 + abs(golden["objective"]))
+    worst = max(cert["rel_primal_res"], cert["rel_dual_res"], cert["rel_gap"])
+    ok = bool(worst <= 1.05e-6 and rel_obj <= 2e-6 and
+              abs(cert["primal_obj"] - reported_obj) <= 1e-9 * (1.0 + abs(reported_obj)))
+    return {"checker": "oracle.kkt_verify.certificate on the gathered (x, y) of the last timed (end-to-end) solve",
+            "rel_primal_res": cert["rel_primal_res"], "rel_dual_res": cert["rel_dual_res"],
+            "rel_gap": cert["rel_gap"], "primal_obj": cert["primal_obj"], "dual_obj": cert["dual_obj"],
+            "max_bound_violation": cert["max_bound_violation"],
+            "golden_objective": golden["objective"], "golden_kind": golden["kind"],
+            "rel_objective_vs_golden": rel_obj, "tolerance": {"kkt": 1.05e-6, "objective": 2e-6}, "ok": ok}
+
+
+def cpu_baseline_highs(cfg: int, cap_s: float = 60.0) -> dict:
+    """SciPy-HiGHS on the host cores as the stand-in for the reference's SCIP / lp_solve
+    backends (SCIPsolve reference miplib/scip/solver.cpp:370, ::solve miplib/lpsolve/solver.cpp:156 -
+    not installable offline).  Config 1 to optimality; the bench config in a child process under a
+    hard wall-clock cap (HiGHS' own time limit is not checked inside presolve / factorisation)."""
+    import scipy
+    from oracle import gen, highs_ref
+    out = {"label": "HiGHS stand-in for the reference's SCIP/lp_solve backend (not installable offline)",
+           "scipy": scipy.__version__, "host_cores": os.cpu_count()}
+    L1 = gen.config(1)
+    for method in ("highs-ds", "highs-ipm"):
+        t0 = time.perf_counter()
+        r = highs_ref.solve_lp(L1, method)
+        out[f"C1_{method}"] = {"status": r["status"], "objective": r["obj"], "iterations": r["nit"],
+                               "seconds": time.perf_counter() - t0}
+    if cfg != 1:
+        code = ("import sys, time; sys.path.insert(0, %r)\n"
+                "from oracle import gen, highs_ref\n"
+                "L = gen.config(%d); t0 = time.perf_counter()\n"
+                "r = highs_ref.solve_lp(L, 'highs-ipm', time_limit=%f)\n"
+                "print('HIGHS', r['status'], r['obj'], time.perf_counter() - t0)\n") % (str(ROOT), cfg, cap_s)
+        t0 = time.perf_counter()
+        try:
+            pr = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                                timeout=cap_s + 45.0)   # generation + model copy ride on top of the cap
+            tail = [ln for ln in pr.stdout.splitlines() if ln.startswith("HIGHS")]
+            if tail and tail[-1].split()[1] == "0":
+                f = tail[-1].split()
+                out[f"C{cfg}_highs-ipm"] = {"status": 0, "objective": float(f[2]), "seconds": float(f[3])}
+            else:
+                out[f"C{cfg}_highs-ipm"] = {"status": "did not finish", "cap_seconds": cap_s,
+                                           "detail": (tail[-1] if tail else pr.stderr[-200:])}
+        except subprocess.TimeoutExpired:
+            out[f"C{cfg}_highs-ipm"] = {"status": "did not finish", "cap_seconds": cap_s,
+                                       "detail": f"killed after {time.perf_counter() - t0:.0f} s wall"}
+    return out
 
 
 class ClockSampler:
@@ -180,7 +254,7 @@ def run_reference(args, rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args.config), "m": L.m, "n": L.n, "nnz": L.nnz},
+        "config": config_dict(args.config, L.m, L.n, L.nnz),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference's own SCIP / lp_solve backends are not installable offline; this arm "
@@ -268,85 +342,184 @@ def run_cuda(args, rank, world, local_rank):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_iters = sum(s.iterations for s in e2e_stats)
 
-    if rank != 0:
-        return
+    # ---- parity of the last timed solve: gather y (row blocks) on rank 0, certificate there -------
+    eng_x = eng.x()
+    y_loc = eng.y()
+    if dist is not None:
+        sizes = [sharding.row_block(m, r, world) for r in range(world)]
+        pad = max(b - a for a, b in sizes)
+        mine = torch.zeros(pad, dtype=torch.float64, device="cuda")
+        mine[:y_loc.size] = torch.from_numpy(y_loc).cuda()
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        y_all = np.concatenate([p[:b - a].cpu().numpy() for p, (a, b) in zip(parts, sizes)])
+    else:
+        y_all = y_loc
+    exchange = int(eng.get_param("shard_exchange")) if world > 1 else None
+    multicast = int(eng.get_param("multicast")) if world > 1 else None
     last = stats[-1]
     peak, peak_src = measured_peak_gbs()
     row_us = float(np.mean([s.row_kernel_us for s in stats]))
     col_us = float(np.mean([s.col_kernel_us for s in stats]))
-    if row_us <= 0:   # graph mode (small configs): time the kernels with the hook instead
-        row_us, _ = eng.time_kernel(2, 50, True)
-        col_us, _ = eng.time_kernel(3, 50, True)
+    spmv = {}
+    if rank == 0:
+        if row_us <= 0:   # graph mode (small configs): time the kernels with the hook instead
+            row_us, _ = eng.time_kernel(2, 50, True)
+            col_us, _ = eng.time_kernel(3, 50, True)
+        if world == 1:
+            # the two plain products (B_Ax / B_ATy over >= 100 repetitions, CUDA events on
+            # the library's stream through the mipcu_time_kernel hook); after the timed solves
+            for which, name in ((0, "Ax"), (1, "ATy")):
+                us, nbytes = eng.time_kernel(which, 100, False)
+                spmv[name] = {"launch_us": us, "bytes": int(nbytes), "GBps": nbytes / us / 1e3,
+                              "frac_of_peak": nbytes / us / 1e3 / peak}
+    barrier()
+    eng.close()
+
+    # ---- N = 1: the same end-to-end step through the reference-facing plugin call -----------------
+    plugin = None
+    if world == 1:
+        plugin = plugin_e2e(args, L, A, host)
+
+    # ---- bounded secondary block: node LPs of config 4 dealt across the ranks ---------------------
+    nodes = None
+    if not args.no_nodes:
+        nodes = nodes_block(4, args.nodes_per_gpu, steps=2, warmup=1, rank=rank, world=world,
+                            local_rank=local_rank, dist=dist)
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    parity = parity_block(L, args.config, eng_x, y_all, e2e_stats[-1].primal_obj)
     kernels = {"k_row_step": (row_us, last.row_kernel_bytes), "k_col_step": (col_us, last.col_kernel_bytes)}
     dom = max(kernels, key=lambda k: kernels[k][0])
     dom_us, dom_bytes = kernels[dom]
     achieved = dom_bytes / dom_us / 1e3
+    e2e = {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "seconds_per_solve": e2e_s / args.steps,
+           "through": "C ABI (include/mipcu.h): mipcu_load_lp + mipcu_solve_lp + mipcu_get_x / get_y, host buffers"}
+    if plugin is not None:
+        # headline e2e at N = 1 is the plugin call; the C-ABI figure stays beside it
+        e2e = dict(plugin, c_abi=e2e)
     line = {
         "metric": METRIC, "value": iters / resident_s, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * resident_s / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args.config), "m": m, "n": n, "nnz": int(A.nnz),
-                   "l2": "inputs larger than L2 (no flush)" if A.nnz > 8e6 else "L2-resident working set",
+        "config": config_dict(args.config, m, n, int(A.nnz)),
+        "layout": {"matrix_format": "SELL-32-256, one lane per row (CSR lanes-per-row kernels for long-row models)",
                    "parallelism": "single GPU" if world == 1 else
                    f"row-sharded x{world}, " + {
                        2: "block-owner exchange: each rank streams its row block of K and its column block of K', "
                           "yhat / xbar slices pushed into peer memory over NVLink from the kernels' epilogues",
                        1: "fused P2P reduce-scatter + primal step + all-gather kernel over NVLink",
-                       0: "NCCL all-reduce of K'y"}[int(eng.get_param("shard_exchange"))]},
+                       0: "NCCL all-reduce of K'y"}[exchange],
+                   "multicast": multicast},
         "time_to_tol_s": resident_s / args.steps,
         "iterations_per_solve": iters / args.steps,
         "device_iter_seconds_per_solve": dev_iter_s / args.steps,
         "kkt": {"rel_primal_res": last.rel_primal_res, "rel_dual_res": last.rel_dual_res,
                 "rel_gap": last.rel_gap, "status": last.status, "primal_obj": last.primal_obj},
-        "e2e": {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "seconds_per_solve": e2e_s / args.steps},
+        "parity": parity,
+        "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
                      "peak_source": peak_src, "traffic": ncu_traffic(dom) if world == 1 else None,
                      "algorithmic_bytes_per_launch": int(dom_bytes), "launch_us": dom_us,
-                     "all_kernels": {k: {"launch_us": v[0], "bytes": int(v[1]), "GBps": v[1] / v[0] / 1e3}
+                     "all_kernels": {k: {"launch_us": v[0], "bytes": int(v[1]), "GBps": v[1] / v[0] / 1e3,
+                                         "frac": v[1] / v[0] / 1e3 / peak}
                                      for k, v in kernels.items()}},
     }
-    line["config"]["matrix_format"] = "SELL-32-256, one lane per row (CSR lanes-per-row kernels for long-row models)"
     if world > 1:
-        line["roofline"]["col_step_split_us"] = {
-            "partial_spmv": float(np.mean([s.col_partial_us for s in stats])),
-            "exchange_and_primal": float(np.mean([s.col_exchange_us for s in stats]))}
-    if world == 1:
-        # the two plain products (B_Ax / B_ATy over >= 100 repetitions, CUDA events on
-        # the library's stream through the mipcu_time_kernel hook); after the timed solves
-        spmv = {}
-        for which, name in ((0, "Ax"), (1, "ATy")):
-            us, nbytes = eng.time_kernel(which, 100, False)
-            spmv[name] = {"launch_us": us, "bytes": int(nbytes), "GBps": nbytes / us / 1e3,
-                          "frac_of_peak": nbytes / us / 1e3 / peak}
+        it_us = 1e6 * dev_iter_s / max(1, iters)
+        line["roofline"]["iteration_split_us"] = {
+            "iteration": it_us, "row_step_kernel": row_us, "col_step_kernel": col_us,
+            "other (controller, KKT pass, launch gaps)": it_us - row_us - col_us,
+            "row_step_wait": float(np.mean([s.col_partial_us for s in stats])),
+            "col_step_wait": float(np.mean([s.col_exchange_us for s in stats])),
+            "note": "kernel times include the entry barrier and the pushes of the slice; *_wait = mean time "
+                    "CTA 0 spent in the cross-GPU entry barrier (device clock), 0 when not sampled"}
+    if spmv:
         line["spmv"] = spmv
+    if nodes is not None:
+        line["nodes"] = nodes
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(L)
+        line["cpu_baseline_highs"] = cpu_baseline_highs(args.config, args.highs_cap)
     print(json.dumps(line), flush=True)
-    eng.close()
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
+    if not parity["ok"] or (nodes is not None and not nodes.get("ok", True)):
+        print("bench.py: PARITY CHECK FAILED", json.dumps(parity), file=sys.stderr, flush=True)
+        sys.exit(3)
 
 
-def run_nodes(args, rank, world, local_rank):
-    """Secondary workload (configs 4 / 5): rounds of branch-and-bound node LP relaxations that share
-    the matrix, 128 nodes per GPU per round, dealt to the ranks with no device-side exchange (weak
-    scaling).  A step = one round on every rank.  `python bench.py --workload nodes --config 4`."""
+def plugin_e2e(args, L, A, host) -> dict:
+    """One end-to-end step = what a user of the reference's API runs: miplib_create_solver(Cuda) ->
+    miplib_cuda_load_csr (bulk ingress, host buffers) -> Solver::solve() -> values of all columns,
+    all inside the timed region (libmiplib.so, the C++ front-end + Backend::Cuda adapter)."""
+    import ctypes as C
+    from miplib_b200 import build
+    lib = C.CDLL(str(build.FRONT_LIB))
+    lib.miplib_get_last_error.restype = C.c_char_p
+    lib.miplib_cuda_load_csr.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 9 + [C.c_int]
+    n = A.shape[1]
+    lo = pinned_like(np.maximum(host["row_lo"], -1e30))
+    hi = pinned_like(np.minimum(host["row_hi"], 1e30))
+    x = pinned_like(np.zeros(n))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def step():
+        solver = C.c_void_p()
+        if lib.miplib_create_solver(C.byref(solver), 5):
+            raise RuntimeError(lib.miplib_get_last_error().decode())
+        try:
+            lib.miplib_cuda_set_verbose(solver, 0)
+            rc = lib.miplib_cuda_load_csr(solver, A.shape[0], n, vp(host["indptr"]), vp(host["indices"]),
+                                          vp(host["data"]), vp(host["c"]), vp(host["lb"]), vp(host["ub"]),
+                                          None, vp(lo), vp(hi), int(L.maximize))
+            res, has = C.c_int(), C.c_int()
+            rc = rc or lib.miplib_cuda_solve(solver, C.byref(res), C.byref(has))
+            obj = C.c_double()
+            rc = rc or lib.miplib_cuda_get_values(solver, vp(x), C.byref(obj))
+            if rc:
+                raise RuntimeError(lib.miplib_get_last_error().decode())
+            it = C.c_int64()
+            lib.miplib_cuda_get_info(solver, C.byref(it), None, None, None)
+            return res.value, obj.value, it.value
+        finally:
+            lib.miplib_destroy_solver(solver)
+
+    import torch
+    step()                                       # warm-up of the whole path
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    outs = [step() for _ in range(args.steps)]
+    secs = time.perf_counter() - t0
+    iters = sum(o[2] for o in outs)
+    h2d = sum(host[k].nbytes for k in ("indptr", "indices", "data", "c", "lb", "ub")) + lo.nbytes + hi.nbytes
+    return {"value": iters / secs, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(8 * n),
+            "seconds_per_solve": secs / args.steps, "result": outs[-1][0], "objective": outs[-1][1],
+            "through": "plugin: miplib_create_solver(Cuda) + miplib_cuda_load_csr + Solver::solve() + values "
+                       "(libmiplib.so; host buffers, a fresh solver every step)"}
+
+
+def nodes_block(cfg, per_gpu, steps, warmup, rank, world, local_rank, dist) -> dict | None:
+    """Rounds of branch-and-bound node LP relaxations that share the matrix (configs 4 / 5), `per_gpu`
+    nodes per GPU per round, dealt to the ranks with no device-side exchange (weak scaling).  A step =
+    one round on every rank.  Node 0 of rank 0 is the root relaxation: its (x) is certificate-checked
+    (primal residual, bounds) and its objective compared with the weak-duality bracket of the certificate.
+    Returns the result dict on rank 0, None elsewhere."""
     import torch
     from miplib_b200 import Engine
     from oracle import gen, kkt_verify
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
-    L = gen.config(args.config)
-    per_gpu = args.nodes_per_gpu
-    depth = 12 if args.config == 4 else 30                       # binaries fixed per node
+    L = gen.config(cfg)
+    depth = 12 if cfg == 4 else 30                       # binaries fixed per node
     rng = np.random.default_rng(1000 + rank)
 
     def boxes():
@@ -355,7 +528,7 @@ def run_nodes(args, rank, world, local_rank):
             if rank == 0 and b == 0:
                 continue                                           # node 0 of rank 0 is the root
             cols = rng.choice(L.n, depth, replace=False)
-            vals = (rng.random(depth) < (0.5 if args.config == 4 else 0.1)).astype(float)
+            vals = (rng.random(depth) < (0.5 if cfg == 4 else 0.1)).astype(float)
             lb[b, cols] = vals; ub[b, cols] = vals
         return lb, ub
 
@@ -368,9 +541,9 @@ def run_nodes(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         eng.solve_batch(*boxes(), want_x=False)
-    rounds = [boxes() for _ in range(args.steps)]
+    rounds = [boxes() for _ in range(steps)]
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -389,26 +562,62 @@ def run_nodes(args, rank, world, local_rank):
         t = torch.tensor([float(solved)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t)
         solved = int(t.item())
+    batch_stats = eng.batch_kernel_stats() if hasattr(eng, "batch_kernel_stats") else None
+    eng.close()
     if rank != 0:
-        return
+        return None
     st0, x0 = results[0]
     root = st0[0]
     iters = [s.iterations for st, _ in results for s in st]
-    line = {
-        "metric": "node_lps_per_s", "value": per_gpu * world * args.steps / secs, "unit": "node LP/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+    # root relaxation: independent check of the returned point
+    xr = x0[0]
+    ax = L.A @ xr
+    row_viol = np.maximum(L.row_lo - ax, 0.0) + np.maximum(ax - L.row_hi, 0.0)
+    b = np.maximum(np.where(np.isfinite(L.row_lo), np.abs(L.row_lo), 0.0),
+                   np.where(np.isfinite(L.row_hi), np.abs(L.row_hi), 0.0))
+    rel_p = float(np.linalg.norm(row_viol) / (1.0 + np.linalg.norm(b)))
+    pobj = float(L.c @ xr)
+    ok = bool(root.status == "optimal" and rel_p <= 1.05e-6 and
+              abs(pobj - root.primal_obj) <= 1e-9 * (1 + abs(pobj)) and
+              abs(root.primal_obj - root.dual_obj) <= 1.05e-6 * (1 + abs(root.primal_obj) + abs(root.dual_obj)) and
+              float(np.maximum(L.lb - xr, xr - L.ub).max()) <= 1e-9)
+    out = {
+        "metric": "node_lps_per_s", "value": per_gpu * world * steps / secs, "unit": "node LP/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * secs / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C{args.config}: node LP relaxations of the synthetic "
-                               f"{'set-cover' if args.config == 4 else 'multi-dimensional knapsack'} MIP "
+        "config": {"workload": f"C{cfg}: node LP relaxations of the synthetic "
+                               f"{'set-cover' if cfg == 4 else 'multi-dimensional knapsack'} MIP "
                                f"({L.m} x {L.n}), {per_gpu} nodes per GPU per round, {depth} binaries fixed per node",
                    "parallelism": "nodes dealt to GPUs, no collective"},
-        "node_lps_decided": solved, "node_lps_total": per_gpu * world * args.steps,
+        "node_lps_decided": solved, "node_lps_total": per_gpu * world * steps,
         "iterations_mean": float(np.mean(iters)), "iterations_max": int(np.max(iters)),
-        "root_lp": {"status": root.status, "objective": root.primal_obj, "rel_primal_res": root.rel_primal_res,
-                    "rel_gap": root.rel_gap},
+        "root_lp": {"status": root.status, "objective": root.primal_obj, "dual_objective": root.dual_obj,
+                    "rel_primal_res": root.rel_primal_res, "rel_gap": root.rel_gap,
+                    "verified_rel_primal_res": rel_p, "verified_objective": pobj},
+        "ok": ok,
         "gpu_launches": int(sum(st[0].kernel_launches for st, _ in results)), "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    if batch_stats:
+        out["roofline"] = batch_stats
+    return out
+
+
+def run_nodes(args, rank, world, local_rank):
+    """`python bench.py --workload nodes --config 4|5`: the node-LP block as the whole run."""
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    line = nodes_block(args.config, args.nodes_per_gpu, args.steps, args.warmup, rank, world, local_rank, dist)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0 and not line["ok"]:
+        sys.exit(3)
 
 
 def main():
@@ -421,6 +630,9 @@ def main():
     ap.add_argument("--workload", default="lp", choices=["lp", "nodes"])
     ap.add_argument("--nodes-per-gpu", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-nodes", action="store_true", help="skip the bounded config-4 node-LP block")
+    ap.add_argument("--highs-cap", type=float, default=60.0,
+                    help="wall-clock cap (s) of the HiGHS stand-in on the bench config (N = 1)")
     ap.add_argument("--shard-exchange", type=int, default=2, choices=[0, 1, 2],
                     help="N > 1: 2 = block-owner exchange (row block of K + column block of K' per rank), "
                          "1 = fused P2P reduce-scatter / primal step / all-gather kernel, 0 = ncclAllReduce")

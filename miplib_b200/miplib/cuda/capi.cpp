@@ -75,6 +75,23 @@ int miplib_cuda_get_values(miplib::Solver* p_solver, double* x, double* objectiv
   });
 }
 
+int miplib_cuda_get_info(miplib::Solver* p_solver, std::int64_t* lp_iterations, std::int64_t* kernel_launches,
+                         std::int64_t* nodes, double* seconds)
+{
+  return guarded([&] {
+    miplib::CudaSolver const& s = miplib::CudaSolver::of(*p_solver);
+    if (lp_iterations) *lp_iterations = s.m_info.lp_iterations;
+    if (kernel_launches) *kernel_launches = s.m_info.kernel_launches;
+    if (nodes) *nodes = s.m_info.nodes;
+    if (seconds) *seconds = s.m_info.seconds;
+  });
+}
+
+int miplib_cuda_set_verbose(miplib::Solver* p_solver, int verbose)
+{
+  return guarded([&] { miplib::CudaSolver::of(*p_solver).set_verbose(verbose != 0); });
+}
+
 int miplib_cuda_get_shape(miplib::Solver* p_solver, std::int64_t* n, std::int64_t* m)
 {
   return guarded([&] {

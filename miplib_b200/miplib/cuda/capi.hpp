@@ -36,6 +36,15 @@ int miplib_cuda_solve(miplib::Solver* p_solver, int* result, int* has_solution);
 // Values of ALL columns in creation order (x may be NULL) and the objective value.
 int miplib_cuda_get_values(miplib::Solver* p_solver, double* x, double* objective);
 
+// Statistics of the last solve: PDHG iterations over all LP solves, kernels launched, branch-and-
+// bound nodes, wall seconds inside Solver::solve().  Any pointer may be NULL.
+int miplib_cuda_get_info(miplib::Solver* p_solver, std::int64_t* lp_iterations, std::int64_t* kernel_launches,
+                         std::int64_t* nodes, double* seconds);
+
+// The reference's C API always creates verbose solvers (miplib/capi.cpp:58-63 -> Solver's default
+// second argument, miplib/solver.hpp:34); this turns the backend's iteration log on / off.
+int miplib_cuda_set_verbose(miplib::Solver* p_solver, int verbose);
+
 // Number of columns / alive rows of the lowered model.
 int miplib_cuda_get_shape(miplib::Solver* p_solver, std::int64_t* n, std::int64_t* m);
 

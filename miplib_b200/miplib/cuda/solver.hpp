@@ -134,6 +134,7 @@ struct CudaSolver : detail::ISolver
 
   void column_bounds_changed(std::size_t column);
   void hint(std::size_t column, double value);   // IVar::set_hint: start value of one column
+  void set_verbose(bool verbose) { m_verbose = verbose; }
 
   private:
   friend struct CudaBranchAndBound;

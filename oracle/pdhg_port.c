@@ -37,6 +37,24 @@ void port_set_threads(int n) {
 #endif
 }
 
+/* NUMA first touch: the destination arrays come from np.empty (untouched pages); every thread
+ * writes the rows / entries it will later stream under the same static schedule, so on a
+ * multi-socket host each page lands on the socket that uses it. */
+void port_touch_copy_csr(int64_t nrows, const int64_t* ptr, const int32_t* idx, const double* val,
+                         int64_t* ptr_out, int32_t* idx_out, double* val_out) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < nrows; ++i) {
+    ptr_out[i] = ptr[i];
+    if (i == nrows - 1) ptr_out[nrows] = ptr[nrows];
+    for (int64_t k = ptr[i]; k < ptr[i + 1]; ++k) { idx_out[k] = idx[k]; val_out[k] = val[k]; }
+  }
+}
+
+void port_touch_copy_vec(int64_t n, const double* src, double* dst) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) dst[i] = src[i];
+}
+
 void port_spmv(int64_t nrows, const int64_t* ptr, const int32_t* idx, const double* val,
                const double* v, double* out) {
 #pragma omp parallel for schedule(static)

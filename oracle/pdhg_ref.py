@@ -16,8 +16,9 @@ et al. 2021; r2HPDHG: Lu & Yang 2024).  It is written operation-for-operation li
 kernels in ``miplib_b200/csrc`` so that kernel-level and iterate-level parity can be checked.
 
 PARITY PINNING.  The reference holds no golden vector beyond 3x3 toy models
-(test/unit/expr.cpp:134-149, :201-216, test/unit/solver.cpp:29-65); those are pinned in
-tests/golden/kats.json.  At BASELINE.json sizes this oracle is pinned against SciPy-HiGHS
+(test/unit/expr.cpp:134-149, :201-216, test/unit/solver.cpp:29-65); those known-answer tests
+are re-hosted assertion for assertion in tests/cpp/frontend_tests.cpp and tests/cpp/solver_tests.cpp
+(cases "KAT-A" .. "KAT-D"), run by tests/test_frontend.py.  At BASELINE.json sizes this oracle is pinned against SciPy-HiGHS
 optimal objectives (``highs_ref.py``, golden values in tests/golden/objectives.json) - a
 stand-in for SCIP/lp_solve, which cannot be installed offline: "parity unpinned" against the
 reference's own backends, pinned against an independent exact solver.

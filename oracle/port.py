@@ -37,6 +37,10 @@ def lib():
         L.port_num_threads.restype = C.c_int
         L.port_set_threads.argtypes = [C.c_int]
         L.port_set_threads.restype = None
+        L.port_touch_copy_csr.argtypes = [i64] + [vp] * 6
+        L.port_touch_copy_csr.restype = None
+        L.port_touch_copy_vec.argtypes = [i64, vp, vp]
+        L.port_touch_copy_vec.restype = None
         L.port_spmv.argtypes = [i64, vp, vp, vp, vp, vp]
         L.port_spmv.restype = None
         L.port_row_step.argtypes = [i64] + [vp] * 9 + [dbl, dbl]
@@ -69,20 +73,42 @@ class PortState:
     def __init__(self, S: pdhg_ref.Scaled):
         self.S = S
         K, KT = S.K, S.KT
-        self.rp, self.ri, self.rv = K.indptr.astype(np.int64), K.indices.astype(np.int32), K.data.astype(np.float64)
-        self.cp, self.ci, self.cv = KT.indptr.astype(np.int64), KT.indices.astype(np.int32), KT.data.astype(np.float64)
+        self.rp, self.ri, self.rv = self._touch_csr(K)
+        self.cp, self.ci, self.cv = self._touch_csr(KT)
         self.m, self.n = K.shape
         n, m = self.n, self.m
-        self.x0 = np.clip(np.zeros(n), S.l, S.u)
-        self.y0 = np.zeros(m)
-        self.aty0 = np.zeros(n)
-        self.aty = np.zeros(n)
-        self.y = np.zeros(m)
-        self.yhat = np.zeros(m)
+        tv = self._touch_vec
+        self.x0 = tv(np.clip(np.zeros(n), S.l, S.u))
+        self.y0 = tv(np.zeros(m))
+        self.aty0 = tv(np.zeros(n))
+        self.aty = tv(np.zeros(n))
+        self.y = tv(np.zeros(m))
+        self.yhat = tv(np.zeros(m))
+        # the constant vectors the two passes read (same first-touch placement as the iterates)
+        self.lo, self.hi = tv(S.lo), tv(S.hi)
+        self.c, self.l, self.u = tv(S.c), tv(S.l), tv(S.u)
         tau = S.eta / S.w0
         xhat = np.clip(self.x0 - tau * (S.c - self.aty0), S.l, S.u)
-        self.xbar = 2.0 * xhat - self.x0
+        self.xbar = tv(2.0 * xhat - self.x0)
         self.k = 0
+
+    @staticmethod
+    def _touch_csr(M):
+        """Copies of the CSR arrays whose pages are first written by the OpenMP thread that will
+        stream them (NUMA first touch; the SciPy originals were written by one thread)."""
+        ptr = np.ascontiguousarray(M.indptr, dtype=np.int64)
+        idx = np.ascontiguousarray(M.indices, dtype=np.int32)
+        val = np.ascontiguousarray(M.data, dtype=np.float64)
+        p2, i2, v2 = np.empty_like(ptr), np.empty_like(idx), np.empty_like(val)
+        lib().port_touch_copy_csr(M.shape[0], _p(ptr), _p(idx), _p(val), _p(p2), _p(i2), _p(v2))
+        return p2, i2, v2
+
+    @staticmethod
+    def _touch_vec(v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        out = np.empty_like(v)
+        lib().port_touch_copy_vec(v.size, _p(v), _p(out))
+        return out
 
     def iterate(self, iters: int) -> float:
         """`iters` PDHG iterations from the current state (no restart logic); returns seconds."""
@@ -92,10 +118,10 @@ class PortState:
         t0 = time.perf_counter()
         for _ in range(iters):
             a = (self.k + 1.0) / (self.k + 2.0)
-            L.port_row_step(self.m, _p(self.rp), _p(self.ri), _p(self.rv), _p(self.xbar), _p(S.lo),
-                            _p(S.hi), _p(self.y0), _p(self.y), _p(self.yhat), sigma, a)
+            L.port_row_step(self.m, _p(self.rp), _p(self.ri), _p(self.rv), _p(self.xbar), _p(self.lo),
+                            _p(self.hi), _p(self.y0), _p(self.y), _p(self.yhat), sigma, a)
             L.port_col_step(self.n, _p(self.cp), _p(self.ci), _p(self.cv), _p(self.yhat), _p(self.x0),
-                            _p(self.aty0), _p(S.c), _p(S.l), _p(S.u), _p(self.xbar), _p(self.aty),
+                            _p(self.aty0), _p(self.c), _p(self.l), _p(self.u), _p(self.xbar), _p(self.aty),
                             None, tau, a)
             self.k += 1
         return time.perf_counter() - t0

@@ -228,6 +228,21 @@ def test_kats_and_generated_models_on_gpu(built, golden, tmp_path):
     assert "0 failed" in out and "0 skipped" in out, out
 
 
+@pytest.mark.gpu
+def test_mkp_10x100_mip_on_gpu(built, golden, tmp_path):
+    """The last golden of the MIP parity tier (10 x 100 knapsack with 5 indicator
+    switches -> 1526, HiGHS `milp` proves it with 5 242 nodes): identical incumbent objective
+    through Solver / Var / Constr / IndicatorConstr on Backend::Cuda, proven by the tree."""
+    models = [("mkp_10x100_mip", gen.mkp(10, 100, 4, 5, 20265), golden["mkp_10x100_mip"]["objective"], 1e-9)]
+    path = tmp_path / "models.txt"
+    write_models(path, models)
+    rc, out = run_unit_test(built, "--filter", "Generated models",
+                            env={"MIPLIB_TEST_MODELS": str(path), "MIPLIB_TEST_TIME_LIMIT": "900"}, timeout=1200)
+    print(out)
+    assert rc == 0, out
+    assert "0 failed" in out and "0 skipped" in out, out
+
+
 # ---- bulk ingress through the C entry points (miplib/cuda/capi.hpp) ---------------------------
 def _front(built):
     import ctypes as C
