@@ -48,10 +48,15 @@ struct Constr
   Constr scale(double skip_lb = MIN_MAX_ABS_SKIP_SCALE, double skip_ub = MAX_MAX_ABS_SKIP_SCALE,
                bool ignore_inf_var_bounds = false) const;
 
-  // backends hang their row handle on the impl and reach it by downcast; the reference keeps this
-  // private behind a hard-coded friend list (miplib/constr.hpp:52-56), which a new backend cannot
-  // join without editing the header - see INTEGRATION.md
+  private:
+  // backends hang their row handle on the impl and reach it by downcast; private behind a friend
+  // list exactly as in the reference (miplib/constr.hpp:52-56) - the two Cuda lines are the edit a
+  // maintainer makes there (tests/test_dropin.py applies it to a copy of
+  // the reference's header and compiles the adapter against it)
   std::shared_ptr<detail::IConstr> p_impl;
+  friend std::ostream& operator<<(std::ostream& os, Constr const& c);
+  friend struct CudaSolver;
+  friend struct CudaBranchAndBound;
 };
 
 std::ostream& operator<<(std::ostream& os, Constr const& c);

@@ -155,7 +155,8 @@ void CudaSolver::remove(Constr const& constr)
 // solve would otherwise accept (integral points / the LP optimum), never on fractional node LPs.
 void CudaSolver::add_lazy_constr_handler(LazyConstrHandler const& handler, bool)
 {
-  if (!handler.valid()) fail("Cuda backend: null lazy constraint handler.");
+  // a handler built from a null pointer faults on first use, exactly as with the reference's
+  // backends (miplib/lazy.hpp:28-41 offers no way to ask)
   m_lazy_handlers.push_back(handler);
 }
 

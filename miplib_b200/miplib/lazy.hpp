@@ -37,7 +37,6 @@ struct LazyConstrHandler
   std::vector<Var> depends() const { return p_impl->depends(); }
   bool is_feasible() { return p_impl->is_feasible(); }
   bool add() { return p_impl->add(); }
-  bool valid() const { return static_cast<bool>(p_impl); }   // not in the reference: null-handler guard
 
   private:
   std::shared_ptr<ILazyConstrHandler> p_impl;

@@ -16,6 +16,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <cmath>
 #include <random>
 #include <vector>
 
@@ -83,6 +85,81 @@ __global__ void k_mix(const int* __restrict__ idx, long long total, const double
   if (out && total <= (1 << 20)) atomicAdd(out + 1, acc0 + acc1);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Other ways to issue the same random gathers out of L2 (no shared-memory panel): does any path
+// avoid the one-line-per-cycle tag stage of the L1?
+//   F_LDG  ld.global.nc (what the product uses)      F_CG   ld.global.cg (L2 only, no L1 line)
+//   F_CV   ld.volatile.global                        F_LDGSTS cp.async 8 B into shared memory
+//   F_BULK cp.async.bulk 16 B (TMA engine) into shared memory, completion on an mbarrier
+// ------------------------------------------------------------------------------------------
+enum { F_LDG = 0, F_CG = 1, F_CV = 2, F_LDGSTS = 3, F_BULK = 4 };
+
+template <int U, int F>
+__global__ void k_flavour(const int* __restrict__ idx, long long total, const double* __restrict__ vec, double* out, Clk* clk) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  long long c0 = 0; unsigned long long t0 = 0;
+  if (threadIdx.x == 0) { c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); }
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double acc0 = 0.0, acc1 = 0.0;
+  // F_LDGSTS / F_BULK: a private landing zone of U 16-byte slots per thread; F_BULK: one mbarrier per warp
+  double2* slots = reinterpret_cast<double2*>(s_raw) + (size_t)threadIdx.x * U;
+  const uint32_t slot_addr = (uint32_t)__cvta_generic_to_shared(slots);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_raw + (size_t)blockDim.x * U * 16);
+  const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(bars + (threadIdx.x >> 5));
+  uint32_t phase = 0;
+  if (F == F_BULK) {
+    if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_addr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+  }
+  for (; p + (U - 1) * stride < total; p += U * stride) {
+    int c[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) c[u] = ld_si(idx + p + u * stride);
+    if (F == F_LDG || F == F_CG || F == F_CV) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        double x;
+        if (F == F_LDG) x = __ldg(vec + c[u]);
+        else if (F == F_CG) asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(x) : "l"(vec + c[u]));
+        else asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(x) : "l"(vec + c[u]));
+        if (u & 1) acc1 += x; else acc0 += x;
+      }
+    } else if (F == F_LDGSTS) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(slot_addr + 16u * u), "l"(vec + c[u]) : "memory");
+      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+      for (int u = 0; u < U; ++u) { const double x = slots[u].x; if (u & 1) acc1 += x; else acc0 += x; }
+    } else {
+      if ((threadIdx.x & 31) == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_addr), "r"(32u * U * 16u) : "memory");
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 16, [%2];"
+                     :: "r"(slot_addr + 16u * u), "l"(vec + (c[u] & ~1)), "r"(bar_addr) : "memory");
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar_addr), "r"(phase) : "memory");
+      phase ^= 1;
+#pragma unroll
+      for (int u = 0; u < U; ++u) { const double x = (c[u] & 1) ? slots[u].y : slots[u].x; if (u & 1) acc1 += x; else acc0 += x; }
+      __syncwarp();
+    }
+  }
+  if (threadIdx.x == 0 && clk) {
+    unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    clk[blockIdx.x].cyc = clock64() - c0; clk[blockIdx.x].ns = t1 - t0;
+  }
+  if (acc0 + acc1 == 123.456) out[0] = acc0;
+  if (out && total <= (1 << 20)) atomicAdd(out + 1, acc0 + acc1);
+}
+
 template <class T> static T* up(const std::vector<T>& v) { T* d; CK(cudaMalloc(&d, v.size() * sizeof(T) + 4096)); CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice)); return d; }
 
 static int g_sms = 148;
@@ -123,12 +200,14 @@ static void run(const char* tag, int threads, int W, int N, long long total, con
   // correctness on a small prefix: checksum against the host
   {
     const long long small = std::min<long long>(total, 1 << 20);
-    const long long per = (long long)cfg.gridDim.x * threads * U;
-    const long long covered = small / per * per;   // the kernel drops the ragged tail
+    const long long stride = (long long)cfg.gridDim.x * threads;
     CK(cudaLaunchKernelEx(&cfg, kern, (const int*)didx, small, dvec, P, W, dout, (Clk*)nullptr));
     CK(cudaDeviceSynchronize());
     double got[2]; CK(cudaMemcpy(got, dout, 16, cudaMemcpyDeviceToHost));
-    double want = 0; for (long long q = 0; q < covered; ++q) want += hvec[hidx[q]];
+    double want = 0;   // the kernel drops the ragged tail of every thread
+    for (long long t = 0; t < stride; ++t)
+      for (long long q = t; q + (U - 1) * stride < small; q += U * stride)
+        for (int u = 0; u < U; ++u) want += hvec[hidx[q + u * stride]];
     if (fabs(got[1] - want) > 1e-6 * (1 + fabs(want))) printf("   !! checksum mismatch: got %.9g want %.9g\n", got[1], want);
   }
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -151,6 +230,54 @@ static void run(const char* tag, int threads, int W, int N, long long total, con
   CK(cudaFree(dout)); CK(cudaFree(dclk)); CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1));
 }
 
+
+template <int U, int F>
+static void run_flavour(const char* tag, int threads, int ctas_per_sm_cap, int N, long long total, const double* dvec, const std::vector<double>& hvec, int reps) {
+  static std::vector<int> hidx; static int last_n = -1; static int* didx = nullptr;
+  if (last_n != N) {
+    hidx.resize(total);
+    std::mt19937_64 rng(7 + N);
+    for (auto& v : hidx) v = (int)(rng() % (uint64_t)N);
+    if (didx) CK(cudaFree(didx));
+    didx = up(hidx); last_n = N;
+  }
+  auto kern = k_flavour<U, F>;
+  const size_t smem = (F == F_LDGSTS || F == F_BULK) ? (size_t)threads * U * 16 + 8 * (threads / 32) : 0;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+  if (ctas_per_sm_cap > 0) occ = std::min(occ, ctas_per_sm_cap);
+  const int grid = g_sms * occ;
+  double* dout; CK(cudaMalloc(&dout, 64)); CK(cudaMemset(dout, 0, 64));
+  Clk* dclk; CK(cudaMalloc(&dclk, sizeof(Clk) * grid));
+  {
+    const long long small = std::min<long long>(total, 1 << 20);
+    const long long stride = (long long)grid * threads;
+    kern<<<grid, threads, smem>>>(didx, small, dvec, dout, nullptr);
+    CK(cudaDeviceSynchronize());
+    double got[2]; CK(cudaMemcpy(got, dout, 16, cudaMemcpyDeviceToHost));
+    double want = 0;
+    for (long long t = 0; t < stride; ++t)
+      for (long long q = t; q + (U - 1) * stride < small; q += U * stride)
+        for (int u = 0; u < U; ++u) want += hvec[hidx[q + u * stride]];
+    if (fabs(got[1] - want) > 1e-6 * (1 + fabs(want))) printf("   !! checksum mismatch: got %.9g want %.9g\n", got[1], want);
+  }
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int w = 0; w < 3; ++w) kern<<<grid, threads, smem>>>(didx, total, dvec, dout, dclk);
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  for (int r = 0; r < reps; ++r) kern<<<grid, threads, smem>>>(didx, total, dvec, dout, dclk);
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+  std::vector<Clk> hc(grid); CK(cudaMemcpy(hc.data(), dclk, sizeof(Clk) * hc.size(), cudaMemcpyDeviceToHost));
+  double mhz = 0; for (auto& c : hc) mhz += (double)c.cyc / (double)c.ns * 1e3; mhz /= hc.size();
+  const double us = ms * 1e3 / reps;
+  printf("%-34s thr %4d x %d CTAs/SM smem %3zu KB/CTA N %8d U%-2d: %8.1f us  %5.2f gathers/SM-cycle  %.0f MHz\n",
+         tag, threads, occ, smem >> 10, N, U, us, (double)total / (us * mhz) / g_sms, mhz);
+  fflush(stdout);
+  CK(cudaFree(dout)); CK(cudaFree(dclk)); CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1));
+}
+
 int main(int argc, char** argv) {
   const long long total = argc > 1 ? atoll(argv[1]) : 32000000LL;
   const int reps = 10;
@@ -162,6 +289,27 @@ int main(int argc, char** argv) {
   for (auto& v : hvec) v = uv(rng);
   double* dvec = up(hvec);
   const int W128 = 16384, W200 = 25600, W64 = 8192;
+  const char* mode = argc > 2 ? argv[2] : "all";
+  if (!strcmp(mode, "flavours") || !strcmp(mode, "all")) {
+    run_flavour<8, F_LDG>("ld.global.nc", 256, 0, 2000000, total, dvec, hvec, reps);
+    run_flavour<16, F_LDG>("ld.global.nc", 256, 0, 2000000, total, dvec, hvec, reps);
+    run_flavour<8, F_CG>("ld.global.cg", 256, 0, 2000000, total, dvec, hvec, reps);
+    run_flavour<16, F_CG>("ld.global.cg", 256, 0, 2000000, total, dvec, hvec, reps);
+    run_flavour<8, F_CV>("ld.volatile.global", 256, 0, 2000000, total, dvec, hvec, reps);
+    run_flavour<8, F_LDGSTS>("cp.async 8 B -> smem", 256, 0, 2000000, total, dvec, hvec, reps);
+    run_flavour<8, F_LDGSTS>("cp.async 8 B -> smem, 2 CTAs/SM", 256, 2, 2000000, total, dvec, hvec, reps);
+    run_flavour<4, F_BULK>("cp.async.bulk 16 B (TMA)", 256, 0, 2000000, total, dvec, hvec, reps);
+    run_flavour<8, F_BULK>("cp.async.bulk 16 B (TMA)", 256, 0, 2000000, total, dvec, hvec, reps);
+    run_flavour<8, F_BULK>("cp.async.bulk 16 B (TMA), 2 CTAs/SM", 256, 2, 2000000, total, dvec, hvec, reps);
+  }
+  if (!strcmp(mode, "ncu")) {   // the three launches worth a counter capture
+    run<8, 0>("L2 only, 1024 thr", 1024, 0, 2000000, total, dvec, hvec, 1);
+    run<8, 4>("DSMEM only", 1024, W128, 16 * W128, total, dvec, hvec, 1);
+    run<8, 4>("mixed, yhat-sized (1M)", 1024, W200, 1000000, total, dvec, hvec, 1);
+    run<8, 4>("L2 only under 200 KB smem", 1024, W200, 2000000, total, dvec, hvec, 1, 0);
+    return 0;
+  }
+  if (strcmp(mode, "all") && strcmp(mode, "dsmem")) { printf("done\n"); return 0; }
   // 1. baseline: everything through L2 (no smem; then with 128 / 200 KB of smem taken away from L1)
   run<8, 0>("L2 only, 256 thr", 256, 0, 2000000, total, dvec, hvec, reps);
   run<8, 0>("L2 only, 1024 thr", 1024, 0, 2000000, total, dvec, hvec, reps);
