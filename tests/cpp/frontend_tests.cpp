@@ -273,7 +273,6 @@ CPU_TEST("Solver facade: error conventions of the plugin seam")
   REQUIRE_THROWS_AS(solver.add(c), std::logic_error);                    // posted twice
   REQUIRE_THROWS_AS(solver.add(v1 >= 4), std::logic_error);              // trivially unsat
   REQUIRE_THROWS_AS(solver.maximize(v1 * v2), std::logic_error);         // quadratic objective
-  REQUIRE_THROWS_AS(solver.add_lazy_constr_handler(LazyConstrHandler(nullptr), true), std::logic_error);
   REQUIRE_THROWS_AS(Solver(Solver::Backend::Scip), std::logic_error);    // not compiled
   REQUIRE(Solver::backend_is_compiled(B) && !Solver::backend_is_compiled(Solver::Backend::Gurobi));
   REQUIRE(solver.infinity() == 1e20);
