@@ -93,7 +93,7 @@ __global__ void k_mix(const int* __restrict__ idx, long long total, const double
 //   F_CV   ld.volatile.global                        F_LDGSTS cp.async 8 B into shared memory
 //   F_BULK cp.async.bulk 16 B (TMA engine) into shared memory, completion on an mbarrier
 // ------------------------------------------------------------------------------------------
-enum { F_LDG = 0, F_CG = 1, F_CV = 2, F_LDGSTS = 3, F_BULK = 4 };
+enum { F_LDG = 0, F_CG = 1, F_CV = 2, F_LDGSTS = 3, F_BULK = 4, F_MIX2 = 5, F_MIX4 = 6 };   // F_MIXk: k of the U gathers by cp.async.bulk, the rest by ld.global.nc
 
 template <int U, int F>
 __global__ void k_flavour(const int* __restrict__ idx, long long total, const double* __restrict__ vec, double* out, Clk* clk) {
@@ -104,12 +104,13 @@ __global__ void k_flavour(const int* __restrict__ idx, long long total, const do
   const long long stride = (long long)gridDim.x * blockDim.x;
   double acc0 = 0.0, acc1 = 0.0;
   // F_LDGSTS / F_BULK: a private landing zone of U 16-byte slots per thread; F_BULK: one mbarrier per warp
-  double2* slots = reinterpret_cast<double2*>(s_raw) + (size_t)threadIdx.x * U;
+  double2* slots = reinterpret_cast<double2*>(s_raw) + (size_t)threadIdx.x * (F == F_MIX2 ? 2 : F == F_MIX4 ? 4 : U);
   const uint32_t slot_addr = (uint32_t)__cvta_generic_to_shared(slots);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_raw + (size_t)blockDim.x * U * 16);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_raw + (size_t)blockDim.x * (F == F_MIX2 ? 2 : F == F_MIX4 ? 4 : U) * 16);
   const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(bars + (threadIdx.x >> 5));
   uint32_t phase = 0;
-  if (F == F_BULK) {
+  constexpr int UT = F == F_BULK ? U : F == F_MIX2 ? 2 : F == F_MIX4 ? 4 : 0;   // gathers by the TMA engine
+  if (UT > 0) {
     if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_addr));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
@@ -136,19 +137,21 @@ __global__ void k_flavour(const int* __restrict__ idx, long long total, const do
       for (int u = 0; u < U; ++u) { const double x = slots[u].x; if (u & 1) acc1 += x; else acc0 += x; }
     } else {
       if ((threadIdx.x & 31) == 0)
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_addr), "r"(32u * U * 16u) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_addr), "r"(32u * UT * 16u) : "memory");
       __syncwarp();
 #pragma unroll
-      for (int u = 0; u < U; ++u)
+      for (int u = 0; u < UT; ++u)
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 16, [%2];"
                      :: "r"(slot_addr + 16u * u), "l"(vec + (c[u] & ~1)), "r"(bar_addr) : "memory");
+#pragma unroll
+      for (int u = UT; u < U; ++u) { const double x = __ldg(vec + c[u]); if (u & 1) acc1 += x; else acc0 += x; }
       uint32_t done = 0;
       while (!done)
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done) : "r"(bar_addr), "r"(phase) : "memory");
       phase ^= 1;
 #pragma unroll
-      for (int u = 0; u < U; ++u) { const double x = (c[u] & 1) ? slots[u].y : slots[u].x; if (u & 1) acc1 += x; else acc0 += x; }
+      for (int u = 0; u < UT; ++u) { const double x = (c[u] & 1) ? slots[u].y : slots[u].x; if (u & 1) acc1 += x; else acc0 += x; }
       __syncwarp();
     }
   }
@@ -242,7 +245,7 @@ static void run_flavour(const char* tag, int threads, int ctas_per_sm_cap, int N
     didx = up(hidx); last_n = N;
   }
   auto kern = k_flavour<U, F>;
-  const size_t smem = (F == F_LDGSTS || F == F_BULK) ? (size_t)threads * U * 16 + 8 * (threads / 32) : 0;
+  const size_t smem = F >= F_LDGSTS ? (size_t)threads * (F == F_MIX2 ? 2 : F == F_MIX4 ? 4 : U) * 16 + 8 * (threads / 32) : 0;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
   if (ctas_per_sm_cap > 0) occ = std::min(occ, ctas_per_sm_cap);
@@ -301,6 +304,16 @@ int main(int argc, char** argv) {
     run_flavour<4, F_BULK>("cp.async.bulk 16 B (TMA)", 256, 0, 2000000, total, dvec, hvec, reps);
     run_flavour<8, F_BULK>("cp.async.bulk 16 B (TMA)", 256, 0, 2000000, total, dvec, hvec, reps);
     run_flavour<8, F_BULK>("cp.async.bulk 16 B (TMA), 2 CTAs/SM", 256, 2, 2000000, total, dvec, hvec, reps);
+  }
+  if (!strcmp(mode, "mix")) {   // LSU gathers and TMA gathers side by side: are the two paths additive?
+    run_flavour<8, F_LDG>("ld.global.nc", 256, 0, 2000000, total, dvec, hvec, reps);
+    run_flavour<10, F_MIX2>("8 ld.global.nc + 2 cp.async.bulk", 256, 0, 2000000, total, dvec, hvec, reps);
+    run_flavour<12, F_MIX4>("8 ld.global.nc + 4 cp.async.bulk", 256, 0, 2000000, total, dvec, hvec, reps);
+    run_flavour<16, F_MIX2>("14 ld.global.nc + 2 cp.async.bulk", 256, 0, 2000000, total, dvec, hvec, reps);
+    run_flavour<16, F_MIX4>("12 ld.global.nc + 4 cp.async.bulk", 256, 0, 2000000, total, dvec, hvec, reps);
+    run_flavour<10, F_MIX2>("8 + 2, 4 CTAs/SM", 256, 4, 2000000, total, dvec, hvec, reps);
+    run_flavour<10, F_MIX2>("8 + 2, 512 thr", 512, 0, 2000000, total, dvec, hvec, reps);
+    printf("done\n"); return 0;
   }
   if (!strcmp(mode, "ncu")) {   // the three launches worth a counter capture
     run<8, 0>("L2 only, 1024 thr", 1024, 0, 2000000, total, dvec, hvec, 1);
