@@ -75,7 +75,10 @@ enum {
   MIPCU_PARAM_ROW_SORT = 14,      /* 1 (default): rows are stored sorted by decreasing length on the device (no padding in
                                      the sliced-ELL copy); invisible through this ABI.  0: rows keep the caller's order.
                                      Set before load */
-  MIPCU_PARAM_COUNT_ = 15
+  MIPCU_PARAM_PEER_TIMEOUT = 15,  /* row-sharded contexts: seconds a kernel waits at a cross-GPU barrier for its peers
+                                     (default 120; 0 = forever).  On expiry the solve returns rc = 1 with a message
+                                     instead of hanging or trapping: sharded load / solve are collective and fail-stop */
+  MIPCU_PARAM_COUNT_ = 16
 };
 
 typedef struct mipcu_stats {
@@ -139,9 +142,21 @@ int  mipcu_solve_lp(mipcu_ctx* ctx, mipcu_stats* out);
 /* B node LPs that share A, c and the row sides but differ in column bounds; bounds are
  * [B][n] row-major on the host.  cutoff ([B], model's own sense, NaN = none) may be NULL: then
  * MIPCU_PARAM_OBJ_CUTOFF applies to every node.  x_out ([B][n]) may be NULL.  All nodes start
- * from x = clamp(0), y = 0 and run to MIPCU_PARAM_EPS_REL / ITER_LIMIT / TIME_LIMIT. */
+ * from x = clamp(0), y = 0 (mipcu_solve_lp_batch_warm takes start points) and run to
+ * MIPCU_PARAM_EPS_REL / ITER_LIMIT / TIME_LIMIT. */
 int  mipcu_solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* ub,
                           const double* cutoff, mipcu_stats* out /* [B] */, double* x_out);
+/* The same with a start point per node - in a branch and bound, the parent's LP solution (what
+ * lp_solve's and SCIP's tree do with the parent basis behind ::solve / SCIPsolve, reference
+ * miplib/lpsolve/solver.cpp:156, miplib/scip/solver.cpp:370): x0 [B][n] and y0 [B][m] in the caller's
+ * terms (x0 is clamped into the node's box; all-zero rows = cold start), primal_weight0 [B] the
+ * mipcu_stats.primal_weight the parent's solve ended with (<= 0: default).  Any of the three may be
+ * NULL.  y_out ([B][m]) may be NULL.  stats[b].row/col_kernel_us and _bytes describe the batched
+ * kernels with all B problems in flight. */
+int  mipcu_solve_lp_batch_warm(mipcu_ctx* ctx, int32_t B, const double* lb, const double* ub,
+                               const double* cutoff, const double* x0, const double* y0,
+                               const double* primal_weight0, mipcu_stats* out /* [B] */,
+                               double* x_out, double* y_out);
 int  mipcu_get_x(mipcu_ctx* ctx, double* x /* n */);
 int  mipcu_get_y(mipcu_ctx* ctx, double* y /* m (local rows when sharded) */);
 

@@ -16,7 +16,8 @@ void dist_init(mipcu_ctx* ctx, int rank, int world, const void* unique_id);
 void dist_destroy(mipcu_ctx* ctx);
 // batch.cu
 void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* ub, const double* cutoff,
-                    mipcu_stats* out, double* x_out);
+                    const double* x0, const double* y0, const double* weight0,
+                    mipcu_stats* out, double* x_out, double* y_out);
 }  // namespace mipcu
 
 thread_local const mipcu_ctx* g_alloc_ctx = nullptr;
@@ -65,6 +66,7 @@ void set_default_params(mipcu_ctx* ctx) {
   ctx->params[MIPCU_PARAM_USE_PDL] = 0;
   ctx->params[MIPCU_PARAM_MULTICAST] = 1;
   ctx->params[MIPCU_PARAM_ROW_SORT] = 1;
+  ctx->params[MIPCU_PARAM_PEER_TIMEOUT] = 120.0;
 }
 
 mipcu_ctx* create_on(int device) {
@@ -86,14 +88,27 @@ mipcu_ctx* create_on(int device) {
   set_default_params(ctx);
   try {
     MIPCU_CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    // keep freed model arrays in the device's memory pool (see setup.cu: dalloc)
+    // model arrays come stream-ordered from a memory pool PRIVATE to this context that keeps what is
+    // freed (see setup.cu: dalloc); the device's default pool - which a host application such as
+    // PyTorch's cudaMallocAsync allocator may share - is left alone
     int pools = 0;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, device) == cudaSuccess && pools &&
-        cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      uint64_t keep = UINT64_MAX;
-      if (cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess)
-        ctx->pool_alloc = true;
+    if (cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, device) == cudaSuccess && pools) {
+      cudaMemPoolProps props;
+      std::memset(&props, 0, sizeof(props));
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = device;
+      cudaMemPool_t pool = nullptr;
+      if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        if (cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess) {
+          ctx->pool = pool;
+          ctx->pool_alloc = true;
+        } else {
+          cudaMemPoolDestroy(pool);
+        }
+      }
     }
     cudaGetLastError();
   } catch (...) {
@@ -165,11 +180,8 @@ void mipcu_destroy(mipcu_ctx* ctx) {
     if (e) cudaEventDestroy(e);
   if (ctx->stream) {
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->pool_alloc) {   // hand the pool's cached memory back to the device
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
-    }
     cudaStreamDestroy(ctx->stream);
+    if (ctx->pool) cudaMemPoolDestroy((cudaMemPool_t)ctx->pool);   // hands the cached memory back to the device
   }
   cudaGetLastError();
   delete ctx;
@@ -177,8 +189,11 @@ void mipcu_destroy(mipcu_ctx* ctx) {
 
 const char* mipcu_last_error(const mipcu_ctx* ctx) {
   if (ctx) return ctx->err.c_str();
+  // a copy private to the calling thread: the pointer stays valid after the lock is released
+  thread_local std::string copy;
   std::lock_guard<std::mutex> lk(g_mutex);
-  return g_create_error.c_str();
+  copy = g_create_error;
+  return copy.c_str();
 }
 
 int mipcu_load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr,
@@ -187,10 +202,34 @@ int mipcu_load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64
   if (!ctx) return 1;
   return guarded(ctx, [&] {
     ctx->launches = 0;
-    p2p_teardown(ctx);
-    load_lp(ctx, m, n, nnz, row_ptr, col_idx, val, c, lb, ub, row_lo, row_hi, maximize);
-    p2p_setup(ctx);   // collective on sharded contexts: maps the peers' exchange buffers
-    own_setup(ctx);   // block-owner exchange (MIPCU_PARAM_SHARD_EXCHANGE = 2): column block of the whole matrix
+    // Row-sharded contexts: a model of the same shape as the one before (every rank: same n, same
+    // row count, same exchange parameters) keeps the exported vectors, the CUDA-IPC mappings and the
+    // multicast window - re-creating them is most of the cost of a re-load.  All ranks must agree.
+    bool keep = false;
+    if (ctx->world > 1) {
+      MIPCU_CK(cudaSetDevice(ctx->device));
+      const bool same = ctx->loaded && p2p_active(ctx) && n == ctx->n && m == ctx->m &&
+                        ctx->params[MIPCU_PARAM_SHARD_EXCHANGE] == ctx->exchange_at_setup &&
+                        ctx->params[MIPCU_PARAM_MULTICAST] == ctx->multicast_at_setup;
+      keep = dist_sum_scalar(ctx, same ? 1.0 : 0.0) > ctx->world - 0.5;
+    }
+    if (!keep) p2p_teardown(ctx);
+    ctx->keep_exchange = keep;
+    try {
+      load_lp(ctx, m, n, nnz, row_ptr, col_idx, val, c, lb, ub, row_lo, row_hi, maximize);
+    } catch (...) {
+      ctx->keep_exchange = false;
+      throw;
+    }
+    ctx->keep_exchange = false;
+    if (keep) {
+      own_rebuild(ctx);   // only the column block of the block-owner exchange depends on the matrix
+    } else {
+      p2p_setup(ctx);   // collective on sharded contexts: maps the peers' exchange buffers
+      own_setup(ctx);   // block-owner exchange (MIPCU_PARAM_SHARD_EXCHANGE = 2): column block of the whole matrix
+      ctx->exchange_at_setup = ctx->params[MIPCU_PARAM_SHARD_EXCHANGE];
+      ctx->multicast_at_setup = ctx->params[MIPCU_PARAM_MULTICAST];
+    }
   });
 }
 
@@ -264,7 +303,14 @@ int mipcu_solve_lp(mipcu_ctx* ctx, mipcu_stats* out) {
 int mipcu_solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* ub,
                          const double* cutoff, mipcu_stats* out, double* x_out) {
   if (!ctx) return 1;
-  return guarded(ctx, [&] { solve_lp_batch(ctx, B, lb, ub, cutoff, out, x_out); });
+  return guarded(ctx, [&] { solve_lp_batch(ctx, B, lb, ub, cutoff, nullptr, nullptr, nullptr, out, x_out, nullptr); });
+}
+
+int mipcu_solve_lp_batch_warm(mipcu_ctx* ctx, int32_t B, const double* lb, const double* ub,
+                              const double* cutoff, const double* x0, const double* y0,
+                              const double* primal_weight0, mipcu_stats* out, double* x_out, double* y_out) {
+  if (!ctx) return 1;
+  return guarded(ctx, [&] { solve_lp_batch(ctx, B, lb, ub, cutoff, x0, y0, primal_weight0, out, x_out, y_out); });
 }
 
 int mipcu_get_x(mipcu_ctx* ctx, double* x) {

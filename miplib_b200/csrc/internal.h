@@ -9,10 +9,21 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost nothing unless a profiler is attached
+
 #include "../../include/mipcu.h"
 #include "params.h"
 
 namespace mipcu {
+
+// NVTX range over a host-side phase (load, setup, iteration block, KKT pass, node-LP round) so that
+// Nsight Systems timelines of a host application show where the backend spends its time.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct Error : std::runtime_error {
   using std::runtime_error::runtime_error;
@@ -95,7 +106,7 @@ struct Scalars {
   int ray_hits_primal, ray_hits_dual;   // consecutive checks on which a certificate test passed
   int restarts;
   int nblk_row, nblk_col, max_blocks;
-  int pad_;
+  int fault;            // set by a kernel whose cross-GPU barrier timed out (p2p.cu:own_barrier); the host reports it
   double ray_dual_value, ray_primal_value;   // last normalised Farkas value / c.dx (diagnostics)
 };
 
@@ -121,6 +132,7 @@ struct PeerTable {
   // this rank's included; null = unicast pushes through the arrays above
   double* mc_xbar = nullptr;
   double* mc_yhat_full = nullptr;
+  unsigned long long barrier_timeout_ns = 0;   // how long a block-owner kernel waits for its peers (0: forever)
 };
 
 // mc.cu: the window [xbar | yhat_full] of this rank, bound to the job's multicast object
@@ -152,6 +164,10 @@ struct mipcu_ctx {
   std::vector<void*> peer_mappings;
   unsigned long long* p2p_flags = nullptr;
   mipcu::McWindow mc;
+  // a re-load of a model of the same shape keeps the exported vectors, their peer mappings and the
+  // multicast window (api.cu: mipcu_load_lp); set only while that load runs
+  bool keep_exchange = false;
+  double exchange_at_setup = -1.0, multicast_at_setup = -1.0;   // parameter values the mappings were built for
   bool own_ready = false;             // block-owner exchange: column block built, yhat_full mapped
   bool use_pdl = false;               // iteration kernels launched as programmatic dependents (MIPCU_PDL)
   int own_blocks_per_cta = 0;         // block-owner kernels: 256-row blocks one CTA works through (0 = automatic)
@@ -204,7 +220,8 @@ struct mipcu_ctx {
 
   int64_t launches = 0;   // kernels launched by the current call
   cudaEvent_t split_event = nullptr;   // sharded col step: recorded between the partial SpMV and the exchange
-  bool pool_alloc = false;   // model arrays come from the stream-ordered memory pool
+  bool pool_alloc = false;   // model arrays come from the stream-ordered memory pool below
+  void* pool = nullptr;      // cudaMemPool_t private to this context (api.cu: create_on)
   std::vector<void*> raw_allocs;   // arrays that had to come from cudaMalloc (exported over CUDA IPC)
 };
 
@@ -244,6 +261,7 @@ bool p2p_active(const mipcu_ctx* ctx);
 bool own_active(const mipcu_ctx* ctx);   // block-owner exchange in use
 struct RowStepArgs;
 void own_setup(mipcu_ctx* ctx);          // collective, after p2p_setup: builds the column block
+void own_rebuild(mipcu_ctx* ctx);        // collective: new column block for a re-loaded model, mappings kept
 void own_row_step(mipcu_ctx* ctx, const RowStepArgs& a, bool check);
 void own_col_step(mipcu_ctx* ctx, int iter_in_block, bool check, const double* xhat_in, double* xhat_out);
 void p2p_setup(mipcu_ctx* ctx);

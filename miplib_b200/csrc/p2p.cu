@@ -139,25 +139,42 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
   return v;
 }
 
-__device__ __forceinline__ void own_barrier(const PeerTable& t, const unsigned long long epoch, const int variant) {
-  if (variant & OWN_NO_BARRIER) return;
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Entry barrier of the block-owner kernels.  Returns false when the kernel must not run: a peer did
+// not arrive within PeerTable::barrier_timeout_ns (MIPCU_PARAM_PEER_TIMEOUT), now or in an earlier
+// kernel of this solve.  The expiry is recorded in the control block (Scalars::fault) - no trap, the
+// context stays usable - and every later kernel of the queue falls through at once; the host turns it
+// into rc = 1 + mipcu_last_error (solve.cu).
+__device__ __forceinline__ bool own_barrier(const PeerTable& t, const unsigned long long epoch, const int variant,
+                                            const Scalars* sc) {
+  if (variant & OWN_NO_BARRIER) return true;
+  int* fault = const_cast<int*>(&sc->fault);
   if (threadIdx.x < t.world) {
     if (blockIdx.x == 0) {
       __threadfence_system();
       st_release_sys(t.flags[threadIdx.x] + kOwnFlagBase + t.rank, epoch);
     }
     const unsigned long long* f = t.flags[t.rank] + kOwnFlagBase + threadIdx.x;
+    const bool relaxed = variant & OWN_RELAXED_POLL;
+    unsigned long long deadline = 0;
     int spins = 0;
-    if (variant & OWN_RELAXED_POLL) {
-      while (ld_relaxed_sys(f) < epoch)
-        if (++spins > (1 << 27)) asm volatile("trap;");
-      __threadfence_system();
-    } else {
-      while (ld_acquire_sys(f) < epoch)
-        if (++spins > (1 << 27)) asm volatile("trap;");   // a lost peer must not hang the device (~1 min)
+    while ((relaxed ? ld_relaxed_sys(f) : ld_acquire_sys(f)) < epoch) {
+      if ((++spins & 1023) != 0) continue;
+      if (*(volatile int*)fault) break;                       // an earlier kernel already gave up
+      if (t.barrier_timeout_ns == 0) continue;
+      const unsigned long long now = global_timer_ns();
+      if (deadline == 0) deadline = now + t.barrier_timeout_ns;
+      else if (now > deadline) { atomicExch(fault, 1); break; }
     }
+    if (relaxed) __threadfence_system();
   }
   __syncthreads();
+  return *(volatile int*)fault == 0;
 }
 
 __device__ __forceinline__ void own_publish(const int variant) {
@@ -183,8 +200,7 @@ k_row_step_own(const RowStepArgs a, const PeerTable t, const unsigned long long 
     if (!cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.perm, a.xbar, a.m, s_sum, [&] {
           if (!first) return true;
           pdl_wait();
-          own_barrier(t, epoch, variant);
-          return !sc->done;
+          return own_barrier(t, epoch, variant, sc) && !sc->done;
         }, blk))
       return;
     if (first) {
@@ -227,8 +243,7 @@ k_col_step_own(const ColStepArgs a, const PeerTable t, const unsigned long long 
     if (!cta_row_sums<TPR>(a.ptr, a.idx, a.val, a.perm, a.yhat, a.n, s_sum, [&] {
           if (!first) return true;
           pdl_wait();
-          own_barrier(t, epoch, variant);
-          return !sc->done;
+          return own_barrier(t, epoch, variant, sc) && !sc->done;
         }, blk))
       return;
     if (first) {
@@ -360,7 +375,15 @@ void own_setup(mipcu_ctx* ctx) {
   ctx->own_variant = v ? std::atoi(v) : OWN_NO_PUBLISH;
   const char* b = std::getenv("MIPCU_OWN_BLOCKS");
   ctx->own_blocks_per_cta = b ? std::atoi(b) : 0;     // 0: chosen per kernel (own_grid)
+  ctx->peers.barrier_timeout_ns = (unsigned long long)(std::max(0.0, ctx->params[MIPCU_PARAM_PEER_TIMEOUT]) * 1e9);
   ctx->own_ready = true;
+}
+
+// Re-load of a model of the same shape (mipcu_load_lp kept the exported vectors and every mapping):
+// only the column block depends on the matrix.
+void own_rebuild(mipcu_ctx* ctx) {
+  if (!ctx->own_ready) return;
+  build_col_block(ctx);
 }
 
 #define MIPCU_OWN_DISPATCH(fmt, CALL)                                                          \

@@ -18,8 +18,8 @@ inline int grid_for(int64_t n, int per_block = kThreads) {
   return (int)((n + per_block - 1) / per_block);
 }
 
-// Device allocations of this file.  A context allocates stream-ordered from the device's memory
-// pool (release threshold raised at creation, api.cu): cudaMalloc / cudaFree synchronise the
+// Device allocations of this file.  A context allocates stream-ordered from its own memory
+// pool (created with an unlimited release threshold, api.cu): cudaMalloc / cudaFree synchronise the
 // device and map / unmap memory on every call, which made RE-loading a config-3 model cost 0.7 s;
 // from the pool the same buffers are reused.  The few vectors a row-sharded context exports over
 // CUDA IPC (pool memory cannot be exported) come from cudaMalloc and are remembered as such.
@@ -31,7 +31,7 @@ T* dalloc(int64_t count) {
   const size_t bytes = sizeof(T) * (size_t)(count > 0 ? count : 1);
   mipcu_ctx* ctx = const_cast<mipcu_ctx*>(g_alloc_ctx);
   if (ctx && ctx->pool_alloc && !g_alloc_exported) {
-    MIPCU_CK(cudaMallocAsync(&p, bytes, ctx->stream));
+    MIPCU_CK(cudaMallocFromPoolAsync(&p, bytes, (cudaMemPool_t)ctx->pool, ctx->stream));
   } else {
     MIPCU_CK(cudaMalloc(&p, bytes));
     if (ctx && ctx->pool_alloc) ctx->raw_allocs.push_back(p);
@@ -665,7 +665,10 @@ void free_model(mipcu_ctx* ctx) {
   free_csr(ctx->rows);
   free_csr(ctx->cols);
   free_csr(ctx->colblk);
-  dfree(ctx->yhat_full);
+  // keep_exchange (re-load of the same shape on a row-sharded context): the vectors the peers have
+  // mapped - and the multicast window xbar / yhat_full may live in - stay where they are
+  const bool keep = ctx->keep_exchange;
+  if (!keep) dfree(ctx->yhat_full);
   dfree(ctx->row_perm);
   ctx->h_row_perm.clear();
   double** vecs[] = {&ctx->c, &ctx->lb, &ctx->ub, &ctx->lo, &ctx->hi, &ctx->cs, &ctx->ls, &ctx->us,
@@ -673,7 +676,10 @@ void free_model(mipcu_ctx* ctx) {
                      &ctx->aty0, &ctx->xhat_first, &ctx->xhat_chk, &ctx->aty_cand, &ctx->y,
                      &ctx->y0, &ctx->yhat, &ctx->tmp_n, &ctx->tmp_m, &ctx->x_start, &ctx->y_start,
                      &ctx->x_sol, &ctx->y_sol, &ctx->partials};
-  for (double** p : vecs) dfree(*p);
+  for (double** p : vecs) {
+    if (keep && (p == &ctx->xbar || p == &ctx->xhat_chk || p == &ctx->tmp_n || p == &ctx->x_sol)) continue;
+    dfree(*p);
+  }
   if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
   ctx->graph_period = 0;
   ctx->loaded = ctx->prepared = ctx->has_solution = false;
@@ -683,6 +689,7 @@ void free_model(mipcu_ctx* ctx) {
 void load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr,
              const int32_t* col_idx, const double* val, const double* c, const double* lb,
              const double* ub, const double* row_lo, const double* row_hi, int maximize) {
+  NvtxRange nvtx("mipcu:load_lp (H2D, transpose, row sort)");
   MIPCU_REQUIRE(m >= 0 && n >= 0 && nnz >= 0, "mipcu_load_lp: negative dimension");
   MIPCU_REQUIRE(m < (1ll << 31) - 1024 && n < (1ll << 31) - 1024 && nnz < (1ll << 31) - 1024,
                 "mipcu_load_lp: dimensions beyond int32 indexing are not supported");
@@ -769,13 +776,16 @@ void load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* r
                       &ctx->x_sol};
   for (double** p : nvecs) {
     // row-sharded: the exchange buffers are mapped by the peers (p2p.cu)
-    g_alloc_exported = ctx->world > 1 && (p == &ctx->xbar || p == &ctx->xhat_chk || p == &ctx->tmp_n || p == &ctx->x_sol);
+    const bool exported = ctx->world > 1 && (p == &ctx->xbar || p == &ctx->xhat_chk || p == &ctx->tmp_n || p == &ctx->x_sol);
+    if (exported && ctx->keep_exchange) continue;     // same shape as the model before: still mapped
+    g_alloc_exported = exported;
     *p = dalloc<double>(n + 2);   // +2: TMA reads an even number of doubles
     g_alloc_exported = false;
   }
   double** mvecs[] = {&ctx->los, &ctx->his, &ctx->d1, &ctx->y, &ctx->y0, &ctx->yhat, &ctx->tmp_m,
                       &ctx->y_sol};
   for (double** p : mvecs) *p = dalloc<double>(m + 2);
+  const int m_glob_before = ctx->m_glob;
   ctx->m_glob = (int)m;
   for (int& v : ctx->row_off) v = 0;
   ctx->row_off[1] = (int)m;
@@ -794,10 +804,13 @@ void load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* r
     for (int g = 0; g < W; ++g) { ctx->row_off[g] = (int)acc; acc += rows_of[g]; }
     MIPCU_REQUIRE(acc < (1ll << 31) - 1024, "mipcu_load_lp: total row count beyond int32 indexing");
     ctx->row_off[W] = (int)acc;
+    MIPCU_REQUIRE(!ctx->keep_exchange || m_glob_before == (int)acc, "mipcu_load_lp: row blocks changed under kept mappings");
     ctx->m_glob = (int)acc;
-    g_alloc_exported = true;
-    ctx->yhat_full = dalloc<double>(acc + 2);
-    g_alloc_exported = false;
+    if (!ctx->keep_exchange) {
+      g_alloc_exported = true;
+      ctx->yhat_full = dalloc<double>(acc + 2);
+      g_alloc_exported = false;
+    }
     MIPCU_CK(cudaMemsetAsync(ctx->yhat_full, 0, sizeof(double) * (acc + 2), st));
   }
   ctx->max_blocks = std::max(1024, std::max(grid_for(m, 64), grid_for(n, 64)));   // 64 = TMA tile rows
@@ -820,6 +833,7 @@ void load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* r
 void prepare(mipcu_ctx* ctx) {
   MIPCU_REQUIRE(ctx->loaded, "no model loaded");
   if (ctx->prepared) return;
+  NvtxRange nvtx("mipcu:setup (Ruiz / Pock-Chambolle scaling, SELL copies, step size)");
   auto t0 = std::chrono::steady_clock::now();
   cudaStream_t st = ctx->stream;
   const int m = ctx->m, n = ctx->n;

@@ -442,6 +442,7 @@ const double* global_row_sums(mipcu_ctx* ctx) {
 
 void kkt_row(mipcu_ctx* ctx) {
   if (ctx->m == 0) return;
+  NvtxRange nvtx("mipcu:kkt pass");
   const int fmt = kernel_format(ctx, ctx->rows);
   if (fmt == 0) launch_kkt<0>(ctx);
   else MIPCU_DISPATCH_TPR(fmt, launch_kkt<T>(ctx));
@@ -466,6 +467,7 @@ void restart_apply(mipcu_ctx* ctx) {
 // stored into xhat_first by the last col step (or by k_restart_apply).
 // time_events != null: record events around the row and col kernels of iteration 1.
 void enqueue_block(mipcu_ctx* ctx, int period, cudaEvent_t* time_events, cudaEvent_t split = nullptr) {
+  NvtxRange nvtx("mipcu:iteration block");
   cudaStream_t st = ctx->stream;
   for (int i = 0; i < period; ++i) {
     const bool first = (i == 0), last = (i == period - 1);
@@ -576,6 +578,7 @@ int64_t col_kernel_bytes(const mipcu_ctx* ctx) {
 void solve_lp(mipcu_ctx* ctx, mipcu_stats* out) {
   MIPCU_REQUIRE(ctx->loaded, "mipcu_solve_lp: no model loaded");
   MIPCU_REQUIRE(out, "mipcu_solve_lp: null stats");
+  NvtxRange nvtx("mipcu:solve_lp");
   MIPCU_CK(cudaSetDevice(ctx->device));
   auto t0 = std::chrono::steady_clock::now();
   cudaStream_t st = ctx->stream;
@@ -654,6 +657,13 @@ void solve_lp(mipcu_ctx* ctx, mipcu_stats* out) {
     MIPCU_CK(cudaEventSynchronize(ev_slot[slot]));
     last = ctx->h_sc[slot];
     ++blocks_seen;
+    if (last.fault) {
+      // every later kernel of the queue falls through on the flag: drain, then report (p2p.cu:own_barrier)
+      MIPCU_CK(cudaStreamSynchronize(st));
+      throw Error("mipcu_solve_lp: a peer rank did not arrive at a cross-GPU barrier within " +
+                  std::to_string(ctx->params[MIPCU_PARAM_PEER_TIMEOUT]) +
+                  " s (MIPCU_PARAM_PEER_TIMEOUT): row-sharded load and solve are collective and fail-stop");
+    }
     if (!use_graph && !last.done) {
       float a = 0.f, b = 0.f;
       MIPCU_CK(cudaEventElapsedTime(&a, ev_time[slot][0], ev_time[slot][1]));

@@ -59,7 +59,9 @@ CudaBranchAndBound::CudaBranchAndBound(CudaSolver& solver) : S(solver)
     is_int[j] = S.m_columns[j].type != Var::Type::Continuous;
     if (!is_int[j]) pure_integer = false;
     if (cost[j] != 0 && (!is_int[j] || !integral(cost[j]))) objective_integral = false;
+    cost_norm += cost[j] * cost[j];
   }
+  cost_norm = std::sqrt(cost_norm);
 }
 
 // CSC of the rows (which rows to revisit when a column's box shrinks)
@@ -449,16 +451,22 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
     return a.bound != b.bound ? a.bound > b.bound : a.depth < b.depth;
   };
   std::priority_queue<Node, std::vector<Node>, decltype(by_bound)> open(by_bound);
-  open.push(Node{{}, -kInf, 0, {}, {}});
+  open.push(Node{{}, -kInf, 0, nullptr, nullptr, 0.0});
   bool complete = true;
   bool unbounded_relaxation = false;
   std::int64_t const node_limit = 4000000;
   std::size_t const per_gpu = 128;                       // node LPs per GPU per round
   std::size_t const round_cap = per_gpu * gpus.size();
 
-  struct Pending { Node node; std::vector<double> lb, ub; double cut; };
+  // finite_box: every column of the node's box has two finite bounds.  Only then is the engine's dual
+  // objective a Lagrangian bound valid for ANY multiplier; with a free or one-sided column the reduced
+  // costs on the infinite side are counted into the dual residual instead (solve.cu: Q_DRES2), so the
+  // dual objective may overshoot the node optimum by about that residual times |x|.
+  struct Pending { Node node; std::vector<double> lb, ub; double cut; bool finite_box; };
   std::vector<Pending> round;
-  std::vector<double> box_lb, box_ub, cuts, xs;
+  std::vector<double> box_lb, box_ub, cuts, xs, ys, x0s, y0s, w0s;
+  // parents' solutions ride on the open nodes only while that stays cheap on the host
+  std::size_t const warm_budget_bytes = std::size_t(2) << 30;
   std::vector<mipcu_stats> stats;
   while (!open.empty())
   {
@@ -483,7 +491,7 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
       open.pop();
       if (node.bound >= cutoff()) continue;            // best-first: cannot improve the incumbent
       S.m_info.nodes += 1;
-      Pending p{std::move(node), root_lb, root_ub, kInf};
+      Pending p{std::move(node), root_lb, root_ub, kInf, true};
       for (Change const& c : p.node.changes) { p.lb[c.col] = c.lb; p.ub[c.col] = c.ub; }
       if (!propagate(p.lb, p.ub)) continue;
       if (all_fixed(p.lb, p.ub))
@@ -500,15 +508,35 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
     cuts.resize(B);
     stats.assign(B, mipcu_stats{});
     xs.resize(B * n);
+    ys.resize(B * m);
+    x0s.assign(B * n, 0.0);
+    y0s.assign(B * m, 0.0);
+    w0s.assign(B, 0.0);
     for (std::size_t b = 0; b < B; ++b)
     {
-      double const umax = box_objective_max(round[b].lb, round[b].ub);
-      double const cut = std::min(cutoff(), std::isinf(umax) ? kInf : umax + 1e-6 * (1.0 + std::abs(umax)));
-      cuts[b] = std::isinf(cut) ? std::nan("") : sgn * cut;
+      Pending& p = round[b];
+      for (std::size_t j = 0; j < n && p.finite_box; ++j)
+        p.finite_box = !std::isinf(p.lb[j]) && !std::isinf(p.ub[j]);
+      if (p.finite_box)
+      {
+        // a dual bound above the largest objective value the box allows proves the node LP infeasible
+        double const umax = box_objective_max(p.lb, p.ub);
+        double const cut = std::min(cutoff(), std::isinf(umax) ? kInf : umax + 1e-6 * (1.0 + std::abs(umax)));
+        cuts[b] = std::isinf(cut) ? std::nan("") : sgn * cut;
+      }
+      else
+        cuts[b] = std::nan("");      // no early stop on a bound that may overshoot: decided after the solve
       for (std::size_t j = 0; j < n; ++j)
       {
-        box_lb[b * n + j] = std::isinf(round[b].lb[j]) ? -inf : round[b].lb[j];
-        box_ub[b * n + j] = std::isinf(round[b].ub[j]) ? inf : round[b].ub[j];
+        box_lb[b * n + j] = std::isinf(p.lb[j]) ? -inf : p.lb[j];
+        box_ub[b * n + j] = std::isinf(p.ub[j]) ? inf : p.ub[j];
+      }
+      // start from the parent's LP solution (rows may have joined the model since: then only x)
+      if (p.node.x && p.node.x->size() == n)
+      {
+        std::copy(p.node.x->begin(), p.node.x->end(), x0s.begin() + b * n);
+        if (p.node.y && p.node.y->size() == m) std::copy(p.node.y->begin(), p.node.y->end(), y0s.begin() + b * m);
+        w0s[b] = p.node.weight;
       }
     }
     // deal the round to the GPUs: nodes are independent, no device-side exchange
@@ -523,9 +551,10 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
           mipcu_ctx* ctx = gpus[g];
           if (S.m_time_limit > 0)
             mipcu_set_param(ctx, MIPCU_PARAM_TIME_LIMIT, std::max(0.01, S.m_time_limit - elapsed()));
-          if (mipcu_solve_lp_batch(ctx, static_cast<std::int32_t>(b1 - b0), box_lb.data() + b0 * n,
-                                   box_ub.data() + b0 * n, cuts.data() + b0, stats.data() + b0,
-                                   xs.data() + b0 * n))
+          if (mipcu_solve_lp_batch_warm(ctx, static_cast<std::int32_t>(b1 - b0), box_lb.data() + b0 * n,
+                                        box_ub.data() + b0 * n, cuts.data() + b0, x0s.data() + b0 * n,
+                                        y0s.data() + b0 * m, w0s.data() + b0, stats.data() + b0,
+                                        xs.data() + b0 * n, ys.data() + b0 * m))
             errors[g] = mipcu_last_error(ctx);
         };
         if (G == 1) job(); else workers.emplace_back(job);
@@ -562,9 +591,25 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
       double node_bound = node.bound;
       if (lp.status == MIPCU_OPTIMAL)
       {
-        double const d = sgn * lp.dual_obj;
-        node_bound = std::max(node_bound, d - 1e-6 * (1.0 + std::abs(d)));
-        if (objective_integral) node_bound = std::ceil(node_bound - 1e-9);
+        double const d = sgn * lp.dual_obj, p = sgn * lp.primal_obj;
+        double const tol = std::max(1e-6, S.m_feas_tol);
+        if (round[b].finite_box)
+        {
+          node_bound = std::max(node_bound, d - tol * (1.0 + std::abs(d)));
+          if (objective_integral) node_bound = std::ceil(node_bound - 1e-9);
+        }
+        else
+        {
+          // the dual objective is exact only up to the reduced-cost violations on infinite sides:
+          // (absolute dual residual) x (norm of the columns that have such a side), plus the gap tolerance
+          double xfree = 0;
+          for (std::size_t j = 0; j < n; ++j)
+            if (std::isinf(lb[j]) || std::isinf(ub[j])) xfree += x[j] * x[j];
+          double const slack = 2.0 * tol * (1.0 + std::abs(p) + std::abs(d)) +
+                               2.0 * lp.rel_dual_res * (1.0 + cost_norm) * std::sqrt(xfree);
+          node_bound = std::max(node_bound, d - slack);
+          if (objective_integral) node_bound = std::ceil(node_bound - 1e-9);
+        }
         try_roundings(x, lb, ub);
         if (node_bound >= cutoff()) continue;
       }
@@ -591,6 +636,8 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
             {
               // the handlers cut this point off: solve the same box again under the new rows
               Node again;
+              again.x = std::make_shared<std::vector<double> const>(x);   // rows changed: the dual starts cold
+              again.weight = lp.primal_weight;
               for (std::size_t j = 0; j < n; ++j)
                 if (lb[j] != root_lb[j] || ub[j] != root_ub[j])
                   again.changes.push_back({static_cast<std::int32_t>(j), lb[j], ub[j]});
@@ -607,9 +654,18 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
         continue;
       }
       double const split = std::floor(x[pick]);
+      std::shared_ptr<std::vector<double> const> px, py;
+      if (lp.status == MIPCU_OPTIMAL && (open.size() + 2) * (n + m) * sizeof(double) <= warm_budget_bytes)
+      {
+        px = std::make_shared<std::vector<double> const>(x);
+        py = std::make_shared<std::vector<double> const>(ys.begin() + b * m, ys.begin() + (b + 1) * m);
+      }
       for (int side = 0; side < 2; ++side)
       {
         Node child;
+        child.x = px;
+        child.y = py;
+        child.weight = px ? lp.primal_weight : 0.0;
         // carry every bound propagation found, so the child starts from the tightened box
         for (std::size_t j = 0; j < n; ++j)
           if (lb[j] != root_lb[j] || ub[j] != root_ub[j])

@@ -17,6 +17,7 @@
 #pragma once
 
 #include <cstdint>
+#include <memory>
 #include <utility>
 #include <vector>
 
@@ -36,7 +37,10 @@ struct CudaBranchAndBound
     std::vector<Change> changes;   // bounds that differ from the root box
     double bound;                  // lower bound on the (minimisation-sense) objective
     int depth;
-    std::vector<double> x, y;      // parent LP solution: warm start
+    // parent LP solution (shared by both children) and the primal weight its solve ended with:
+    // the start point of this node's LP (mipcu_solve_lp_batch_warm)
+    std::shared_ptr<std::vector<double> const> x, y;
+    double weight = 0;
   };
 
   bool propagate(std::vector<double>& lb, std::vector<double>& ub) const;
@@ -62,6 +66,7 @@ struct CudaBranchAndBound
   bool have_incumbent = false;
   bool lazy_rejected = false, lazy_added = false;   // outcome of the last try_incumbent
   std::vector<double> best_x;
+  double cost_norm = 0;            // ||c||_2: turns the engine's relative dual residual back into an absolute one
 };
 
 }  // namespace miplib

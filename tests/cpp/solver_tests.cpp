@@ -112,6 +112,50 @@ GPU_TEST("KAT-D remove a constraint and re-solve (ref test/unit/solver.cpp:246-2
   REQUIRE(v2.value() == 1);
 }
 
+GPU_TEST("MIP with free continuous columns and an integral objective: the dual bound is not trusted blindly")
+{
+  // with a free (or one-sided) column the engine's dual objective prices only finite
+  // bounds, so it may overshoot the node optimum by about eps (1 + |p| + |d|); rounding it up for an
+  // integral objective could then cut off the node that holds the optimum.  Here every node LP of the
+  // optimal branch has an INTEGRAL optimum (3, 7): the worst case for ceil().
+  {
+    Solver solver(B, false);
+    Var x1(solver, Var::Type::Integer, 0, 10, "x1");
+    Var x2(solver, Var::Type::Integer, 0, 10, "x2");
+    Var t(solver, Var::Type::Continuous, std::nullopt, std::nullopt, "t");     // free
+    Var s(solver, Var::Type::Continuous, 0, std::nullopt, "s");                // one-sided
+    solver.add(x1 + x2 + t >= 3);
+    solver.add(t <= 0);
+    solver.add(x1 - x2 + s == 1);
+    solver.add(s <= 4);
+    auto [r, has_solution] = solver.minimize(x1 + x2);
+    REQUIRE(r == Solver::Result::Optimal);
+    REQUIRE(has_solution);
+    REQUIRE(std::abs(solver.get_objective_value() - 3) < 1e-9);
+    REQUIRE(x1.value() + x2.value() == 3);
+    REQUIRE(t.value() <= 1e-6);
+  }
+  {
+    Solver solver(B, false);
+    std::vector<Var> x;
+    Expr cover, weight;
+    for (int j = 0; j < 6; ++j)
+    {
+      x.emplace_back(solver, Var::Type::Binary, std::nullopt, std::nullopt, "x" + std::to_string(j));
+      cover += (j + 1) * x.back();
+      weight += x.back();
+    }
+    Var slack(solver, Var::Type::Continuous, std::nullopt, std::nullopt, "slack");   // free, zero cost
+    solver.add(cover + slack >= 10.5);
+    solver.add(slack <= 0.5);
+    solver.add(slack >= -100);
+    auto [r, has_solution] = solver.minimize(weight);      // fewest items with 1 x1 + ... + 6 x6 >= 10
+    REQUIRE(r == Solver::Result::Optimal);
+    REQUIRE(has_solution);
+    REQUIRE(std::abs(solver.get_objective_value() - 2) < 1e-9);    // 6 + 4 or 6 + 5
+  }
+}
+
 GPU_TEST("Continuous LP through the expression API: a textbook optimum")
 {
   // max 3x + 2y  s.t. x + y <= 4, x + 3y <= 6, x <= 3, x,y >= 0  ->  (3,1), 11

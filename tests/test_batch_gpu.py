@@ -136,3 +136,41 @@ def test_batch_throughput_vs_serial(built):
           f"iterations max {max(s.iterations for s in stats)}")
     assert sum(s.status == "optimal" for s in stats) >= B // 2
     assert t_batch < t_serial
+
+
+def test_batch_warm_start_from_the_parent(built):
+    """mipcu_solve_lp_batch_warm: node LPs started from the root relaxation's (x, y, primal weight)
+    reach the same optima as from zero in fewer iterations, and the returned duals certify them."""
+    from miplib_b200 import Engine
+    from oracle import kkt_verify
+    L = gen.set_cover(2000, 5000, 8, 20264)
+    rng = np.random.default_rng(7)
+    B = 40
+    lb, ub = node_boxes(L, B, rng, 8)
+    with Engine(0) as e:
+        e.load_lp(L)
+        e.set_param("iter_limit", 60000)
+        root = e.solve()
+        xr, yr = e.x(), e.y()
+        cold, xc = e.solve_batch(lb, ub)
+        warm, xw, yw = e.solve_batch(lb, ub, x0=np.tile(xr, (B, 1)), y0=np.tile(yr, (B, 1)),
+                                     weight0=np.full(B, root.primal_weight), want_y=True)
+        # zeros as start point = the cold path, bit for bit
+        zero, xz, _ = e.solve_batch(lb, ub, x0=np.zeros((B, L.n)), y0=np.zeros((B, L.m)), want_y=True)
+    assert root.status == "optimal"
+    both = [b for b in range(B) if cold[b].status == "optimal" and warm[b].status == "optimal"]
+    assert len(both) >= B - 2
+    assert warm[0].status == "optimal" and warm[0].iterations <= 128          # node 0 is the root itself
+    for b in both:
+        assert rel(warm[b].primal_obj, cold[b].primal_obj) <= 3e-6, (b, warm[b].primal_obj, cold[b].primal_obj)
+        Lb = gen.LP(L.A, L.c, lb[b], ub[b], L.row_lo, L.row_hi, L.maximize)
+        cert = kkt_verify.certificate(Lb, xw[b], yw[b])
+        assert max(cert["rel_primal_res"], cert["rel_dual_res"], cert["rel_gap"]) <= 1.05e-6, (b, cert)
+    it_cold = sum(cold[b].iterations for b in both)
+    it_warm = sum(warm[b].iterations for b in both)
+    print(f"iterations cold {it_cold} warm {it_warm}")
+    assert it_warm < 0.7 * it_cold
+    for b in range(B):
+        assert zero[b].iterations == cold[b].iterations and zero[b].status == cold[b].status
+        assert np.array_equal(xz[b], xc[b])
+    assert warm[0].row_kernel_us > 0 and warm[0].col_kernel_bytes > 0

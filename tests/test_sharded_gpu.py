@@ -18,6 +18,12 @@ def _worker(rank, world, uid, which, exchange, out):
         e.set_param("shard_exchange", exchange)       # 2: block-owner, 1: fused P2P kernel, 0: ncclAllReduce
         e.load(ptr, idx, val, L.c, L.lb, L.ub, lo, hi, L.maximize, n=L.n)
         assert e.get_param("shard_exchange") == exchange      # no silent fall-back to NCCL
+        if which == "small":
+            # a solve, then a re-load of the same shape: the peer mappings (and the multicast window)
+            # are kept, only the matrix-dependent parts are rebuilt; the solve below must not notice
+            e.solve()
+            e.load(ptr, idx, val, L.c, L.lb, L.ub, lo, hi, L.maximize, n=L.n)
+            assert e.get_param("shard_exchange") == exchange
         st = e.solve()
         out[rank] = (st.status, st.primal_obj, st.iterations, st.restarts, e.x(), e.y(),
                      st.rel_primal_res, st.rel_gap)
