@@ -108,6 +108,10 @@ typedef struct mipcu_stats {
 int  mipcu_device_count(void);                         /* usable sm_100 devices; 0 if none */
 int  mipcu_create(mipcu_ctx** out, int device);        /* one context = one GPU */
 void mipcu_destroy(mipcu_ctx* ctx);
+/* forget the loaded model and restore every parameter to its default; the device memory the model
+ * held stays in the context's pool, so the next mipcu_load_lp of a similar size costs no allocation
+ * (what lets an adapter recycle contexts between Solver objects).  Not for row-sharded contexts. */
+int  mipcu_reset(mipcu_ctx* ctx);
 const char* mipcu_last_error(const mipcu_ctx* ctx);    /* ctx may be NULL: last create() error */
 
 /* --- row-sharded contexts (one process per GPU, one NCCL communicator) ---------------------- *

@@ -96,6 +96,7 @@ def load_library() -> C.CDLL:
         "mipcu_device_count": (C.c_int, []),
         "mipcu_create": (C.c_int, [P(vp), C.c_int]),
         "mipcu_destroy": (None, [vp]),
+        "mipcu_reset": (C.c_int, [vp]),
         "mipcu_last_error": (C.c_char_p, [vp]),
         "mipcu_dist_unique_id": (C.c_int, [vp]),
         "mipcu_create_sharded": (C.c_int, [P(vp), C.c_int, C.c_int, C.c_int, vp]),

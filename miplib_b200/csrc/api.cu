@@ -187,6 +187,18 @@ void mipcu_destroy(mipcu_ctx* ctx) {
   delete ctx;
 }
 
+int mipcu_reset(mipcu_ctx* ctx) {
+  if (!ctx) return 1;
+  return guarded(ctx, [&] {
+    MIPCU_REQUIRE(ctx->world <= 1, "mipcu_reset: not supported on row-sharded contexts");
+    MIPCU_CK(cudaSetDevice(ctx->device));
+    MIPCU_CK(cudaStreamSynchronize(ctx->stream));
+    free_model(ctx);
+    set_default_params(ctx);
+    ctx->err.clear();
+  });
+}
+
 const char* mipcu_last_error(const mipcu_ctx* ctx) {
   if (ctx) return ctx->err.c_str();
   // a copy private to the calling thread: the pointer stays valid after the lock is released

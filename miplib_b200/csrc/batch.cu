@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "internal.h"
@@ -48,10 +49,24 @@ struct BatchArgs {
 // load depends on another load, so the 256-byte gathers of four nonzeros are in flight together
 // (the round-1 version read val[k] / idx[k] warp-uniformly: a dependent chain of two loads per
 // nonzero, 41 node LPs/s on config 4).  Fixed summation order.
+__device__ int g_batch_scalar_loads = 0;   // laboratory switch (MIPCU_BATCH_SCALAR=1): the round-1 inner loop
+
 __device__ __forceinline__ double row_dot_batch(const int* __restrict__ ptr, const int* __restrict__ idx,
                                                 const double* __restrict__ val,
                                                 const double* __restrict__ vec, int row, int BP, int b) {
   const int beg = ptr[row], end = ptr[row + 1];
+  if (g_batch_scalar_loads) {
+    double a0 = 0.0, a1 = 0.0;
+    int k = beg;
+    for (; k + 1 < end; k += 2) {
+      const double v0 = val[k], v1 = val[k + 1];
+      const int c0 = idx[k], c1 = idx[k + 1];
+      a0 = fma(v0, vec[(size_t)c0 * BP + b], a0);
+      a1 = fma(v1, vec[(size_t)c1 * BP + b], a1);
+    }
+    if (k < end) a0 = fma(val[k], vec[(size_t)idx[k] * BP + b], a0);
+    return a0 + a1;
+  }
   const int lane = threadIdx.x & 31;
   double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
   for (int base = beg; base < end; base += 32) {
@@ -515,6 +530,11 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
   auto t0 = std::chrono::steady_clock::now();
   cudaStream_t st = ctx->stream;
   ctx->launches = 0;
+  {
+    const char* v = std::getenv("MIPCU_BATCH_SCALAR");
+    const int scalar = v ? std::atoi(v) : 0;
+    MIPCU_CK(cudaMemcpyToSymbolAsync(g_batch_scalar_loads, &scalar, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+  }
   if (!ctx->d_sc) MIPCU_CK(cudaMalloc(&ctx->d_sc, sizeof(Scalars)));
   if (!ctx->h_sc) MIPCU_CK(cudaMallocHost(&ctx->h_sc, sizeof(Scalars) * 2));
   for (auto& e : ctx->ev)

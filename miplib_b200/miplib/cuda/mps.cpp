@@ -62,7 +62,7 @@ void CudaSolver::read_mps(Solver const& solver, std::string const& path)
   struct Row { char sense; std::vector<std::pair<std::int32_t, double>> entries; double rhs = 0, range = NAN; };
   std::vector<Row> rows;                                   // constraint rows, file order
   std::unordered_map<std::string, std::int64_t> row_of;   // name -> index into rows, -1 objective, -2 ignored
-  struct Col { double cost = 0, lb = 0, ub = INFINITY; bool integer = false, binary = false, ub_set = false; };
+  struct Col { double cost = 0, lb = 0, ub = INFINITY; bool integer = false, binary = false, bounded = false; };
   std::vector<Col> cols;
   std::unordered_map<std::string, std::int32_t> col_of;
   std::vector<std::string> col_names;
@@ -168,21 +168,25 @@ void CudaSolver::read_mps(Solver const& solver, std::string const& path)
       }
       case Bounds:
       {
-        if (tok.size() < 2) bad(path, line, "expected '<type> [set] column [value]'");
+        if (tok.size() < 2 || tok.size() > 4) bad(path, line, "expected '<type> [set] column [value]'");
         std::string const& type = tok[0];
         bool const needs_value = type == "UP" || type == "LO" || type == "FX" || type == "LI" || type == "UI";
-        // '<type> set column value' or '<type> column value'; '<type> set column' or '<type> column'
-        std::size_t const name_at = tok.size() - (needs_value ? 2 : 1);
+        // '<type> [set] column value' for the valued types.  BV / FR / MI / PL take no value, but some
+        // writers (CPLEX, SCIP) add one anyway: '<type> [set] column [ignored]' - the column is
+        // whichever of the candidate positions names one
+        std::size_t name_at = tok.size() - (needs_value ? 2 : 1);
+        if (!needs_value && tok.size() >= 3 && !col_of.count(tok[name_at]) && col_of.count(tok[name_at - 1]))
+          name_at -= 1;                                  // trailing value field
         if (name_at < 1 || name_at > 2) bad(path, line, "malformed bound");
         auto c = col_of.find(tok[name_at]);
         if (c == col_of.end()) bad(path, line, "unknown column " + tok[name_at]);
         Col& col = cols[c->second];
         double const v = needs_value ? number(tok.back(), path, line) : 0.0;
+        col.bounded = true;
         if (type == "UP" || type == "UI")
         {
           if (v < 0 && col.lb == 0) col.lb = -INFINITY;
           col.ub = v;
-          col.ub_set = true;
           if (type == "UI") col.integer = true;
         }
         else if (type == "LO" || type == "LI")
@@ -190,11 +194,11 @@ void CudaSolver::read_mps(Solver const& solver, std::string const& path)
           col.lb = v;
           if (type == "LI") col.integer = true;
         }
-        else if (type == "FX") { col.lb = col.ub = v; col.ub_set = true; }
+        else if (type == "FX") col.lb = col.ub = v;
         else if (type == "FR") { col.lb = -INFINITY; col.ub = INFINITY; }
         else if (type == "MI") col.lb = -INFINITY;
         else if (type == "PL") col.ub = INFINITY;
-        else if (type == "BV") { col.lb = 0; col.ub = 1; col.integer = col.binary = true; col.ub_set = true; }
+        else if (type == "BV") { col.lb = 0; col.ub = 1; col.integer = col.binary = true; }
         else bad(path, line, "unknown bound type " + type);
         break;
       }
@@ -233,8 +237,11 @@ void CudaSolver::read_mps(Solver const& solver, std::string const& path)
     lo.push_back(l);
     hi.push_back(h);
   }
-  for (Col const& col : cols)
+  for (Col& col : cols)
   {
+    // an integer column declared only by 'MARKER' lines, with no BOUNDS entry at all, is binary:
+    // the convention of CPLEX, SCIP and HiGHS (whose reader the tests compare with)
+    if (col.integer && !col.bounded) col.ub = 1;
     c.push_back(col.cost);
     lb.push_back(std::isinf(col.lb) ? (col.lb < 0 ? -inf : inf) : col.lb);
     ub.push_back(std::isinf(col.ub) ? (col.ub < 0 ? -inf : inf) : col.ub);

@@ -20,6 +20,7 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <mutex>
 #include <numeric>
 #include <sstream>
 #include <stdexcept>
@@ -45,10 +46,53 @@ void check(mipcu_ctx* ctx, int rc)
 
 CudaSolver::CudaSolver(bool verbose) : m_verbose(verbose) {}
 
+// Engine contexts outlive the solver objects that used them: a context owns a CUDA stream and a
+// device memory pool that keeps what a model freed, and building those anew costs far more than
+// re-loading a model into a warm one (config 3: ~0.7 s against ~0.05 s).  A program that creates one
+// Solver per model - the reference's usage, README.md:24-60 - therefore gets its next context out of
+// this per-device cache, reset to default parameters with no model loaded.
+namespace {
+std::mutex g_ctx_cache_mutex;
+std::vector<std::pair<int, mipcu_ctx*>> g_ctx_cache;     // (device, context)
+constexpr std::size_t kCtxCacheMax = 16;
+
+mipcu_ctx* acquire_context(int device)
+{
+  {
+    std::lock_guard<std::mutex> lock(g_ctx_cache_mutex);
+    for (std::size_t i = 0; i < g_ctx_cache.size(); ++i)
+      if (g_ctx_cache[i].first == device)
+      {
+        mipcu_ctx* ctx = g_ctx_cache[i].second;
+        g_ctx_cache.erase(g_ctx_cache.begin() + static_cast<std::ptrdiff_t>(i));
+        return ctx;
+      }
+  }
+  mipcu_ctx* ctx = nullptr;
+  if (mipcu_create(&ctx, device)) fail(std::string("Cuda backend: ") + mipcu_last_error(nullptr));
+  return ctx;
+}
+
+void release_context(int device, mipcu_ctx* ctx)
+{
+  if (!ctx) return;
+  if (mipcu_reset(ctx) == 0)
+  {
+    std::lock_guard<std::mutex> lock(g_ctx_cache_mutex);
+    if (g_ctx_cache.size() < kCtxCacheMax)
+    {
+      g_ctx_cache.emplace_back(device, ctx);
+      return;
+    }
+  }
+  mipcu_destroy(ctx);
+}
+}  // namespace
+
 CudaSolver::~CudaSolver()
 {
-  for (mipcu_ctx* ctx : m_extra_ctx) mipcu_destroy(ctx);
-  if (m_ctx) mipcu_destroy(m_ctx);
+  for (std::size_t g = 0; g < m_extra_ctx.size(); ++g) release_context(static_cast<int>(g + 1), m_extra_ctx[g]);
+  release_context(0, m_ctx);
 }
 
 bool CudaSolver::is_available() { return mipcu_device_count() > 0; }
@@ -242,19 +286,9 @@ void CudaSolver::load_csr(Solver const&, std::int64_t m, std::int64_t n, std::in
   if (row_ptr[0] != 0 || (row_ptr[m] > 0 && (!col_idx || !val))) fail("miplib_cuda_load_csr: bad row_ptr");
   std::size_t const first = m_columns.size();
   double const inf = infinity();
-  m_columns.reserve(first + static_cast<std::size_t>(n));
-  for (std::int64_t j = 0; j < n; ++j)
-  {
-    Column col;
-    int const t = var_type ? var_type[j] : 0;
-    if (t < 0 || t > 2) fail("miplib_cuda_load_csr: unknown variable type");
-    col.type = static_cast<Var::Type>(t);
-    col.lb = col.type == Var::Type::Binary ? 0.0 : std::max(lb[j], -inf);
-    col.ub = col.type == Var::Type::Binary ? 1.0 : std::min(ub[j], inf);
-    m_columns.push_back(col);
-  }
-  m_row_idx.reserve(m_row_idx.size() + static_cast<std::size_t>(row_ptr[m]));
-  m_row_val.reserve(m_row_val.size() + static_cast<std::size_t>(row_ptr[m]));
+  // validate everything before the row store is touched: a bad array must not leave half a model behind
+  for (std::int64_t j = 0; j < n && var_type; ++j)
+    if (var_type[j] < 0 || var_type[j] > 2) fail("miplib_cuda_load_csr: unknown variable type");
   for (std::int64_t i = 0; i < m; ++i)
   {
     std::int32_t prev = -1;
@@ -264,14 +298,35 @@ void CudaSolver::load_csr(Solver const&, std::int64_t m, std::int64_t n, std::in
       if (col_idx[k] <= prev || col_idx[k] >= n)
         fail("miplib_cuda_load_csr: column indices must be increasing inside a row and below n");
       prev = col_idx[k];
-      m_row_idx.push_back(static_cast<std::int32_t>(first) + col_idx[k]);
-      m_row_val.push_back(val[k]);
     }
-    m_row_start.push_back(static_cast<std::int64_t>(m_row_idx.size()));
+  }
+  m_columns.reserve(first + static_cast<std::size_t>(n));
+  for (std::int64_t j = 0; j < n; ++j)
+  {
+    Column col;
+    col.type = static_cast<Var::Type>(var_type ? var_type[j] : 0);
+    col.lb = col.type == Var::Type::Binary ? 0.0 : std::max(lb[j], -inf);
+    col.ub = col.type == Var::Type::Binary ? 1.0 : std::min(ub[j], inf);
+    m_columns.push_back(col);
+  }
+  m_row_idx.reserve(m_row_idx.size() + static_cast<std::size_t>(row_ptr[m]));
+  m_row_val.reserve(m_row_val.size() + static_cast<std::size_t>(row_ptr[m]));
+  std::int64_t const nnz_before = static_cast<std::int64_t>(m_row_idx.size());
+  m_row_idx.insert(m_row_idx.end(), col_idx, col_idx + row_ptr[m]);
+  if (first)
+    for (std::size_t k = static_cast<std::size_t>(nnz_before); k < m_row_idx.size(); ++k)
+      m_row_idx[k] += static_cast<std::int32_t>(first);
+  m_row_val.insert(m_row_val.end(), val, val + row_ptr[m]);
+  m_row_start.reserve(m_row_start.size() + static_cast<std::size_t>(m));
+  m_row_lo.reserve(m_row_lo.size() + static_cast<std::size_t>(m));
+  m_row_hi.reserve(m_row_hi.size() + static_cast<std::size_t>(m));
+  for (std::int64_t i = 0; i < m; ++i)
+  {
+    m_row_start.push_back(nnz_before + row_ptr[i + 1]);
     m_row_lo.push_back(std::max(row_lo[i], -inf));
     m_row_hi.push_back(std::min(row_hi[i], inf));
-    m_row_alive.push_back(1);
   }
+  m_row_alive.insert(m_row_alive.end(), static_cast<std::size_t>(m), char(1));
   m_objective.assign(m_columns.size(), 0.0);
   for (std::int64_t j = 0; j < n; ++j) m_objective[first + static_cast<std::size_t>(j)] = c[j];
   m_sense = maximize ? Solver::Sense::Maximize : Solver::Sense::Minimize;
@@ -443,7 +498,7 @@ void CudaSolver::dump(std::string const& filename) const
 void CudaSolver::ensure_context()
 {
   if (m_ctx) return;
-  if (mipcu_create(&m_ctx, 0)) fail(std::string("Cuda backend: ") + mipcu_last_error(nullptr));
+  m_ctx = acquire_context(0);
 }
 
 void CudaSolver::upload_model()
@@ -454,35 +509,54 @@ void CudaSolver::upload_model()
   bool const maximize = m_sense == Solver::Sense::Maximize;
   if (m_structure_dirty)
   {
-    std::vector<std::int64_t> ptr{0};
-    std::vector<std::int32_t> idx;
-    std::vector<double> val, lo, hi, lb(n), ub(n);
-    m_device_row_of.clear();
-    idx.reserve(m_row_idx.size());
-    val.reserve(m_row_val.size());
-    for (std::size_t r = 0; r < m_row_alive.size(); ++r)
-    {
-      if (!m_row_alive[r]) continue;
-      idx.insert(idx.end(), m_row_idx.begin() + m_row_start[r], m_row_idx.begin() + m_row_start[r + 1]);
-      val.insert(val.end(), m_row_val.begin() + m_row_start[r], m_row_val.begin() + m_row_start[r + 1]);
-      ptr.push_back(static_cast<std::int64_t>(idx.size()));
-      lo.push_back(m_row_lo[r]);
-      hi.push_back(m_row_hi[r]);
-      m_device_row_of.push_back(static_cast<std::int64_t>(r));
-    }
+    std::vector<double> lb(n), ub(n);
     for (std::size_t j = 0; j < n; ++j)
     {
       lb[j] = m_columns[j].lb;
       ub[j] = m_columns[j].ub;
     }
-    check(m_ctx, mipcu_load_lp(m_ctx, static_cast<std::int64_t>(lo.size()), static_cast<std::int64_t>(n),
-                               static_cast<std::int64_t>(idx.size()), ptr.data(), idx.data(), val.data(),
-                               m_objective.data(), lb.data(), ub.data(), lo.data(), hi.data(), maximize));
-    m_last_ptr.swap(ptr);
-    m_last_idx.swap(idx);
-    m_last_val.swap(val);
-    m_last_lo.swap(lo);
-    m_last_hi.swap(hi);
+    bool const all_alive = std::find(m_row_alive.begin(), m_row_alive.end(), char(0)) == m_row_alive.end();
+    m_device_row_of.clear();
+    if (all_alive)
+    {
+      // the row store IS the CSR the engine wants: hand it over as it is
+      m_device_row_of.resize(m_row_alive.size());
+      std::iota(m_device_row_of.begin(), m_device_row_of.end(), std::int64_t(0));
+      std::vector<std::int64_t>().swap(m_last_ptr);
+      std::vector<std::int32_t>().swap(m_last_idx);
+      std::vector<double>().swap(m_last_val);
+      std::vector<double>().swap(m_last_lo);
+      std::vector<double>().swap(m_last_hi);
+      m_up = UploadedCsr{m_row_start.data(), m_row_idx.data(), m_row_val.data(), m_row_lo.data(), m_row_hi.data(),
+                         m_row_lo.size(), m_row_idx.size()};
+    }
+    else
+    {
+      std::vector<std::int64_t> ptr{0};
+      std::vector<std::int32_t> idx;
+      std::vector<double> val, lo, hi;
+      idx.reserve(m_row_idx.size());
+      val.reserve(m_row_val.size());
+      for (std::size_t r = 0; r < m_row_alive.size(); ++r)
+      {
+        if (!m_row_alive[r]) continue;
+        idx.insert(idx.end(), m_row_idx.begin() + m_row_start[r], m_row_idx.begin() + m_row_start[r + 1]);
+        val.insert(val.end(), m_row_val.begin() + m_row_start[r], m_row_val.begin() + m_row_start[r + 1]);
+        ptr.push_back(static_cast<std::int64_t>(idx.size()));
+        lo.push_back(m_row_lo[r]);
+        hi.push_back(m_row_hi[r]);
+        m_device_row_of.push_back(static_cast<std::int64_t>(r));
+      }
+      m_last_ptr.swap(ptr);
+      m_last_idx.swap(idx);
+      m_last_val.swap(val);
+      m_last_lo.swap(lo);
+      m_last_hi.swap(hi);
+      view_last();
+    }
+    check(m_ctx, mipcu_load_lp(m_ctx, static_cast<std::int64_t>(m_up.m), static_cast<std::int64_t>(n),
+                               static_cast<std::int64_t>(m_up.nnz), m_up.ptr, m_up.idx, m_up.val,
+                               m_objective.data(), lb.data(), ub.data(), m_up.lo, m_up.hi, maximize));
     m_structure_dirty = false;
     m_objective_dirty = false;
     m_dirty_columns.clear();
@@ -534,9 +608,16 @@ void CudaSolver::upload_rows(std::vector<std::int64_t> const& ptr, std::vector<s
   m_last_val = val;
   m_last_lo = lo;
   m_last_hi = hi;
+  view_last();
   m_structure_dirty = true;   // the device no longer holds the user's own rows
   m_objective_dirty = false;
   m_dirty_columns.clear();
+}
+
+void CudaSolver::view_last()
+{
+  m_up = UploadedCsr{m_last_ptr.data(), m_last_idx.data(), m_last_val.data(), m_last_lo.data(), m_last_hi.data(),
+                     m_last_lo.size(), m_last_idx.size()};
 }
 
 std::vector<mipcu_ctx*> CudaSolver::node_contexts()
@@ -555,14 +636,14 @@ std::vector<mipcu_ctx*> CudaSolver::node_contexts()
     if (m_extra_ctx.size() < g)
     {
       mipcu_ctx* ctx = nullptr;
-      if (mipcu_create(&ctx, static_cast<int>(g))) fail(std::string("Cuda backend: ") + mipcu_last_error(nullptr));
+      ctx = acquire_context(static_cast<int>(g));
       m_extra_ctx.push_back(ctx);
     }
     mipcu_ctx* ctx = m_extra_ctx[g - 1];
-    check(ctx, mipcu_load_lp(ctx, static_cast<std::int64_t>(m_last_lo.size()), static_cast<std::int64_t>(n),
-                             static_cast<std::int64_t>(m_last_idx.size()), m_last_ptr.data(), m_last_idx.data(),
-                             m_last_val.data(), m_objective.data(), lb.data(), ub.data(), m_last_lo.data(),
-                             m_last_hi.data(), m_sense == Solver::Sense::Maximize));
+    check(ctx, mipcu_load_lp(ctx, static_cast<std::int64_t>(m_up.m), static_cast<std::int64_t>(n),
+                             static_cast<std::int64_t>(m_up.nnz), m_up.ptr, m_up.idx, m_up.val,
+                             m_objective.data(), lb.data(), ub.data(), m_up.lo, m_up.hi,
+                             m_sense == Solver::Sense::Maximize));
     all.push_back(ctx);
   }
   return all;
@@ -628,8 +709,10 @@ std::pair<Solver::Result, bool> CudaSolver::solve()
 // row and bound to 1e-9 and does not move the objective.  Anything else keeps the PDHG point.
 void CudaSolver::polish_vertex(std::vector<double>& x)
 {
-  std::size_t const n = m_columns.size(), m = m_last_lo.size();
-  if (n == 0 || m_last_ptr.size() != m + 1) return;
+  std::size_t const n = m_columns.size(), m = m_up.m;
+  if (n == 0 || !m_up.ptr) return;
+  // cheap way out before anything proportional to the model: far more columns than the limit
+  if (m_polish_limit == 0) return;
   double const inf = infinity(), tol = 1e-5;
   std::vector<double> snapped(x);
   std::vector<std::int32_t> free_of(n, -1);
@@ -649,12 +732,12 @@ void CudaSolver::polish_vertex(std::vector<double>& x)
   {
     double act = 0;
     bool touches_free = false;
-    for (std::int64_t k = m_last_ptr[r]; k < m_last_ptr[r + 1]; ++k)
+    for (std::int64_t k = m_up.ptr[r]; k < m_up.ptr[r + 1]; ++k)
     {
-      act += m_last_val[k] * x[m_last_idx[k]];
-      touches_free = touches_free || free_of[m_last_idx[k]] >= 0;
+      act += m_up.val[k] * x[m_up.idx[k]];
+      touches_free = touches_free || free_of[m_up.idx[k]] >= 0;
     }
-    double const lo = m_last_lo[r], hi = m_last_hi[r];
+    double const lo = m_up.lo[r], hi = m_up.hi[r];
     bool const at_hi = hi < inf && std::abs(act - hi) <= tol * (1 + std::abs(hi));
     bool const at_lo = lo > -inf && std::abs(act - lo) <= tol * (1 + std::abs(lo));
     if (!touches_free || !(at_hi || at_lo)) continue;
@@ -673,11 +756,11 @@ void CudaSolver::polish_vertex(std::vector<double>& x)
     {
       std::int32_t const r = R[i];
       double rhs = target[i];
-      for (std::int64_t k = m_last_ptr[r]; k < m_last_ptr[r + 1]; ++k)
+      for (std::int64_t k = m_up.ptr[r]; k < m_up.ptr[r + 1]; ++k)
       {
-        std::int32_t const f = free_of[m_last_idx[k]];
-        if (f >= 0) M[i * w + f] += m_last_val[k];
-        else rhs -= m_last_val[k] * snapped[m_last_idx[k]];
+        std::int32_t const f = free_of[m_up.idx[k]];
+        if (f >= 0) M[i * w + f] += m_up.val[k];
+        else rhs -= m_up.val[k] * snapped[m_up.idx[k]];
       }
       M[i * w + nf] = rhs;
     }
@@ -718,8 +801,8 @@ void CudaSolver::polish_vertex(std::vector<double>& x)
   for (std::size_t r = 0; r < m; ++r)
   {
     double act = 0;
-    for (std::int64_t k = m_last_ptr[r]; k < m_last_ptr[r + 1]; ++k) act += m_last_val[k] * cand[m_last_idx[k]];
-    double const lo = m_last_lo[r], hi = m_last_hi[r];
+    for (std::int64_t k = m_up.ptr[r]; k < m_up.ptr[r + 1]; ++k) act += m_up.val[k] * cand[m_up.idx[k]];
+    double const lo = m_up.lo[r], hi = m_up.hi[r];
     if (hi < inf && act > hi + 1e-9 * (1 + std::abs(hi))) return;
     if (lo > -inf && act < lo - 1e-9 * (1 + std::abs(lo))) return;
   }

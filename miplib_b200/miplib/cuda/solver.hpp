@@ -159,7 +159,21 @@ struct CudaSolver : detail::ISolver
 
   mipcu_ctx* m_ctx = nullptr;
   std::vector<mipcu_ctx*> m_extra_ctx;           // devices 1.. for dealing node LPs (set_nr_threads)
-  std::vector<std::int64_t> m_last_ptr;          // last uploaded CSR, kept to load the extra GPUs
+  // the CSR last handed to the device (extra GPUs are loaded from it, polish_vertex reads it).  When
+  // every row of the store is alive this is a VIEW of the row store itself - no second copy of a
+  // 32 M-nonzero model on the host; otherwise it points into the compacted m_last_* vectors.
+  struct UploadedCsr
+  {
+    std::int64_t const* ptr = nullptr;
+    std::int32_t const* idx = nullptr;
+    double const* val = nullptr;
+    double const* lo = nullptr;
+    double const* hi = nullptr;
+    std::size_t m = 0, nnz = 0;
+  };
+  UploadedCsr m_up;
+  void view_last();                              // m_up <- the m_last_* vectors
+  std::vector<std::int64_t> m_last_ptr;
   std::vector<std::int32_t> m_last_idx;
   std::vector<double> m_last_val, m_last_lo, m_last_hi;
   bool m_verbose;

@@ -316,6 +316,7 @@ COLUMNS
  i1 cost 1 eq1 2
  i1 rng3 1
  i2 lim2 1 rng4 4
+ i3 cost 2 lim1 1
  MARKER 'MARKER' 'INTEND'
  c lim1 -1 rng1 2.5
  d cost 0.25 rng2 1
@@ -338,11 +339,11 @@ BOUNDS
  LO bnd c -2.5
  UP bnd c 6
  FX bnd d 1.25
- FR bnd e
+ FR bnd e 0
  MI bnd f
  UP bnd f 9
- PL bnd g
- BV bnd h
+ PL g 1e30
+ BV bnd h 1
  LI bnd i1 -3
  UI bnd i1 5
  UP bnd i2 12
@@ -364,7 +365,7 @@ def test_mps_reader_agrees_with_highs_reader(built, golden, tmp_path):
     assert lib.miplib_cuda_read_mps(solver, str(src).encode()) == 0, lib.miplib_get_last_error()
     n, m = C.c_int64(), C.c_int64()
     assert lib.miplib_cuda_get_shape(solver, C.byref(n), C.byref(m)) == 0
-    assert (n.value, m.value) == (10, 7)
+    assert (n.value, m.value) == (11, 7)
     out = tmp_path / "hand_out.mps"
     assert lib.miplib_cuda_dump(solver, str(out).encode()) == 0, lib.miplib_get_last_error()
     assert lib.miplib_destroy_solver(solver) == 0
@@ -380,6 +381,9 @@ def test_mps_reader_agrees_with_highs_reader(built, golden, tmp_path):
     assert np.abs(got["lo"][fin] - want["lo"][fin]).max() <= 1e-12          # ranges are written as hi - lo
     assert np.array_equal(got["hi"][np.isfinite(want["hi"])], want["hi"][np.isfinite(want["hi"])])
     # what the file says, spelled out for the cases readers disagree on most often
+    i3 = 4                                                            # integer by MARKER only, no BOUNDS line: binary
+    assert want["integer"][i3] and (want["lb"][i3], want["ub"][i3]) == (0.0, 1.0)
+    assert (got["lb"][i3], got["ub"][i3]) == (0.0, 1.0)
     assert want["lb"][1] == -np.inf and want["ub"][1] == -1
     assert (want["lo"][3], want["hi"][3]) == (5.0, 8.0)               # L row with a range
     assert (want["lo"][4], want["hi"][4]) == (1.0, 3.5)               # G row with a range
@@ -451,3 +455,25 @@ def test_bulk_ingress_solves_lp_and_mip(built, golden):
         assert abs(obj.value - exp) <= 1e-6 * (1 + abs(exp))
         assert abs(float(L.c @ x) - obj.value) <= 1e-9 * (1 + abs(exp))
         assert lib.miplib_destroy_solver(solver) == 0
+
+
+def test_dumped_instances_are_pinned_by_checksum_and_solve_to_the_golden(built, golden, tmp_path):
+    """scripts/dump_instances.py: the config-1 / config-2 MPS files an external SCIP / lp_solve would
+    be run on.  Their SHA-256 is pinned in tests/golden/instances.json, the C1 file read back by an
+    independent reader (HiGHS) is the generator's model entry for entry, and an exact solve of the
+    FILE gives the golden objective - so a parity run elsewhere is a run on this instance."""
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    p = subprocess.run([sys.executable, str(root / "scripts" / "dump_instances.py"), "--configs", "1", "2",
+                        "--out", str(tmp_path), "--check"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    M = _read_mps_with_highs(tmp_path / "C1.mps")
+    L = gen.config(1)
+    A = L.A.tocsr(); A.sort_indices()
+    assert (M["A"] != A).nnz == 0
+    assert np.array_equal(M["c"], L.c) and np.array_equal(M["lb"], L.lb) and np.array_equal(M["ub"], L.ub)
+    assert np.array_equal(M["lo"], L.row_lo) and np.array_equal(M["hi"], L.row_hi)
+    M["h"].run()
+    obj = M["h"].getInfo().objective_function_value
+    assert abs(obj - golden["C1_lp"]["objective"]) <= 1e-9 * (1 + abs(obj))
