@@ -175,7 +175,9 @@ int  mipcu_get_scaling(mipcu_ctx* ctx, double* d1 /* m */, double* d2 /* n */);
  * and return the scaled iterates (xbar: n, y: m) - iterate-level parity against oracle/pdhg_ref */
 int  mipcu_debug_iterate(mipcu_ctx* ctx, int64_t iters, double* xbar_out, double* y_out);
 /* time `reps` back-to-back launches of one device-resident kernel with CUDA events on the
- * launching stream; which: 0 = plain K v, 1 = plain K' v, 2 = fused row step, 3 = fused col step.
+ * launching stream; which: 0 = plain K v, 1 = plain K' v, 2 = fused row step, 3 = fused col step,
+ * 4 = one whole iteration as shipped (row step + col step), 5 = the same iteration with what an adaptive
+ * step-size rule adds (per-iteration reductions in both epilogues + a single-CTA controller launch).
  * flush_l2 != 0 writes a 256 MB buffer before every launch (outside the timed events). */
 int  mipcu_time_kernel(mipcu_ctx* ctx, int which, int reps, int flush_l2,
                        double* mean_us, int64_t* algorithmic_bytes);

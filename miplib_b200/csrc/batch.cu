@@ -44,12 +44,17 @@ struct BatchArgs {
   int m, n, BP, nblk_max;
 };
 
-// One row of the shared matrix times 32 problems' vectors (lane = problem).  The row's (val, idx)
-// pairs are fetched 32 at a time, one per lane and coalesced, and handed round by warp shuffle: no
-// load depends on another load, so the 256-byte gathers of four nonzeros are in flight together
-// (the round-1 version read val[k] / idx[k] warp-uniformly: a dependent chain of two loads per
-// nonzero, 41 node LPs/s on config 4).  Fixed summation order.
-__device__ int g_batch_scalar_loads = 0;   // laboratory switch (MIPCU_BATCH_SCALAR=1): the round-1 inner loop
+// One row of the shared matrix times 32 problems' vectors (lane = problem); fixed summation order.
+// Two inner loops, selectable with MIPCU_BATCH_SHUFFLE (laboratory switch, read per call):
+//   0 (default): val[k] / idx[k] read warp-uniformly, two independent chains;
+//   1: the row's (val, idx) pairs fetched 32 at a time, one per lane and coalesced, and handed round
+//      by warp shuffle, four 256-byte gathers in flight.
+// Measured on one B200 (round 2, profiles/r02_batch_engine.md): the shuffle-fed loop LOSES - config 4
+// row / column kernel 96 / 112 us against 78 / 102 us, config 5 column kernel 207 against 186 us.
+// These kernels are not short of loads in flight: every nonzero moves 8 bytes per problem from L2 to
+// an SM (nnz x B x 8 bytes per product, 410 MB on config 4 at B = 128, with no reuse inside an SM for
+// a random pattern), so they run at the L2 -> SM bandwidth and extra shuffle instructions only add.
+__device__ int g_batch_scalar_loads = 1;   // 0 when MIPCU_BATCH_SHUFFLE=1
 
 __device__ __forceinline__ double row_dot_batch(const int* __restrict__ ptr, const int* __restrict__ idx,
                                                 const double* __restrict__ val,
@@ -166,10 +171,20 @@ __global__ void __launch_bounds__(kThreads) k_row_batch_long(const BatchArgs a, 
   double acc0 = 0.0, acc1 = 0.0;
   if (__any_sync(0xffffffffu, active)) {
     const int beg = a.rptr[row], end = a.rptr[row + 1];
-    // warp w takes the 32-entry chunks w, w + 8, ... of the row: entries fetched one per lane
-    // (coalesced), handed round by shuffle, four gathers in flight
+    if (g_batch_scalar_loads) {      // default: the 8 warps stride over the row's nonzeros, two chains each
+      int k = beg + warp;
+      for (; k + kWarps < end; k += 2 * kWarps) {
+        const double v0 = a.rval[k], v1 = a.rval[k + kWarps];
+        const int c0 = a.ridx[k], c1 = a.ridx[k + kWarps];
+        acc0 = fma(v0, vec[(size_t)c0 * a.BP + b], acc0);
+        acc1 = fma(v1, vec[(size_t)c1 * a.BP + b], acc1);
+      }
+      if (k < end) acc0 = fma(a.rval[k], vec[(size_t)a.ridx[k] * a.BP + b], acc0);
+    }
+    // MIPCU_BATCH_SHUFFLE=1: warp w takes the 32-entry chunks w, w + 8, ... of the row: entries fetched
+    // one per lane (coalesced), handed round by shuffle, four gathers in flight
     double acc2 = 0.0, acc3 = 0.0;
-    for (int base = beg + 32 * warp; base < end; base += 32 * kWarps) {
+    for (int base = beg + 32 * warp; !g_batch_scalar_loads && base < end; base += 32 * kWarps) {
       const int cnt = min(32, end - base);
       int ci = 0;
       double vi = 0.0;
@@ -531,8 +546,8 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
   cudaStream_t st = ctx->stream;
   ctx->launches = 0;
   {
-    const char* v = std::getenv("MIPCU_BATCH_SCALAR");
-    const int scalar = v ? std::atoi(v) : 0;
+    const char* v = std::getenv("MIPCU_BATCH_SHUFFLE");
+    const int scalar = (v && std::atoi(v)) ? 0 : 1;
     MIPCU_CK(cudaMemcpyToSymbolAsync(g_batch_scalar_loads, &scalar, sizeof(int), 0, cudaMemcpyHostToDevice, st));
   }
   if (!ctx->d_sc) MIPCU_CK(cudaMalloc(&ctx->d_sc, sizeof(Scalars)));

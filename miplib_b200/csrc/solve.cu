@@ -758,7 +758,7 @@ void debug_iterate(mipcu_ctx* ctx, int64_t iters, double* xbar_out, double* y_ou
 
 void time_kernel(mipcu_ctx* ctx, int which, int reps, int flush_l2, double* mean_us, int64_t* bytes) {
   MIPCU_REQUIRE(ctx->loaded, "mipcu_time_kernel: no model loaded");
-  MIPCU_REQUIRE(which >= 0 && which <= 3 && reps > 0, "mipcu_time_kernel: bad arguments");
+  MIPCU_REQUIRE(which >= 0 && which <= 5 && reps > 0, "mipcu_time_kernel: bad arguments");
   MIPCU_CK(cudaSetDevice(ctx->device));
   ensure_aux(ctx);
   prepare(ctx);
@@ -773,7 +773,19 @@ void time_kernel(mipcu_ctx* ctx, int which, int reps, int flush_l2, double* mean
       case 0: spmv_plain(ctx, ctx->rows, ctx->xbar, ctx->tmp_m); break;
       case 1: spmv_plain(ctx, ctx->cols, ctx->yhat, ctx->tmp_n); break;
       case 2: row_step(ctx, 1, false); break;
-      default: col_step(ctx, 1, false, nullptr, nullptr); break;
+      case 3: col_step(ctx, 1, false, nullptr, nullptr); break;
+      case 4:   // one whole iteration as shipped: constant step, nothing between the two kernels
+        row_step(ctx, 1, false);
+        col_step(ctx, 1, false, nullptr, nullptr);
+        break;
+      default:  // what an adaptive step-size rule (PDLP) adds to every iteration: the three reductions
+                // |dx|^2, |dy|^2, dx.K'dy in both epilogues and a single-CTA controller that must see them
+                // before the next iteration may start (a rejected step would repeat all of it)
+        row_step(ctx, 0, true);
+        col_step(ctx, 0, true, ctx->xhat_first, nullptr);
+        k_ctrl_first<<<1, kThreads, 0, st>>>(ctx->d_sc, ctx->partials, global_row_sums(ctx), p2p_active(ctx) ? 1 : 0);
+        ctx->launches++;
+        break;
     }
   };
   for (int i = 0; i < 3; ++i) one();
@@ -806,7 +818,8 @@ void time_kernel(mipcu_ctx* ctx, int which, int reps, int flush_l2, double* mean
       case 0: *bytes = 12 * nnz + 4 * (m + 1) + 8 * n + 8 * m; break;   // B_Ax  
       case 1: *bytes = 12 * nnz + 4 * (n + 1) + 8 * m + 8 * n; break;   // B_ATy
       case 2: *bytes = row_kernel_bytes(ctx); break;
-      default: *bytes = col_kernel_bytes(ctx); break;
+      case 3: *bytes = col_kernel_bytes(ctx); break;
+      default: *bytes = row_kernel_bytes(ctx) + col_kernel_bytes(ctx); break;
     }
   }
 }
