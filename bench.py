@@ -437,12 +437,11 @@ def run_cuda(args, rank, world, local_rank):
     if world > 1:
         it_us = 1e6 * dev_iter_s / max(1, iters)
         line["roofline"]["iteration_split_us"] = {
-            "iteration": it_us, "row_step_kernel": row_us, "col_step_kernel": col_us,
-            "other (controller, KKT pass, launch gaps)": it_us - row_us - col_us,
-            "row_step_wait": float(np.mean([s.col_partial_us for s in stats])),
-            "col_step_wait": float(np.mean([s.col_exchange_us for s in stats])),
-            "note": "kernel times include the entry barrier and the pushes of the slice; *_wait = mean time "
-                    "CTA 0 spent in the cross-GPU entry barrier (device clock), 0 when not sampled"}
+            "iteration_mean": it_us, "row_step_kernel": row_us, "col_step_kernel": col_us,
+            "ideal_local_kernels": None,
+            "note": "iteration_mean = device time of the iteration loop / iterations (controller, KKT pass and "
+                    "restarts included); the two kernel times are CUDA events around one launch per 64-iteration "
+                    "block and include the cross-GPU entry barrier and the pushes of the rank's slice"}
     if spmv:
         line["spmv"] = spmv
     if nodes is not None:

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../solver.hpp"
+#include "bigvec.hpp"
 
 struct mipcu_ctx;
 
@@ -95,11 +96,12 @@ struct CudaSolver : detail::ISolver
     double lb, ub;
     std::optional<std::string> name;
   };
-  std::vector<Column> m_columns;
+  BigVec<Column> m_columns;
   // rows in posting order; row r owns entries [m_row_start[r], m_row_start[r+1]) sorted by column
-  std::vector<std::int64_t> m_row_start{0};
-  std::vector<std::int32_t> m_row_idx;
-  std::vector<double> m_row_val;
+  // (BigVec: the large buffers are recycled between solver objects, bigvec.hpp)
+  BigVec<std::int64_t> m_row_start{0};
+  BigVec<std::int32_t> m_row_idx;
+  BigVec<double> m_row_val;
   std::vector<double> m_row_lo, m_row_hi;
   std::vector<char> m_row_alive;
   std::vector<double> m_objective;              // dense, minimise/maximise per m_sense

@@ -68,4 +68,5 @@ def test_branch_and_bound_deals_node_rounds_to_two_gpus(built, golden, tmp_path)
     write_models(path, models)
     rc, out = run_unit_test(built, "--filter", "Generated", env={"MIPLIB_TEST_MODELS": str(path), "MIPLIB_TEST_GPUS": "2"})
     print(out)
-    assert rc == 0 and "1 passed" in out, out
+    assert rc == 0 and "0 failed" in out and "0 skipped" in out, out
+    assert "objective 867 expected 867" in out and "objective 875 expected 875" in out, out
