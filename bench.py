@@ -438,7 +438,6 @@ def run_cuda(args, rank, world, local_rank):
         it_us = 1e6 * dev_iter_s / max(1, iters)
         line["roofline"]["iteration_split_us"] = {
             "iteration_mean": it_us, "row_step_kernel": row_us, "col_step_kernel": col_us,
-            "ideal_local_kernels": None,
             "note": "iteration_mean = device time of the iteration loop / iterations (controller, KKT pass and "
                     "restarts included); the two kernel times are CUDA events around one launch per 64-iteration "
                     "block and include the cross-GPU entry barrier and the pushes of the rank's slice"}
@@ -546,11 +545,11 @@ def nodes_block(cfg, per_gpu, steps, warmup, rank, world, local_rank, dist) -> d
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(rounds, warm):
+    def timed(rounds, warm, cutoff=None, branch_tol=None):
         barrier()
         t0 = time.perf_counter()
-        res = [eng.solve_batch(lb, ub, want_x=False, x0=x0 if warm else None, y0=y0 if warm else None,
-                               weight0=w0 if warm else None)[0] for lb, ub in rounds]
+        res = [eng.solve_batch(lb, ub, cutoff=cutoff, want_x=False, x0=x0 if warm else None, y0=y0 if warm else None,
+                               weight0=w0 if warm else None, branch_tol=branch_tol)[0] for lb, ub in rounds]
         barrier()
         secs = time.perf_counter() - t0
         if dist is not None:
@@ -569,6 +568,15 @@ def nodes_block(cfg, per_gpu, steps, warmup, rank, world, local_rank, dist) -> d
     results, secs = timed(rounds, warm=True)
     clocks = sampler.stop() if rank == 0 else None
     cold, cold_secs = timed(rounds[:1], warm=False)
+    # the same rounds as the branch and bound runs them (miplib_b200/miplib/cuda/bnb.cpp): an incumbent 2 % off
+    # the root bound as cutoff, and nodes that provably cannot be pruned by bound handed back for
+    # branching at 1e-4 (MIPCU_BRANCH) instead of being polished to 1e-6
+    inc = root.primal_obj * (0.98 if L.maximize else 1.02)
+    tree, tree_secs = timed(rounds, warm=True, cutoff=np.full(per_gpu, inc), branch_tol=np.full(per_gpu, 1e-4))
+    tree_status = {}
+    for st in tree:
+        for s_ in st:
+            tree_status[s_.status] = tree_status.get(s_.status, 0) + 1
     decided = ("optimal", "cutoff", "infeasible")
     solved = sum(sum(s.status in decided for s in st) for st in results)
     # the same boxes from a cold start must reach the same objectives (the start point changes the path only)
@@ -607,6 +615,12 @@ def nodes_block(cfg, per_gpu, steps, warmup, rank, world, local_rank, dist) -> d
         "cold_start": {"value": per_gpu * world / cold_secs, "unit": "node LP/s", "rounds": 1,
                        "iterations_mean": float(np.mean(cold_iters)), "iterations_max": int(np.max(cold_iters)),
                        "max_rel_objective_difference_warm_vs_cold": agree},
+        "tree_mode": {"value": per_gpu * world * steps / tree_secs, "unit": "node LP decided/s",
+                      "what": "same rounds as the branch and bound issues them: cutoff = incumbent 2 % off the root "
+                              "bound, nodes that cannot be pruned by bound returned for branching at 1e-4 "
+                              "(MIPCU_BRANCH, dual bound still valid); rank 0's outcomes below",
+                      "outcomes_rank0": tree_status,
+                      "iterations_mean": float(np.mean([s_.iterations for st in tree for s_ in st]))},
         "root_lp": {"status": root.status, "objective": root.primal_obj, "iterations": root.iterations,
                     "certificate": {k: cert[k] for k in ("rel_primal_res", "rel_dual_res", "rel_gap", "primal_obj")}},
         "ok": ok,

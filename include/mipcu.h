@@ -44,7 +44,11 @@ enum {
   MIPCU_ITERATION_LIMIT = 4,   /* -> Result::Interrupted */
   MIPCU_TIME_LIMIT = 5,        /* -> Result::Interrupted */
   MIPCU_NUMERICAL_ERROR = 6,   /* -> Result::Error */
-  MIPCU_CUTOFF = 7             /* dual bound crossed MIPCU_PARAM_OBJ_CUTOFF (B&B pruning) */
+  MIPCU_CUTOFF = 7,            /* dual bound crossed MIPCU_PARAM_OBJ_CUTOFF (B&B pruning) */
+  MIPCU_BRANCH = 8             /* node LP stopped early (mipcu_solve_lp_batch_warm, branch_tol): the iterate is
+                                  feasible to branch_tol and its objective is below the cutoff by more than the
+                                  error it can still have, so the node cannot be pruned by bound - branch on x.
+                                  dual_obj is a valid (weaker) bound */
 };
 
 /* keys for mipcu_set_param / mipcu_get_param */
@@ -155,12 +159,16 @@ int  mipcu_solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const dou
  * miplib/lpsolve/solver.cpp:156, miplib/scip/solver.cpp:370): x0 [B][n] and y0 [B][m] in the caller's
  * terms (x0 is clamped into the node's box; all-zero rows = cold start), primal_weight0 [B] the
  * mipcu_stats.primal_weight the parent's solve ended with (<= 0: default).  Any of the three may be
- * NULL.  y_out ([B][m]) may be NULL.  stats[b].row/col_kernel_us and _bytes describe the batched
- * kernels with all B problems in flight. */
+ * NULL.  branch_tol [B] (or NULL = all 0): a node with branch_tol > 0 stops with MIPCU_BRANCH as soon
+ * as its relative primal / dual residual and gap are <= branch_tol and its primal objective is better
+ * than the node's cutoff by more than 2 branch_tol (1 + |pobj| + |dobj|) - such a node cannot be pruned
+ * by bound however accurately it is solved, so a branch and bound need not wait for 1e-6 (no cutoff:
+ * any branch_tol-accurate point qualifies).  y_out ([B][m]) may be NULL.  stats[b].row/col_kernel_us
+ * and _bytes describe the batched kernels with all B problems in flight. */
 int  mipcu_solve_lp_batch_warm(mipcu_ctx* ctx, int32_t B, const double* lb, const double* ub,
                                const double* cutoff, const double* x0, const double* y0,
-                               const double* primal_weight0, mipcu_stats* out /* [B] */,
-                               double* x_out, double* y_out);
+                               const double* primal_weight0, const double* branch_tol,
+                               mipcu_stats* out /* [B] */, double* x_out, double* y_out);
 int  mipcu_get_x(mipcu_ctx* ctx, double* x /* n */);
 int  mipcu_get_y(mipcu_ctx* ctx, double* y /* m (local rows when sharded) */);
 

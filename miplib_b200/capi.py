@@ -20,7 +20,7 @@ PARAM = {
     "step_size": 5, "use_graph": 6, "scaling": 7, "threads_per_row": 8, "obj_cutoff": 9, "use_tma": 10, "shard_exchange": 11, "use_pdl": 12, "multicast": 13, "row_sort": 14, "peer_timeout": 15,
 }
 STATUS_NAMES = {0: "optimal", 1: "infeasible", 2: "infeasible_or_unbounded", 3: "unbounded",
-                4: "iteration_limit", 5: "time_limit", 6: "numerical_error", 7: "cutoff"}
+                4: "iteration_limit", 5: "time_limit", 6: "numerical_error", 7: "cutoff", 8: "branch"}
 UNIQUE_ID_BYTES = 128
 
 
@@ -108,7 +108,7 @@ def load_library() -> C.CDLL:
         "mipcu_warm_start": (C.c_int, [vp, vp, vp]),
         "mipcu_solve_lp": (C.c_int, [vp, P(_Stats)]),
         "mipcu_solve_lp_batch": (C.c_int, [vp, i32, vp, vp, vp, P(_Stats), vp]),
-        "mipcu_solve_lp_batch_warm": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, P(_Stats), vp, vp]),
+        "mipcu_solve_lp_batch_warm": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, P(_Stats), vp, vp]),
         "mipcu_get_x": (C.c_int, [vp, vp]),
         "mipcu_get_y": (C.c_int, [vp, vp]),
         "mipcu_spmv": (C.c_int, [vp, C.c_int, vp, vp]),
@@ -233,9 +233,10 @@ class Engine:
         self._check(self.lib.mipcu_solve_lp(self.h, C.byref(s)))
         return Stats.from_c(s)
 
-    def solve_batch(self, lb, ub, cutoff=None, want_x=True, x0=None, y0=None, weight0=None, want_y=False):
-        """B node LPs over the loaded matrix.  x0 / y0 ([B][n] / [B][m]) / weight0 ([B]): start points
-        (mipcu_solve_lp_batch_warm).  Returns (stats, x) or, with want_y, (stats, x, y)."""
+    def solve_batch(self, lb, ub, cutoff=None, want_x=True, x0=None, y0=None, weight0=None, want_y=False,
+                    branch_tol=None):
+        """B node LPs over the loaded matrix.  x0 / y0 ([B][n] / [B][m]) / weight0 ([B]): start points;
+        branch_tol ([B]): early MIPCU_BRANCH stop (mipcu_solve_lp_batch_warm).  Returns (stats, x) or, with want_y, (stats, x, y)."""
         lb = np.ascontiguousarray(lb, dtype=np.float64)
         ub = np.ascontiguousarray(ub, dtype=np.float64)
         B = lb.shape[0]
@@ -243,14 +244,16 @@ class Engine:
         stats = (_Stats * B)()
         x = np.empty((B, self.n)) if want_x else None
         y = np.empty((B, self.m)) if want_y else None
-        if x0 is None and y0 is None and weight0 is None and not want_y:
+        if x0 is None and y0 is None and weight0 is None and branch_tol is None and not want_y:
             self._check(self.lib.mipcu_solve_lp_batch(self.h, B, _ptr(lb), _ptr(ub), _ptr(cutoff), stats, _ptr(x)))
         else:
             x0 = None if x0 is None else _f64(x0, B * self.n)
             y0 = None if y0 is None else _f64(y0, B * self.m)
             weight0 = None if weight0 is None else _f64(weight0, B)
+            branch_tol = None if branch_tol is None else _f64(branch_tol, B)
             self._check(self.lib.mipcu_solve_lp_batch_warm(self.h, B, _ptr(lb), _ptr(ub), _ptr(cutoff), _ptr(x0),
-                                                           _ptr(y0), _ptr(weight0), stats, _ptr(x), _ptr(y)))
+                                                           _ptr(y0), _ptr(weight0), _ptr(branch_tol), stats,
+                                                           _ptr(x), _ptr(y)))
         out = [Stats.from_c(s) for s in stats]
         return (out, x, y) if want_y else (out, x)
 

@@ -16,7 +16,7 @@ void dist_init(mipcu_ctx* ctx, int rank, int world, const void* unique_id);
 void dist_destroy(mipcu_ctx* ctx);
 // batch.cu
 void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* ub, const double* cutoff,
-                    const double* x0, const double* y0, const double* weight0,
+                    const double* x0, const double* y0, const double* weight0, const double* branch_tol,
                     mipcu_stats* out, double* x_out, double* y_out);
 }  // namespace mipcu
 
@@ -315,14 +315,17 @@ int mipcu_solve_lp(mipcu_ctx* ctx, mipcu_stats* out) {
 int mipcu_solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* ub,
                          const double* cutoff, mipcu_stats* out, double* x_out) {
   if (!ctx) return 1;
-  return guarded(ctx, [&] { solve_lp_batch(ctx, B, lb, ub, cutoff, nullptr, nullptr, nullptr, out, x_out, nullptr); });
+  return guarded(ctx, [&] { solve_lp_batch(ctx, B, lb, ub, cutoff, nullptr, nullptr, nullptr, nullptr, out, x_out, nullptr); });
 }
 
 int mipcu_solve_lp_batch_warm(mipcu_ctx* ctx, int32_t B, const double* lb, const double* ub,
                               const double* cutoff, const double* x0, const double* y0,
-                              const double* primal_weight0, mipcu_stats* out, double* x_out, double* y_out) {
+                              const double* primal_weight0, const double* branch_tol, mipcu_stats* out,
+                              double* x_out, double* y_out) {
   if (!ctx) return 1;
-  return guarded(ctx, [&] { solve_lp_batch(ctx, B, lb, ub, cutoff, x0, y0, primal_weight0, out, x_out, y_out); });
+  return guarded(ctx, [&] {
+    solve_lp_batch(ctx, B, lb, ub, cutoff, x0, y0, primal_weight0, branch_tol, out, x_out, y_out);
+  });
 }
 
 int mipcu_get_x(mipcu_ctx* ctx, double* x) {

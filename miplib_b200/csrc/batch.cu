@@ -388,6 +388,13 @@ __global__ void __launch_bounds__(kThreads) k_ctrl_check_batch(const BatchArgs a
   if (!(worst == worst) || isinf(worst)) { sc->done = 1 + MIPCU_NUMERICAL_ERROR; return; }
   if (worst <= sc->eps) { sc->done = 1 + MIPCU_OPTIMAL; return; }
   if (sc->rel_d <= sc->eps && dobj >= sc->cutoff) { sc->done = 1 + MIPCU_CUTOFF; return; }
+  // early branch: the iterate is branch_tol-accurate and its objective is below the cutoff by more than
+  // the error it can still carry, so no accuracy will ever prune this node by bound (include/mipcu.h)
+  if (sc->branch_tol > 0.0 && worst <= sc->branch_tol &&
+      pobj + 2.0 * sc->branch_tol * (1.0 + fabs(pobj) + fabs(dobj)) < sc->cutoff) {
+    sc->done = 1 + MIPCU_BRANCH;
+    return;
+  }
   {  // certificates of infeasibility from the displacement (same tests as k_ctrl_check)
     const double nd = sqrt(q[Q_DY2]), nx = sqrt(q[Q_DX2]);
     const double dval = nd > 1e-12 ? (q[Q_RAYD_ROW] + q[Q_RAYD_COL]) / nd : 0.0;
@@ -535,7 +542,7 @@ int64_t batch_col_bytes(const mipcu_ctx* ctx, int BP) {
 }
 
 void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* ub, const double* cutoff,
-                    const double* x0, const double* y0, const double* weight0,
+                    const double* x0, const double* y0, const double* weight0, const double* branch_tol,
                     mipcu_stats* out, double* x_out, double* y_out) {
   NvtxRange nvtx("mipcu:solve_lp_batch (round of node LPs)");
   MIPCU_REQUIRE(ctx->loaded, "mipcu_solve_lp_batch: no model loaded");
@@ -633,6 +640,7 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
     s.eps = ctx->params[MIPCU_PARAM_EPS_REL];
     double cut = cutoff ? cutoff[std::min(b, B - 1)] : ctx->params[MIPCU_PARAM_OBJ_CUTOFF];
     s.cutoff = (cut == cut) ? sgn * cut : INFINITY;
+    s.branch_tol = branch_tol ? std::max(0.0, branch_tol[std::min(b, B - 1)]) : 0.0;
     s.bnorm = ctx->bnorm;
     s.cnorm = ctx->cnorm;
     s.period = period;

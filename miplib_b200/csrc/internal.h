@@ -95,6 +95,7 @@ struct Scalars {
   double tau, sigma, eta, w;
   double eps;
   double cutoff;        // minimisation-sense objective cutoff for the dual bound (+inf: off)
+  double branch_tol;    // batched node LPs: > 0 allows the early MIPCU_BRANCH stop at this tolerance (batch.cu)
   double bnorm, cnorm;
   double fp0, fp_prev, fp;
   double rel_p, rel_d, rel_g, pobj, dobj;

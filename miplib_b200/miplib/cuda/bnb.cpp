@@ -451,7 +451,7 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
     return a.bound != b.bound ? a.bound > b.bound : a.depth < b.depth;
   };
   std::priority_queue<Node, std::vector<Node>, decltype(by_bound)> open(by_bound);
-  open.push(Node{{}, -kInf, 0, nullptr, nullptr, 0.0});
+  open.push(Node{{}, -kInf, 0, nullptr, nullptr, 0.0, false});
   bool complete = true;
   bool unbounded_relaxation = false;
   std::int64_t const node_limit = 4000000;
@@ -464,7 +464,9 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
   // dual objective may overshoot the node optimum by about that residual times |x|.
   struct Pending { Node node; std::vector<double> lb, ub; double cut; bool finite_box; };
   std::vector<Pending> round;
-  std::vector<double> box_lb, box_ub, cuts, xs, ys, x0s, y0s, w0s;
+  std::vector<double> box_lb, box_ub, cuts, xs, ys, x0s, y0s, w0s, btol;
+  // accuracy at which a node that cannot be pruned by bound is handed back for branching
+  double const branch_tol = std::max(1e-4, S.m_feas_tol);
   // parents' solutions ride on the open nodes only while that stays cheap on the host
   std::size_t const warm_budget_bytes = std::size_t(2) << 30;
   std::vector<mipcu_stats> stats;
@@ -512,6 +514,7 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
     x0s.assign(B * n, 0.0);
     y0s.assign(B * m, 0.0);
     w0s.assign(B, 0.0);
+    btol.assign(B, 0.0);
     for (std::size_t b = 0; b < B; ++b)
     {
       Pending& p = round[b];
@@ -523,6 +526,7 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
         double const umax = box_objective_max(p.lb, p.ub);
         double const cut = std::min(cutoff(), std::isinf(umax) ? kInf : umax + 1e-6 * (1.0 + std::abs(umax)));
         cuts[b] = std::isinf(cut) ? std::nan("") : sgn * cut;
+        if (!p.node.exact && S.m_lazy_handlers.empty()) btol[b] = branch_tol;
       }
       else
         cuts[b] = std::nan("");      // no early stop on a bound that may overshoot: decided after the solve
@@ -553,8 +557,8 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
             mipcu_set_param(ctx, MIPCU_PARAM_TIME_LIMIT, std::max(0.01, S.m_time_limit - elapsed()));
           if (mipcu_solve_lp_batch_warm(ctx, static_cast<std::int32_t>(b1 - b0), box_lb.data() + b0 * n,
                                         box_ub.data() + b0 * n, cuts.data() + b0, x0s.data() + b0 * n,
-                                        y0s.data() + b0 * m, w0s.data() + b0, stats.data() + b0,
-                                        xs.data() + b0 * n, ys.data() + b0 * m))
+                                        y0s.data() + b0 * m, w0s.data() + b0, btol.data() + b0,
+                                        stats.data() + b0, xs.data() + b0 * n, ys.data() + b0 * m))
             errors[g] = mipcu_last_error(ctx);
         };
         if (G == 1) job(); else workers.emplace_back(job);
@@ -589,6 +593,15 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
       if (lp.status == MIPCU_NUMERICAL_ERROR) { complete = false; continue; }
       if (lp.status == MIPCU_TIME_LIMIT) { complete = false; continue; }
       double node_bound = node.bound;
+      bool const early = lp.status == MIPCU_BRANCH;      // cannot be pruned by bound: branch on the 1e-4 point
+      if (early)
+      {
+        // the dual objective of ANY multiplier bounds a finite box (only finite boxes stop early)
+        double const d = sgn * lp.dual_obj;
+        node_bound = std::max(node_bound, d - std::max(1e-6, S.m_feas_tol) * (1.0 + std::abs(d)));
+        try_roundings(x, lb, ub);
+        if (node_bound >= cutoff()) continue;
+      }
       if (lp.status == MIPCU_OPTIMAL)
       {
         double const d = sgn * lp.dual_obj, p = sgn * lp.primal_obj;
@@ -622,6 +635,19 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
           double const f = std::abs(x[j] - std::round(x[j]));
           if (f > worst) { worst = f; pick = static_cast<std::int32_t>(j); }
         }
+      if (early && worst < 0.02)
+      {
+        // a 1e-4 point that looks integral decides nothing: the same box again, to full accuracy
+        Node again = node;
+        again.exact = true;
+        again.bound = node_bound;
+        again.x = std::make_shared<std::vector<double> const>(x);
+        again.y = std::make_shared<std::vector<double> const>(ys.begin() + b * m, ys.begin() + (b + 1) * m);
+        again.weight = lp.primal_weight;
+        S.m_info.nodes -= 1;                             // counted again when it is popped
+        open.push(std::move(again));
+        continue;
+      }
       if (pick < 0)
       {
         if (lp.status == MIPCU_OPTIMAL)
@@ -655,7 +681,7 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
       }
       double const split = std::floor(x[pick]);
       std::shared_ptr<std::vector<double> const> px, py;
-      if (lp.status == MIPCU_OPTIMAL && (open.size() + 2) * (n + m) * sizeof(double) <= warm_budget_bytes)
+      if ((lp.status == MIPCU_OPTIMAL || early) && (open.size() + 2) * (n + m) * sizeof(double) <= warm_budget_bytes)
       {
         px = std::make_shared<std::vector<double> const>(x);
         py = std::make_shared<std::vector<double> const>(ys.begin() + b * m, ys.begin() + (b + 1) * m);

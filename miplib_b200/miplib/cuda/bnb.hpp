@@ -6,7 +6,10 @@
 // no LP at all and catches the structurally infeasible nodes PDHG cannot certify), rounding
 // heuristics, pruning by the DUAL objective of the node LP (a valid bound, unlike the primal value
 // of an inexact first-order solve).  Device side: one PDHG solve per node, warm started from the
-// parent, stopped early by MIPCU_PARAM_OBJ_CUTOFF as soon as its dual bound crosses the incumbent.
+// parent, stopped early by MIPCU_PARAM_OBJ_CUTOFF as soon as its dual bound crosses the incumbent -
+// or, the other way round, as soon as a 1e-4-accurate iterate shows that the node can NOT be pruned
+// by bound (MIPCU_BRANCH): such a node is branched on at once; only nodes whose LP value is close to
+// the incumbent, and nodes whose LP point looks integral, are solved to the full tolerance.
 //
 // Root strengthening: implied-bound rows.  A row in which fixing one binary z to a value forces
 // another column to a tighter bound (the big-M rows IndicatorConstr::reformulation() emits,
@@ -41,6 +44,7 @@ struct CudaBranchAndBound
     // the start point of this node's LP (mipcu_solve_lp_batch_warm)
     std::shared_ptr<std::vector<double> const> x, y;
     double weight = 0;
+    bool exact = false;            // solve this node's LP to full accuracy (no early MIPCU_BRANCH stop)
   };
 
   bool propagate(std::vector<double>& lb, std::vector<double>& ub) const;

@@ -176,3 +176,39 @@ def test_batch_warm_start_from_the_parent(built):
         assert zero[b].iterations == cold[b].iterations and zero[b].status == cold[b].status
         assert np.array_equal(xz[b], xc[b])
     assert warm[0].row_kernel_us > 0 and warm[0].col_kernel_bytes > 0
+
+
+def test_batch_early_branch_stop(built):
+    """branch_tol: a node whose 1e-4 iterate is already below the cutoff by more than its error stops with
+    status "branch" (it cannot be pruned by bound), with a VALID dual bound and a usable point; a node
+    above the cutoff is still cut off; branch_tol = 0 nodes are solved to 1e-6 as before."""
+    from miplib_b200 import Engine
+    L = gen.set_cover(400, 1000, 8, 20264)
+    rng = np.random.default_rng(3)
+    B = 12
+    lb, ub = node_boxes(L, B, rng, 6)
+    with Engine(0) as e:
+        e.load_lp(L)
+        e.set_param("iter_limit", 60000)
+        exact, _ = e.solve_batch(lb, ub)
+        opt = [s.primal_obj for s in exact]
+        cutoff = np.array([o + 5.0 for o in opt])          # every node is 5 below its cutoff ...
+        cutoff[4] = opt[4] - 5.0                            # ... except node 4, which is above it
+        tol = np.full(B, 1e-4)
+        tol[7] = 0.0                                        # node 7 keeps the full tolerance
+        early, x = e.solve_batch(lb, ub, cutoff=cutoff, branch_tol=tol)
+    assert all(s.status == "optimal" for s in exact)
+    assert early[4].status == "cutoff"
+    assert early[7].status == "optimal" and early[7].iterations == exact[7].iterations
+    for b in range(B):
+        if b in (4, 7):
+            continue
+        assert early[b].status == "branch", (b, early[b])
+        assert early[b].iterations < exact[b].iterations
+        assert early[b].dual_obj <= opt[b] + 1e-6 * (1 + abs(opt[b]))                 # still a valid bound
+        assert abs(early[b].primal_obj - opt[b]) <= 1e-3 * (1 + abs(opt[b]))         # and a 1e-4 point
+        assert max(early[b].rel_primal_res, early[b].rel_dual_res, early[b].rel_gap) <= 1e-4
+        assert np.all(x[b] >= lb[b] - 1e-12) and np.all(x[b] <= ub[b] + 1e-12)
+    saved = 1 - sum(s.iterations for s in early) / sum(s.iterations for s in exact)
+    print(f"iterations saved by the early stop: {100 * saved:.0f} %")
+    assert saved > 0.3
