@@ -82,7 +82,12 @@ enum {
   MIPCU_PARAM_PEER_TIMEOUT = 15,  /* row-sharded contexts: seconds a kernel waits at a cross-GPU barrier for its peers
                                      (default 120; 0 = forever).  On expiry the solve returns rc = 1 with a message
                                      instead of hanging or trapping: sharded load / solve are collective and fail-stop */
-  MIPCU_PARAM_COUNT_ = 16
+  MIPCU_PARAM_VALIDATE = 16,      /* debug: 1 = after setup, device kernels check every index structure the iteration kernels
+                                     dereference (CSR / sliced-ELL column indices in range, slice offsets monotone and
+                                     consistent with the entry count, block-local permutations, the column block and the
+                                     slice extents of row-sharded contexts); a violation fails the call with a message.
+                                     The in-house stand-in for compute-sanitizer memcheck, which this pool does not offer */
+  MIPCU_PARAM_COUNT_ = 17
 };
 
 typedef struct mipcu_stats {

@@ -17,7 +17,7 @@ _LIB = None
 
 PARAM = {
     "eps_rel": 0, "iter_limit": 1, "time_limit": 2, "check_period": 3, "verbose": 4,
-    "step_size": 5, "use_graph": 6, "scaling": 7, "threads_per_row": 8, "obj_cutoff": 9, "use_tma": 10, "shard_exchange": 11, "use_pdl": 12, "multicast": 13, "row_sort": 14, "peer_timeout": 15,
+    "step_size": 5, "use_graph": 6, "scaling": 7, "threads_per_row": 8, "obj_cutoff": 9, "use_tma": 10, "shard_exchange": 11, "use_pdl": 12, "multicast": 13, "row_sort": 14, "peer_timeout": 15, "validate": 16,
 }
 STATUS_NAMES = {0: "optimal", 1: "infeasible", 2: "infeasible_or_unbounded", 3: "unbounded",
                 4: "iteration_limit", 5: "time_limit", 6: "numerical_error", 7: "cutoff", 8: "branch"}

@@ -67,6 +67,7 @@ void set_default_params(mipcu_ctx* ctx) {
   ctx->params[MIPCU_PARAM_MULTICAST] = 1;
   ctx->params[MIPCU_PARAM_ROW_SORT] = 1;
   ctx->params[MIPCU_PARAM_PEER_TIMEOUT] = 120.0;
+  ctx->params[MIPCU_PARAM_VALIDATE] = 0;
 }
 
 mipcu_ctx* create_on(int device) {

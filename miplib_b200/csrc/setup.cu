@@ -828,6 +828,96 @@ void load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* r
   ctx->vectors_dirty = true;
 }
 
+// ---- MIPCU_PARAM_VALIDATE: every index structure the iteration kernels dereference ------------------
+// The kernels' memory accesses are driven by these arrays (loop bounds from ptr / sptr, gather
+// addresses from idx / sidx, scatter slots from perm); the epilogues are guarded by i < nrows.  So
+// "arrays consistent and in range" is "no out-of-bounds access", checked here by brute force.
+// bad[0] counts violations, bad[1] keeps the first offending code * 2^32 + position.
+__device__ __forceinline__ void report_bad(unsigned long long* bad, int code, long long where) {
+  atomicAdd(bad, 1ull);
+  atomicCAS(bad + 1, 0ull, ((unsigned long long)code << 40) | (unsigned long long)(where & 0xffffffffffll));
+}
+
+__global__ void k_validate_ptr(const int* __restrict__ ptr, int count, long long total, int code,
+                               unsigned long long* bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > count) return;
+  const int v = ptr[i];
+  if (i == 0 && v != 0) report_bad(bad, code, 0);
+  if (i == count && (long long)v != total) report_bad(bad, code, i);
+  if (i < count && ptr[i + 1] < v) report_bad(bad, code, i);
+}
+
+__global__ void k_validate_idx(const int* __restrict__ idx, long long count, int lo, int hi, int code,
+                               unsigned long long* bad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int v = idx[i];
+  if (v < lo || v >= hi) report_bad(bad, code, i);
+}
+
+// slices of a SELL copy hold whole multiples of 32 entries; perm is a permutation inside each 256-row block
+__global__ void k_validate_sell(const int* __restrict__ sptr, const unsigned char* __restrict__ perm, int nblk,
+                                int code, unsigned long long* bad) {
+  __shared__ int seen[kRowsPerCta];
+  const int blk = blockIdx.x;
+  seen[threadIdx.x] = 0;
+  __syncthreads();
+  atomicAdd(&seen[perm[(size_t)blk * kRowsPerCta + threadIdx.x]], 1);
+  __syncthreads();
+  if (seen[threadIdx.x] != 1) report_bad(bad, code, (long long)blk * kRowsPerCta + threadIdx.x);
+  if (threadIdx.x < kRowsPerCta / 32) {
+    const int s = blk * (kRowsPerCta / 32) + threadIdx.x;
+    if ((sptr[s + 1] - sptr[s]) % 32 != 0) report_bad(bad, code + 1, s);
+  }
+}
+
+void validate_csr(mipcu_ctx* ctx, const Csr& A, int code, unsigned long long* bad) {
+  cudaStream_t st = ctx->stream;
+  if (A.nrows <= 0 || !A.ptr) return;
+  k_validate_ptr<<<grid_for(A.nrows + 1), kThreads, 0, st>>>(A.ptr, A.nrows, A.nnz, code, bad);
+  if (A.nnz) k_validate_idx<<<grid_for(A.nnz), kThreads, 0, st>>>(A.idx, A.nnz, 0, A.ncols, code + 1, bad);
+  ctx->launches += 2;
+  if (A.sptr) {
+    const int nblk = grid_for(A.nrows, kRowsPerCta), nslices = nblk * (kRowsPerCta / 32);
+    k_validate_ptr<<<grid_for(nslices + 1), kThreads, 0, st>>>(A.sptr, nslices, A.sell_entries, code + 2, bad);
+    if (A.sell_entries)
+      k_validate_idx<<<grid_for(A.sell_entries), kThreads, 0, st>>>(A.sidx, A.sell_entries, -1, A.ncols, code + 3, bad);
+    k_validate_sell<<<nblk, kRowsPerCta, 0, st>>>(A.sptr, A.perm, nblk, code + 4, bad);
+    ctx->launches += 3;
+  }
+}
+
+void validate_structures(mipcu_ctx* ctx) {
+  NvtxRange nvtx("mipcu:validate");
+  cudaStream_t st = ctx->stream;
+  unsigned long long* bad = dalloc<unsigned long long>(2);
+  MIPCU_CK(cudaMemsetAsync(bad, 0, 2 * sizeof(unsigned long long), st));
+  validate_csr(ctx, ctx->rows, 10, bad);
+  validate_csr(ctx, ctx->cols, 20, bad);
+  validate_csr(ctx, ctx->colblk, 30, bad);
+  unsigned long long h[2] = {0, 0};
+  MIPCU_CK(cudaMemcpyAsync(h, bad, sizeof(h), cudaMemcpyDeviceToHost, st));
+  MIPCU_CK(cudaStreamSynchronize(st));
+  dfree(bad);
+  // shape relations the kernels rely on
+  bool shape_ok = ctx->rows.nrows == ctx->m && ctx->rows.ncols == ctx->n && ctx->cols.nrows == ctx->n &&
+                  ctx->cols.ncols == ctx->m && ctx->rows.nnz == ctx->cols.nnz;
+  if (ctx->world > 1 && ctx->peers.world == ctx->world) {
+    const PeerTable& t = ctx->peers;
+    shape_ok = shape_ok && t.i0[ctx->rank + 1] - t.i0[ctx->rank] == ctx->m && t.i0[t.world] == ctx->m_glob &&
+               t.j0[0] == 0 && t.j0[t.world] == ctx->n;
+    for (int g = 0; g < t.world; ++g) shape_ok = shape_ok && t.i0[g] <= t.i0[g + 1] && t.j0[g] <= t.j0[g + 1];
+    if (ctx->colblk.nrows > 0)
+      shape_ok = shape_ok && ctx->colblk.nrows == t.j0[ctx->rank + 1] - t.j0[ctx->rank] && ctx->colblk.ncols == ctx->m_glob;
+  }
+  MIPCU_REQUIRE(shape_ok, "MIPCU_PARAM_VALIDATE: matrix copies / slice extents are inconsistent");
+  if (h[0])
+    throw Error("MIPCU_PARAM_VALIDATE: " + std::to_string(h[0]) + " index structure violation(s); first: structure code " +
+                std::to_string((unsigned)(h[1] >> 40)) + " at position " + std::to_string((long long)(h[1] & 0xffffffffffull)) +
+                " (10 rows, 20 columns, 30 column block; +0 ptr, +1 idx, +2 slice ptr, +3 slice idx, +4 perm, +5 slice size)");
+}
+
 // Ruiz x RUIZ_PASSES (row/col max-abs) then Pock-Chambolle alpha = 1 (row/col 1-norms), applied
 // in place to both copies; then eta = STEP_SAFETY / sigma_max(K) by power iteration.
 void prepare(mipcu_ctx* ctx) {
@@ -926,6 +1016,7 @@ void prepare(mipcu_ctx* ctx) {
   }
   lap("step size");
   MIPCU_CK(cudaStreamSynchronize(st));
+  if (ctx->params[MIPCU_PARAM_VALIDATE] != 0.0) validate_structures(ctx);
   ctx->prepared = true;
   ctx->vectors_dirty = true;
   ctx->setup_seconds =
