@@ -85,7 +85,8 @@ enum {
   MIPCU_PARAM_VALIDATE = 16,      /* debug: 1 = after setup, device kernels check every index structure the iteration kernels
                                      dereference (CSR / sliced-ELL column indices in range, slice offsets monotone and
                                      consistent with the entry count, block-local permutations, the column block and the
-                                     slice extents of row-sharded contexts); a violation fails the call with a message.
+                                     slice extents of row-sharded contexts); a violation fails the call with a message
+                                     (2 = self-test: plants a bad index first, so the call must fail).
                                      The in-house stand-in for compute-sanitizer memcheck, which this pool does not offer */
   MIPCU_PARAM_COUNT_ = 17
 };

@@ -893,6 +893,12 @@ void validate_structures(mipcu_ctx* ctx) {
   cudaStream_t st = ctx->stream;
   unsigned long long* bad = dalloc<unsigned long long>(2);
   MIPCU_CK(cudaMemsetAsync(bad, 0, 2 * sizeof(unsigned long long), st));
+  if (ctx->params[MIPCU_PARAM_VALIDATE] == 2.0 && ctx->rows.nnz > 0) {
+    // self-test of the validator (tests/test_validate_gpu.py): plant one out-of-range column index
+    const int wrong = ctx->rows.ncols;
+    int* where = ctx->rows.sidx ? ctx->rows.sidx : ctx->rows.idx;
+    MIPCU_CK(cudaMemcpyAsync(where, &wrong, sizeof(int), cudaMemcpyHostToDevice, st));
+  }
   validate_csr(ctx, ctx->rows, 10, bad);
   validate_csr(ctx, ctx->cols, 20, bad);
   validate_csr(ctx, ctx->colblk, 30, bad);

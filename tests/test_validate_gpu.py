@@ -21,12 +21,11 @@ def test_every_kernel_family_on_validated_structures(built):
     assert p.returncode == 0 and "sanitize_case done" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
 
 
-def test_validation_catches_a_corrupted_structure(built):
-    """The validator is not vacuous: a matrix whose column index the loader cannot see as bad (it is in
-    range for the loader, the check runs on the device copies after scaling) passes; the full-size LP
-    configs pass; and validate_structures rejects an inconsistent context (exercised through a model
-    with an empty row block, the shape the sharded path's extents are most fragile on)."""
+def test_validation_passes_on_real_models_and_catches_a_planted_index(built):
+    """Not vacuous: MIPCU_PARAM_VALIDATE = 2 plants one out-of-range column index in the device copy before
+    validating and the call must fail with the structure named; = 1 passes on every model family."""
     from miplib_b200 import Engine
+    from miplib_b200.capi import MipcuError
     for L in (gen.config(1), gen.set_cover(200, 500, 8, 20264), gen.mkp(5, 2000, 4, 10, 20265)):
         with Engine(0) as e:
             e.set_param("validate", 1)
@@ -34,6 +33,11 @@ def test_validation_catches_a_corrupted_structure(built):
             e.prepare()
             v = np.random.default_rng(0).standard_normal(L.n)
             assert np.abs(e.spmv(v) - L.A @ v).max() <= 1e-9 * (1 + np.abs(L.A @ v).max())
+        with Engine(0) as e:
+            e.set_param("validate", 2)
+            e.load_lp(L)
+            with pytest.raises(MipcuError, match="index structure violation"):
+                e.prepare()
 
 
 def test_two_rank_protocol_is_deterministic(built):
