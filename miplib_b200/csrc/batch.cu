@@ -44,56 +44,73 @@ struct BatchArgs {
   int m, n, BP, nblk_max;
 };
 
-// One row of the shared matrix times 32 problems' vectors (lane = problem); fixed summation order.
-// Two inner loops, selectable with MIPCU_BATCH_SHUFFLE (laboratory switch, read per call):
-//   0 (default): val[k] / idx[k] read warp-uniformly, two independent chains;
-//   1: the row's (val, idx) pairs fetched 32 at a time, one per lane and coalesced, and handed round
-//      by warp shuffle, four 256-byte gathers in flight.
-// Measured on one B200 (round 2, profiles/r02_batch_engine.md): the shuffle-fed loop LOSES - config 4
-// row / column kernel 96 / 112 us against 78 / 102 us, config 5 column kernel 207 against 186 us.
-// These kernels are not short of loads in flight: every nonzero moves 8 bytes per problem from L2 to
-// an SM (nnz x B x 8 bytes per product, 410 MB on config 4 at B = 128, with no reuse inside an SM for
-// a random pattern), so they run at the L2 -> SM bandwidth and extra shuffle instructions only add.
-__device__ int g_batch_scalar_loads = 1;   // 0 when MIPCU_BATCH_SHUFFLE=1
+// One row of the shared matrix times 32 problems' vectors (lane = problem).  val[k] / idx[k] are
+// warp-uniform loads, the gather is one contiguous 256-byte segment per nonzero; two accumulator
+// chains (even / odd entries), fixed summation order.
+//
+// ncu (round 2, profiles/r02_batch_engine.md) shows these kernels bound by LATENCY, not by a memory
+// level: DRAM 22 - 56 % busy, L2 29 - 37 %, the L1 -> XBAR port 19 - 25 %, about 16 cycles of
+// long-scoreboard stall per issued instruction at 50 - 57 % active warps.  A warp walks its 8 rows one
+// after the other and every row is a chain ptr -> (val, idx) -> gather -> step vectors -> store.  Two
+// remedies, switchable for the A/B with MIPCU_BATCH_PAIRS (default 1):
+//   * rows are taken in PAIRS: the step vectors of both rows are requested before either product starts,
+//     and the two products run interleaved (row_dot_batch2: four gathers in flight instead of two) - the
+//     per-row summation order is unchanged, results are bit-identical to the one-row loop;
+//   * the CTA-per-row kernel for long rows keeps 8 chains per warp instead of 2.
+// (A third variant - row entries fetched one per lane and handed round by warp shuffle - was measured
+// slower than the plain loop, 96 / 112 us against 78 / 102 us on config 4, and is gone.)
+__device__ int g_batch_pairs = 1;
 
 __device__ __forceinline__ double row_dot_batch(const int* __restrict__ ptr, const int* __restrict__ idx,
                                                 const double* __restrict__ val,
                                                 const double* __restrict__ vec, int row, int BP, int b) {
   const int beg = ptr[row], end = ptr[row + 1];
-  if (g_batch_scalar_loads) {
-    double a0 = 0.0, a1 = 0.0;
-    int k = beg;
-    for (; k + 1 < end; k += 2) {
-      const double v0 = val[k], v1 = val[k + 1];
-      const int c0 = idx[k], c1 = idx[k + 1];
-      a0 = fma(v0, vec[(size_t)c0 * BP + b], a0);
-      a1 = fma(v1, vec[(size_t)c1 * BP + b], a1);
-    }
-    if (k < end) a0 = fma(val[k], vec[(size_t)idx[k] * BP + b], a0);
-    return a0 + a1;
+  double a0 = 0.0, a1 = 0.0;
+  int k = beg;
+  for (; k + 1 < end; k += 2) {
+    const double v0 = val[k], v1 = val[k + 1];
+    const int c0 = idx[k], c1 = idx[k + 1];
+    a0 = fma(v0, vec[(size_t)c0 * BP + b], a0);
+    a1 = fma(v1, vec[(size_t)c1 * BP + b], a1);
   }
-  const int lane = threadIdx.x & 31;
-  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-  for (int base = beg; base < end; base += 32) {
-    const int cnt = min(32, end - base);
-    int ci = 0;
-    double vi = 0.0;
-    if (lane < cnt) { ci = __ldg(idx + base + lane); vi = __ldg(val + base + lane); }
-    int t = 0;
-    for (; t + 4 <= cnt; t += 4) {
-      const int c0 = __shfl_sync(0xffffffffu, ci, t), c1 = __shfl_sync(0xffffffffu, ci, t + 1);
-      const int c2 = __shfl_sync(0xffffffffu, ci, t + 2), c3 = __shfl_sync(0xffffffffu, ci, t + 3);
-      const double x0 = vec[(size_t)c0 * BP + b], x1 = vec[(size_t)c1 * BP + b];
-      const double x2 = vec[(size_t)c2 * BP + b], x3 = vec[(size_t)c3 * BP + b];
-      acc0 = fma(__shfl_sync(0xffffffffu, vi, t), x0, acc0);
-      acc1 = fma(__shfl_sync(0xffffffffu, vi, t + 1), x1, acc1);
-      acc2 = fma(__shfl_sync(0xffffffffu, vi, t + 2), x2, acc2);
-      acc3 = fma(__shfl_sync(0xffffffffu, vi, t + 3), x3, acc3);
-    }
-    for (; t < cnt; ++t)
-      acc0 = fma(__shfl_sync(0xffffffffu, vi, t), vec[(size_t)__shfl_sync(0xffffffffu, ci, t) * BP + b], acc0);
+  if (k < end) a0 = fma(val[k], vec[(size_t)idx[k] * BP + b], a0);
+  return a0 + a1;
+}
+
+// rows `row` and `row + 1` together: the common prefix of the two rows runs as four independent chains,
+// the longer row finishes alone.  Each row's sum is formed exactly as in row_dot_batch.
+__device__ __forceinline__ void row_dot_batch2(const int* __restrict__ ptr, const int* __restrict__ idx,
+                                               const double* __restrict__ val, const double* __restrict__ vec,
+                                               int row, int BP, int b, double& s0, double& s1) {
+  const int b0 = ptr[row], b1 = ptr[row + 1], e1 = ptr[row + 2];
+  const int e0 = b1;
+  const int joint = min(e0 - b0, e1 - b1) & ~1;
+  double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
+  int k = 0;
+  for (; k < joint; k += 2) {
+    const double v00 = val[b0 + k], v01 = val[b0 + k + 1], v10 = val[b1 + k], v11 = val[b1 + k + 1];
+    const int i00 = idx[b0 + k], i01 = idx[b0 + k + 1], i10 = idx[b1 + k], i11 = idx[b1 + k + 1];
+    const double x00 = vec[(size_t)i00 * BP + b], x01 = vec[(size_t)i01 * BP + b];
+    const double x10 = vec[(size_t)i10 * BP + b], x11 = vec[(size_t)i11 * BP + b];
+    a0 = fma(v00, x00, a0);
+    a1 = fma(v01, x01, a1);
+    c0 = fma(v10, x10, c0);
+    c1 = fma(v11, x11, c1);
   }
-  return (acc0 + acc1) + (acc2 + acc3);
+  int p = b0 + k;
+  for (; p + 1 < e0; p += 2) {
+    a0 = fma(val[p], vec[(size_t)idx[p] * BP + b], a0);
+    a1 = fma(val[p + 1], vec[(size_t)idx[p + 1] * BP + b], a1);
+  }
+  if (p < e0) a0 = fma(val[p], vec[(size_t)idx[p] * BP + b], a0);
+  p = b1 + k;
+  for (; p + 1 < e1; p += 2) {
+    c0 = fma(val[p], vec[(size_t)idx[p] * BP + b], c0);
+    c1 = fma(val[p + 1], vec[(size_t)idx[p + 1] * BP + b], c1);
+  }
+  if (p < e1) c0 = fma(val[p], vec[(size_t)idx[p] * BP + b], c0);
+  s0 = a0 + a1;
+  s1 = c0 + c1;
 }
 
 template <int NQ>
@@ -115,6 +132,29 @@ __device__ __forceinline__ void batch_reduce_store(double (&red)[NQ], const int 
   }
 }
 
+// the per-row part of the batched row step, given (K xbar)_row for this lane's problem
+template <bool CHECK>
+__device__ __forceinline__ void row_epilogue_batch(const BatchArgs& a, int row, size_t e, double kx, double yi,
+                                                   double y0i, double sigma, double w_new, int keep_kx,
+                                                   double (&red)[5]) {
+  const double lo = a.lo[row], hi = a.hi[row];
+  const double t = kx - yi / sigma;
+  const double yh = sigma * (clampd(t, lo, hi) - t);
+  a.yhat[e] = yh;
+  a.y[e] = w_new * (2.0 * yh - yi) + (1.0 - w_new) * y0i;
+  if (CHECK) {
+    const double dy = yh - yi, d0 = yh - y0i;
+    red[0] += dy * dy;
+    red[1] += d0 * d0;
+    red[2] += (isfinite(lo) ? lo * fmax(yh, 0.0) : 0.0) - (isfinite(hi) ? hi * fmax(-yh, 0.0) : 0.0);
+    const double dp = fmax(dy, 0.0), dm = fmax(-dy, 0.0);
+    red[3] += (isfinite(lo) ? lo * dp : 0.0) - (isfinite(hi) ? hi * dm : 0.0);
+    const double rv = (isfinite(lo) ? 0.0 : dp) + (isfinite(hi) ? 0.0 : dm);
+    red[4] += rv * rv;
+    if (keep_kx) a.kx_save[e] = kx;
+  }
+}
+
 template <bool CHECK>
 __global__ void __launch_bounds__(kThreads) k_row_step_batch(const BatchArgs a, int iter_in_block, int keep_kx) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -126,28 +166,30 @@ __global__ void __launch_bounds__(kThreads) k_row_step_batch(const BatchArgs a, 
   const double w_new = (k + 1.0) / (k + 2.0);
   double red[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   if (__any_sync(0xffffffffu, active)) {
-    for (int i = 0; i < kRowsPerCtaB / kWarps; ++i) {
-      const int row = blockIdx.x * kRowsPerCtaB + warp * (kRowsPerCtaB / kWarps) + i;
-      if (row >= a.m) break;
+    constexpr int kPerWarp = kRowsPerCtaB / kWarps;
+    const int first = blockIdx.x * kRowsPerCtaB + warp * kPerWarp;
+    const int last = min(first + kPerWarp, a.m);
+    int row = first;
+    if (g_batch_pairs) {
+      for (; row + 1 < last; row += 2) {
+        // both rows' step vectors are on their way before either product starts
+        const size_t e0 = (size_t)row * a.BP + b, e1 = e0 + a.BP;
+        double y_0 = 0.0, y0_0 = 0.0, y_1 = 0.0, y0_1 = 0.0;
+        if (active) { y_0 = a.y[e0]; y0_0 = a.y0[e0]; y_1 = a.y[e1]; y0_1 = a.y0[e1]; }
+        double kx0, kx1;
+        row_dot_batch2(a.rptr, a.ridx, a.rval, a.xbar, row, a.BP, b, kx0, kx1);
+        if (!active) continue;
+        row_epilogue_batch<CHECK>(a, row, e0, kx0, y_0, y0_0, sigma, w_new, keep_kx, red);
+        row_epilogue_batch<CHECK>(a, row + 1, e1, kx1, y_1, y0_1, sigma, w_new, keep_kx, red);
+      }
+    }
+    for (; row < last; ++row) {
+      const size_t e = (size_t)row * a.BP + b;
+      double yi = 0.0, y0i = 0.0;
+      if (active) { yi = a.y[e]; y0i = a.y0[e]; }
       const double kx = row_dot_batch(a.rptr, a.ridx, a.rval, a.xbar, row, a.BP, b);
       if (!active) continue;
-      const size_t e = (size_t)row * a.BP + b;
-      const double yi = a.y[e], y0i = a.y0[e], lo = a.lo[row], hi = a.hi[row];
-      const double t = kx - yi / sigma;
-      const double yh = sigma * (clampd(t, lo, hi) - t);
-      a.yhat[e] = yh;
-      a.y[e] = w_new * (2.0 * yh - yi) + (1.0 - w_new) * y0i;
-      if (CHECK) {
-        const double dy = yh - yi, d0 = yh - y0i;
-        red[0] += dy * dy;
-        red[1] += d0 * d0;
-        red[2] += (isfinite(lo) ? lo * fmax(yh, 0.0) : 0.0) - (isfinite(hi) ? hi * fmax(-yh, 0.0) : 0.0);
-        const double dp = fmax(dy, 0.0), dm = fmax(-dy, 0.0);
-        red[3] += (isfinite(lo) ? lo * dp : 0.0) - (isfinite(hi) ? hi * dm : 0.0);
-        const double rv = (isfinite(lo) ? 0.0 : dp) + (isfinite(hi) ? 0.0 : dm);
-        red[4] += rv * rv;
-        if (keep_kx) a.kx_save[e] = kx;
-      }
+      row_epilogue_batch<CHECK>(a, row, e, kx, yi, y0i, sigma, w_new, keep_kx, red);
     }
   }
   if (CHECK) {
@@ -171,7 +213,24 @@ __global__ void __launch_bounds__(kThreads) k_row_batch_long(const BatchArgs a, 
   double acc0 = 0.0, acc1 = 0.0;
   if (__any_sync(0xffffffffu, active)) {
     const int beg = a.rptr[row], end = a.rptr[row + 1];
-    if (g_batch_scalar_loads) {      // default: the 8 warps stride over the row's nonzeros, two chains each
+    if (g_batch_pairs) {
+      // the 8 warps stride over the row's nonzeros; each warp keeps 8 gathers in flight (a row of 1600
+      // entries is 200 per warp: two chains made that a dependent sequence of 100 round trips)
+      double c[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      int k = beg + warp;
+      for (; k + 7 * kWarps < end; k += 8 * kWarps) {
+        double v[8], x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          v[u] = a.rval[k + u * kWarps];
+          x[u] = vec[(size_t)a.ridx[k + u * kWarps] * a.BP + b];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) c[u] = fma(v[u], x[u], c[u]);
+      }
+      for (; k < end; k += kWarps) c[0] = fma(a.rval[k], vec[(size_t)a.ridx[k] * a.BP + b], c[0]);
+      acc0 = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
+    } else {
       int k = beg + warp;
       for (; k + kWarps < end; k += 2 * kWarps) {
         const double v0 = a.rval[k], v1 = a.rval[k + kWarps];
@@ -181,30 +240,6 @@ __global__ void __launch_bounds__(kThreads) k_row_batch_long(const BatchArgs a, 
       }
       if (k < end) acc0 = fma(a.rval[k], vec[(size_t)a.ridx[k] * a.BP + b], acc0);
     }
-    // MIPCU_BATCH_SHUFFLE=1: warp w takes the 32-entry chunks w, w + 8, ... of the row: entries fetched
-    // one per lane (coalesced), handed round by shuffle, four gathers in flight
-    double acc2 = 0.0, acc3 = 0.0;
-    for (int base = beg + 32 * warp; !g_batch_scalar_loads && base < end; base += 32 * kWarps) {
-      const int cnt = min(32, end - base);
-      int ci = 0;
-      double vi = 0.0;
-      if (lane < cnt) { ci = __ldg(a.ridx + base + lane); vi = __ldg(a.rval + base + lane); }
-      int t = 0;
-      for (; t + 4 <= cnt; t += 4) {
-        const int c0 = __shfl_sync(0xffffffffu, ci, t), c1 = __shfl_sync(0xffffffffu, ci, t + 1);
-        const int c2 = __shfl_sync(0xffffffffu, ci, t + 2), c3 = __shfl_sync(0xffffffffu, ci, t + 3);
-        const double x0 = vec[(size_t)c0 * a.BP + b], x1 = vec[(size_t)c1 * a.BP + b];
-        const double x2 = vec[(size_t)c2 * a.BP + b], x3 = vec[(size_t)c3 * a.BP + b];
-        acc0 = fma(__shfl_sync(0xffffffffu, vi, t), x0, acc0);
-        acc1 = fma(__shfl_sync(0xffffffffu, vi, t + 1), x1, acc1);
-        acc2 = fma(__shfl_sync(0xffffffffu, vi, t + 2), x2, acc2);
-        acc3 = fma(__shfl_sync(0xffffffffu, vi, t + 3), x3, acc3);
-      }
-      for (; t < cnt; ++t)
-        acc0 = fma(__shfl_sync(0xffffffffu, vi, t), vec[(size_t)__shfl_sync(0xffffffffu, ci, t) * a.BP + b], acc0);
-    }
-    acc0 += acc2;
-    acc1 += acc3;
   }
   s_part[warp][lane] = acc0 + acc1;
   __syncthreads();
@@ -253,6 +288,54 @@ __global__ void __launch_bounds__(kThreads) k_row_batch_long(const BatchArgs a, 
   }
 }
 
+struct ColOperands { double xb, x0, at, at0, lj, uj, xh; };
+
+template <bool CHECK>
+__device__ __forceinline__ ColOperands col_load_batch(const BatchArgs& a, size_t e, const double* xhat_in, bool active) {
+  ColOperands o = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (active) {
+    o.xb = a.xbar[e]; o.x0 = a.x0[e]; o.at = a.aty[e]; o.at0 = a.aty0[e]; o.lj = a.l[e]; o.uj = a.u[e];
+    if (CHECK) o.xh = xhat_in[e];
+  }
+  return o;
+}
+
+// the per-column part of the batched column step, given (K' yhat)_j for this lane's problem
+template <bool CHECK, bool STORE>
+__device__ __forceinline__ void col_epilogue_batch(const BatchArgs& a, int j, size_t e, double atyh,
+                                                   const ColOperands& o, double tau, double w_new,
+                                                   double* xhat_out, double (&red)[10]) {
+  const double xb = o.xb, x0 = o.x0, at = o.at, at0 = o.at0, lj = o.lj, uj = o.uj;
+  const double cj = a.c[j];
+  if (CHECK) {
+    const double xh = o.xh;
+    const double dx = xb - xh, dat = atyh - at, d0 = xh - x0;
+    red[0] += dx * dx;
+    red[1] += dx * dat;
+    red[2] += d0 * d0;
+    const double r = cj - atyh;
+    const double rp = fmax(r, 0.0), rm = fmax(-r, 0.0);
+    const double viol = ((isfinite(lj) ? 0.0 : rp) + (isfinite(uj) ? 0.0 : rm)) / a.d2[j];
+    red[3] += viol * viol;
+    red[4] += cj * xh;
+    red[5] += (isfinite(lj) ? lj * rp : 0.0) - (isfinite(uj) ? uj * rm : 0.0);
+    a.aty_cand[e] = atyh;
+    const double qp = fmax(-dat, 0.0), qm = fmax(dat, 0.0);
+    red[6] += (isfinite(lj) ? lj * qp : 0.0) - (isfinite(uj) ? uj * qm : 0.0);
+    const double qv = (isfinite(lj) ? 0.0 : qp) + (isfinite(uj) ? 0.0 : qm);
+    red[7] += qv * qv;
+    red[8] += cj * dx;
+    const double pv = (isfinite(lj) ? fmax(-dx, 0.0) : 0.0) + (isfinite(uj) ? fmax(dx, 0.0) : 0.0);
+    red[9] += pv * pv;
+  }
+  const double xn = w_new * xb + (1.0 - w_new) * x0;
+  const double atn = w_new * (2.0 * atyh - at) + (1.0 - w_new) * at0;
+  const double xh2 = clampd(xn - tau * (cj - atn), lj, uj);
+  a.xbar[e] = 2.0 * xh2 - xn;
+  a.aty[e] = atn;
+  if (STORE) xhat_out[e] = xh2;
+}
+
 template <bool CHECK, bool STORE>
 __global__ void __launch_bounds__(kThreads)
 k_col_step_batch(const BatchArgs a, int iter_in_block, const double* xhat_in, double* xhat_out) {
@@ -265,41 +348,29 @@ k_col_step_batch(const BatchArgs a, int iter_in_block, const double* xhat_in, do
   const double w_new = (k + 1.0) / (k + 2.0);
   double red[10] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (__any_sync(0xffffffffu, active)) {
-    for (int i = 0; i < kRowsPerCtaB / kWarps; ++i) {
-      const int j = blockIdx.x * kRowsPerCtaB + warp * (kRowsPerCtaB / kWarps) + i;
-      if (j >= a.n) break;
+    constexpr int kPerWarp = kRowsPerCtaB / kWarps;
+    const int first = blockIdx.x * kRowsPerCtaB + warp * kPerWarp;
+    const int last = min(first + kPerWarp, a.n);
+    int j = first;
+    if (g_batch_pairs) {
+      for (; j + 1 < last; j += 2) {
+        // the seven streamed operands of both columns are requested before either product starts
+        const size_t e0 = (size_t)j * a.BP + b, e1 = e0 + a.BP;
+        const ColOperands o0 = col_load_batch<CHECK>(a, e0, xhat_in, active);
+        const ColOperands o1 = col_load_batch<CHECK>(a, e1, xhat_in, active);
+        double s0, s1;
+        row_dot_batch2(a.cptr, a.cidx, a.cval, a.yhat, j, a.BP, b, s0, s1);
+        if (!active) continue;
+        col_epilogue_batch<CHECK, STORE>(a, j, e0, s0, o0, tau, w_new, xhat_out, red);
+        col_epilogue_batch<CHECK, STORE>(a, j + 1, e1, s1, o1, tau, w_new, xhat_out, red);
+      }
+    }
+    for (; j < last; ++j) {
+      const size_t e = (size_t)j * a.BP + b;
+      const ColOperands o = col_load_batch<CHECK>(a, e, xhat_in, active);
       const double atyh = row_dot_batch(a.cptr, a.cidx, a.cval, a.yhat, j, a.BP, b);
       if (!active) continue;
-      const size_t e = (size_t)j * a.BP + b;
-      const double xb = a.xbar[e], x0 = a.x0[e], at = a.aty[e], at0 = a.aty0[e];
-      const double cj = a.c[j], lj = a.l[e], uj = a.u[e];
-      if (CHECK) {
-        const double xh = xhat_in[e];
-        const double dx = xb - xh, dat = atyh - at, d0 = xh - x0;
-        red[0] += dx * dx;
-        red[1] += dx * dat;
-        red[2] += d0 * d0;
-        const double r = cj - atyh;
-        const double rp = fmax(r, 0.0), rm = fmax(-r, 0.0);
-        const double viol = ((isfinite(lj) ? 0.0 : rp) + (isfinite(uj) ? 0.0 : rm)) / a.d2[j];
-        red[3] += viol * viol;
-        red[4] += cj * xh;
-        red[5] += (isfinite(lj) ? lj * rp : 0.0) - (isfinite(uj) ? uj * rm : 0.0);
-        a.aty_cand[e] = atyh;
-        const double qp = fmax(-dat, 0.0), qm = fmax(dat, 0.0);
-        red[6] += (isfinite(lj) ? lj * qp : 0.0) - (isfinite(uj) ? uj * qm : 0.0);
-        const double qv = (isfinite(lj) ? 0.0 : qp) + (isfinite(uj) ? 0.0 : qm);
-        red[7] += qv * qv;
-        red[8] += cj * dx;
-        const double pv = (isfinite(lj) ? fmax(-dx, 0.0) : 0.0) + (isfinite(uj) ? fmax(dx, 0.0) : 0.0);
-        red[9] += pv * pv;
-      }
-      const double xn = w_new * xb + (1.0 - w_new) * x0;
-      const double atn = w_new * (2.0 * atyh - at) + (1.0 - w_new) * at0;
-      const double xh2 = clampd(xn - tau * (cj - atn), lj, uj);
-      a.xbar[e] = 2.0 * xh2 - xn;
-      a.aty[e] = atn;
-      if (STORE) xhat_out[e] = xh2;
+      col_epilogue_batch<CHECK, STORE>(a, j, e, atyh, o, tau, w_new, xhat_out, red);
     }
   }
   if (CHECK) {
@@ -553,9 +624,9 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
   cudaStream_t st = ctx->stream;
   ctx->launches = 0;
   {
-    const char* v = std::getenv("MIPCU_BATCH_SHUFFLE");
-    const int scalar = (v && std::atoi(v)) ? 0 : 1;
-    MIPCU_CK(cudaMemcpyToSymbolAsync(g_batch_scalar_loads, &scalar, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+    const char* v = std::getenv("MIPCU_BATCH_PAIRS");     // laboratory switch: 0 = one row at a time (round 1)
+    const int pairs = (v && !std::atoi(v)) ? 0 : 1;
+    MIPCU_CK(cudaMemcpyToSymbolAsync(g_batch_pairs, &pairs, sizeof(int), 0, cudaMemcpyHostToDevice, st));
   }
   if (!ctx->d_sc) MIPCU_CK(cudaMalloc(&ctx->d_sc, sizeof(Scalars)));
   if (!ctx->h_sc) MIPCU_CK(cudaMallocHost(&ctx->h_sc, sizeof(Scalars) * 2));

@@ -14,6 +14,7 @@
 #include "solver.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -24,6 +25,8 @@
 #include <numeric>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
+#include <cstring>
 
 #include <mipcu.h>
 
@@ -287,19 +290,41 @@ void CudaSolver::load_csr(Solver const&, std::int64_t m, std::int64_t n, std::in
   std::size_t const first = m_columns.size();
   double const inf = infinity();
   // validate everything before the row store is touched: a bad array must not leave half a model behind
+  // (big models: a few host threads - this copy is on the end-to-end path of every bulk-loaded solve)
   for (std::int64_t j = 0; j < n && var_type; ++j)
     if (var_type[j] < 0 || var_type[j] > 2) fail("miplib_cuda_load_csr: unknown variable type");
-  for (std::int64_t i = 0; i < m; ++i)
-  {
-    std::int32_t prev = -1;
-    if (row_ptr[i + 1] < row_ptr[i]) fail("miplib_cuda_load_csr: row_ptr must be non-decreasing");
-    for (std::int64_t k = row_ptr[i]; k < row_ptr[i + 1]; ++k)
+  std::int64_t const nnz_new = row_ptr[m];
+  unsigned const workers = nnz_new >= (std::int64_t(1) << 22)
+                             ? std::max(1u, std::min(8u, std::thread::hardware_concurrency())) : 1u;
+  auto parallel = [&](std::int64_t count, auto&& body) {
+    if (workers == 1 || count < 1024) { body(std::int64_t(0), count); return; }
+    std::vector<std::thread> pool;
+    for (unsigned w = 0; w < workers; ++w)
+      pool.emplace_back([&, w] { body(count * w / workers, count * (w + 1) / workers); });
+    for (std::thread& t : pool) t.join();
+  };
+  auto const tt0 = std::chrono::steady_clock::now();
+  auto lap = [&](char const* what) {
+    if (std::getenv("MIPLIB_CUDA_TIMING"))
+      std::fprintf(stderr, "[load_csr] %s %.3f s\n", what,
+                   std::chrono::duration<double>(std::chrono::steady_clock::now() - tt0).count());
+  };
+  std::atomic<int> bad{0};
+  parallel(m, [&](std::int64_t r0, std::int64_t r1) {
+    for (std::int64_t i = r0; i < r1; ++i)
     {
-      if (col_idx[k] <= prev || col_idx[k] >= n)
-        fail("miplib_cuda_load_csr: column indices must be increasing inside a row and below n");
-      prev = col_idx[k];
+      if (row_ptr[i + 1] < row_ptr[i] || row_ptr[i] < 0 || row_ptr[i + 1] > nnz_new) { bad = 1; return; }
+      std::int32_t prev = -1;
+      for (std::int64_t k = row_ptr[i]; k < row_ptr[i + 1]; ++k)
+      {
+        if (col_idx[k] <= prev || col_idx[k] >= n) { bad = 2; return; }
+        prev = col_idx[k];
+      }
     }
-  }
+  });
+  if (bad == 1) fail("miplib_cuda_load_csr: row_ptr must be non-decreasing");
+  if (bad == 2) fail("miplib_cuda_load_csr: column indices must be increasing inside a row and below n");
+  lap("validated");
   m_columns.reserve(first + static_cast<std::size_t>(n));
   for (std::int64_t j = 0; j < n; ++j)
   {
@@ -309,14 +334,16 @@ void CudaSolver::load_csr(Solver const&, std::int64_t m, std::int64_t n, std::in
     col.ub = col.type == Var::Type::Binary ? 1.0 : std::min(ub[j], inf);
     m_columns.push_back(col);
   }
-  m_row_idx.reserve(m_row_idx.size() + static_cast<std::size_t>(row_ptr[m]));
-  m_row_val.reserve(m_row_val.size() + static_cast<std::size_t>(row_ptr[m]));
+  lap("columns");
   std::int64_t const nnz_before = static_cast<std::int64_t>(m_row_idx.size());
-  m_row_idx.insert(m_row_idx.end(), col_idx, col_idx + row_ptr[m]);
+  // range inserts: one pass, no zero fill (a resize + threaded memcpy measured slower: the copy is bound
+  // by host memory bandwidth, not by one core)
+  m_row_idx.insert(m_row_idx.end(), col_idx, col_idx + nnz_new);
   if (first)
     for (std::size_t k = static_cast<std::size_t>(nnz_before); k < m_row_idx.size(); ++k)
       m_row_idx[k] += static_cast<std::int32_t>(first);
-  m_row_val.insert(m_row_val.end(), val, val + row_ptr[m]);
+  m_row_val.insert(m_row_val.end(), val, val + nnz_new);
+  lap("nonzeros copied");
   m_row_start.reserve(m_row_start.size() + static_cast<std::size_t>(m));
   m_row_lo.reserve(m_row_lo.size() + static_cast<std::size_t>(m));
   m_row_hi.reserve(m_row_hi.size() + static_cast<std::size_t>(m));
@@ -327,8 +354,10 @@ void CudaSolver::load_csr(Solver const&, std::int64_t m, std::int64_t n, std::in
     m_row_hi.push_back(std::min(row_hi[i], inf));
   }
   m_row_alive.insert(m_row_alive.end(), static_cast<std::size_t>(m), char(1));
+  lap("row sides");
   m_objective.assign(m_columns.size(), 0.0);
   for (std::int64_t j = 0; j < n; ++j) m_objective[first + static_cast<std::size_t>(j)] = c[j];
+  lap("objective");
   m_sense = maximize ? Solver::Sense::Maximize : Solver::Sense::Minimize;
   m_structure_dirty = true;
   m_objective_dirty = true;
