@@ -48,23 +48,40 @@ struct BatchArgs {
 // warp-uniform loads, the gather is one contiguous 256-byte segment per nonzero; two accumulator
 // chains (even / odd entries), fixed summation order.
 //
-// ncu (round 2, profiles/r02_batch_engine.md) shows these kernels bound by LATENCY, not by a memory
-// level: DRAM 22 - 56 % busy, L2 29 - 37 %, the L1 -> XBAR port 19 - 25 %, about 16 cycles of
-// long-scoreboard stall per issued instruction at 50 - 57 % active warps.  A warp walks its 8 rows one
-// after the other and every row is a chain ptr -> (val, idx) -> gather -> step vectors -> store.  Two
-// remedies, switchable for the A/B with MIPCU_BATCH_PAIRS (default 1):
-//   * rows are taken in PAIRS: the step vectors of both rows are requested before either product starts,
-//     and the two products run interleaved (row_dot_batch2: four gathers in flight instead of two) - the
-//     per-row summation order is unchanged, results are bit-identical to the one-row loop;
-//   * the CTA-per-row kernel for long rows keeps 8 chains per warp instead of 2.
-// (A third variant - row entries fetched one per lane and handed round by warp shuffle - was measured
-// slower than the plain loop, 96 / 112 us against 78 / 102 us on config 4, and is gone.)
-__device__ int g_batch_pairs = 1;
+// Round 2 tried three ways of putting more loads in flight per warp, all measured on one B200 on
+// configs 4 / 5 with 128 nodes (profiles/r02_batch_engine.md) and all SLOWER than this plain loop:
+//   * row entries fetched one per lane and handed round by warp shuffle, four gathers in flight:
+//     row / column kernel 96 / 112 us against 78 / 102 us on config 4 (removed);
+//   * rows taken in pairs - step vectors of both rows requested before either product, the two
+//     products interleaved (row_dot_batch2), 8 chains in the CTA-per-row kernel: 107 / 146 us against
+//     80 / 115 us (MIPCU_BATCH_PAIRS=1);
+//   * four accumulator chains in the one-row loop: 84 / 119 us against 80 / 115 us (MIPCU_BATCH_PAIRS=2).
+// ncu on the shipped loops: DRAM 22 % (row) / 52 - 56 % (column) busy, L2 29 - 37 %, L1 -> XBAR port
+// 19 - 25 %, 50 - 57 % active warps, no level saturated; every extra register the variants spend costs
+// resident warps (48 registers = 5 CTAs per SM) and the trade has been negative three times.  The
+// throughput that matters for a branch and bound comes from deciding nodes early (MIPCU_BRANCH), not
+// from these loops.
+__device__ int g_batch_pairs = 0;
 
 __device__ __forceinline__ double row_dot_batch(const int* __restrict__ ptr, const int* __restrict__ idx,
                                                 const double* __restrict__ val,
                                                 const double* __restrict__ vec, int row, int BP, int b) {
   const int beg = ptr[row], end = ptr[row + 1];
+  if (g_batch_pairs == 2) {      // four chains: twice the gathers in flight for four more registers
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int k = beg;
+    for (; k + 3 < end; k += 4) {
+      const int c0 = idx[k], c1 = idx[k + 1], c2 = idx[k + 2], c3 = idx[k + 3];
+      const double x0 = vec[(size_t)c0 * BP + b], x1 = vec[(size_t)c1 * BP + b];
+      const double x2 = vec[(size_t)c2 * BP + b], x3 = vec[(size_t)c3 * BP + b];
+      a0 = fma(val[k], x0, a0);
+      a1 = fma(val[k + 1], x1, a1);
+      a2 = fma(val[k + 2], x2, a2);
+      a3 = fma(val[k + 3], x3, a3);
+    }
+    for (; k < end; ++k) a0 = fma(val[k], vec[(size_t)idx[k] * BP + b], a0);
+    return (a0 + a1) + (a2 + a3);
+  }
   double a0 = 0.0, a1 = 0.0;
   int k = beg;
   for (; k + 1 < end; k += 2) {
@@ -170,7 +187,7 @@ __global__ void __launch_bounds__(kThreads) k_row_step_batch(const BatchArgs a, 
     const int first = blockIdx.x * kRowsPerCtaB + warp * kPerWarp;
     const int last = min(first + kPerWarp, a.m);
     int row = first;
-    if (g_batch_pairs) {
+    if (g_batch_pairs == 1) {
       for (; row + 1 < last; row += 2) {
         // both rows' step vectors are on their way before either product starts
         const size_t e0 = (size_t)row * a.BP + b, e1 = e0 + a.BP;
@@ -352,7 +369,7 @@ k_col_step_batch(const BatchArgs a, int iter_in_block, const double* xhat_in, do
     const int first = blockIdx.x * kRowsPerCtaB + warp * kPerWarp;
     const int last = min(first + kPerWarp, a.n);
     int j = first;
-    if (g_batch_pairs) {
+    if (g_batch_pairs == 1) {
       for (; j + 1 < last; j += 2) {
         // the seven streamed operands of both columns are requested before either product starts
         const size_t e0 = (size_t)j * a.BP + b, e1 = e0 + a.BP;
@@ -624,8 +641,8 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
   cudaStream_t st = ctx->stream;
   ctx->launches = 0;
   {
-    const char* v = std::getenv("MIPCU_BATCH_PAIRS");     // laboratory switch: 0 = one row at a time (round 1)
-    const int pairs = (v && !std::atoi(v)) ? 0 : 1;
+    const char* v = std::getenv("MIPCU_BATCH_PAIRS");     // laboratory switch: 0 round-1 loops, 1 row pairs, 2 four chains
+    const int pairs = v ? std::atoi(v) : 0;
     MIPCU_CK(cudaMemcpyToSymbolAsync(g_batch_pairs, &pairs, sizeof(int), 0, cudaMemcpyHostToDevice, st));
   }
   if (!ctx->d_sc) MIPCU_CK(cudaMalloc(&ctx->d_sc, sizeof(Scalars)));
