@@ -579,21 +579,36 @@ __global__ void __launch_bounds__(kThreads) k_aty_batch(const BatchArgs a) {
   }
 }
 
+// node_of[slot]: the caller's node whose problem lives in lane `slot` (lanes are re-packed as nodes finish)
 __global__ void k_unscale_batch(const double* __restrict__ xhat, const double* __restrict__ d2,
-                                double* __restrict__ x_out, int n, int B, int BP) {
+                                const int* __restrict__ node_of, double* __restrict__ x_out, int n, int B, int BP) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (size_t)n * BP) return;
-  const int b = (int)(e % BP), j = (int)(e / BP);
+  const int b = node_of[(int)(e % BP)], j = (int)(e / BP);
   if (b < B) x_out[(size_t)b * n + j] = xhat[e] * d2[j];
+}
+
+// Lane compaction: dst[r][s] = src[r][order[s]] for every row r of a [rows][BP] array.
+__global__ void k_permute_lanes(const double* __restrict__ src, double* __restrict__ dst,
+                                const int* __restrict__ order, size_t count, int BP) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= count) return;
+  const size_t row = e / BP;
+  dst[e] = src[row * BP + order[(int)(e % BP)]];
+}
+__global__ void k_permute_scalars(const Scalars* __restrict__ src, Scalars* __restrict__ dst,
+                                  const int* __restrict__ order, int BP) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < BP) dst[s] = src[order[s]];
 }
 
 // duals back in the caller's terms and row order
 __global__ void k_unscale_duals_batch(const double* __restrict__ yhat, const int* __restrict__ row_perm,
-                                      const double* __restrict__ d1, double sgn, double* __restrict__ y_out,
-                                      int m, int B, int BP) {
+                                      const double* __restrict__ d1, double sgn, const int* __restrict__ node_of,
+                                      double* __restrict__ y_out, int m, int B, int BP) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (size_t)m * BP) return;
-  const int b = (int)(e % BP), i = (int)(e / BP);
+  const int b = node_of[(int)(e % BP)], i = (int)(e / BP);
   if (b < B) y_out[(size_t)b * m + (row_perm ? row_perm[i] : i)] = sgn * yhat[e] * d1[i];
 }
 
@@ -736,7 +751,17 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
     s.done = b < B ? 0 : 1 + MIPCU_OPTIMAL;     // pad lanes never run
   }
   MIPCU_CK(cudaMemcpyAsync(a.sc, h.data(), sizeof(Scalars) * BP, cudaMemcpyHostToDevice, st));
-  const dim3 grid_rows(std::max(nblk_row, 1), BP / 32), grid_cols(std::max(nblk_col, 1), BP / 32);
+  // Lanes are re-packed as nodes finish (compact, below): `chunks` 32-lane groups hold every problem that
+  // still runs, and only those are launched.
+  int chunks = BP / 32;
+  std::vector<int> slot_of(BP), node_of(BP);
+  for (int i = 0; i < BP; ++i) slot_of[i] = node_of[i] = i;
+  int* d_order = buf.get<int>(BP);
+  int* d_node_of = buf.get<int>(BP);
+  MIPCU_CK(cudaMemcpyAsync(d_node_of, node_of.data(), sizeof(int) * BP, cudaMemcpyHostToDevice, st));
+  double* scratch = buf.get<double>(std::max<size_t>(std::max(nB, mB), 1));
+  Scalars* sc_scratch = buf.get<Scalars>(BP);
+  const bool allow_compaction = !(std::getenv("MIPCU_BATCH_COMPACT") && !std::atoi(std::getenv("MIPCU_BATCH_COMPACT")));
   const int grid_elem = grid_for(std::max(nB, mB));
   if (grid_elem) {
     k_restart_apply_batch<<<grid_elem, kThreads, 0, st>>>(a);
@@ -753,12 +778,13 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
       const bool timed = i == (period > 2 ? 1 : 0);
       if (timed) MIPCU_CK(cudaEventRecord(ev_t[0], st));
       if (m && long_rows) {
-        const dim3 g(m, BP / 32);
+        const dim3 g(m, chunks);
         if (first || last) k_row_batch_long<true, 0><<<g, kThreads, 0, st>>>(a, i, last ? 1 : 0);
         else k_row_batch_long<false, 0><<<g, kThreads, 0, st>>>(a, i, 0);
         ctx->launches++;
         if (last) { k_row_batch_long<false, 1><<<g, kThreads, 0, st>>>(a, i, 0); ctx->launches++; }
       } else if (m) {
+        const dim3 grid_rows(std::max(nblk_row, 1), chunks);
         if (first || last) k_row_step_batch<true><<<grid_rows, kThreads, 0, st>>>(a, i, last ? 1 : 0);
         else k_row_step_batch<false><<<grid_rows, kThreads, 0, st>>>(a, i, 0);
         ctx->launches++;
@@ -769,6 +795,7 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
       double* xo = last ? a.xhat_first : (i == period - 2 ? a.xhat_chk : nullptr);
       if (n) {
         const bool chk = first || last;
+        const dim3 grid_cols(std::max(nblk_col, 1), chunks);
         if (chk && xo) k_col_step_batch<true, true><<<grid_cols, kThreads, 0, st>>>(a, i, xin, xo);
         else if (chk) k_col_step_batch<true, false><<<grid_cols, kThreads, 0, st>>>(a, i, xin, xo);
         else if (xo) k_col_step_batch<false, true><<<grid_cols, kThreads, 0, st>>>(a, i, xin, xo);
@@ -776,11 +803,56 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
         ctx->launches++;
       }
       if (timed) MIPCU_CK(cudaEventRecord(ev_t[2], st));
-      if (first) { k_ctrl_first_batch<<<BP / 32, kThreads, 0, st>>>(a, nblk_row, nblk_col); ctx->launches++; }
+      if (first) { k_ctrl_first_batch<<<chunks, kThreads, 0, st>>>(a, nblk_row, nblk_col); ctx->launches++; }
     }
-    k_ctrl_check_batch<<<BP / 32, kThreads, 0, st>>>(a, nblk_row, nblk_col);
+    k_ctrl_check_batch<<<chunks, kThreads, 0, st>>>(a, nblk_row, nblk_col);
     ctx->launches++;
     if (grid_elem) { k_restart_apply_batch<<<grid_elem, kThreads, 0, st>>>(a); ctx->launches++; }
+  };
+
+  // Re-pack the lanes once a whole 32-lane group can be retired: problems that still run move to the front
+  // (stable), finished ones keep their final vectors further back.  A round is as long as its slowest
+  // node (config 5: mean 6.8k iterations, max 21k), and a warp streams its rows for all 32 lanes as long
+  // as one of them runs; after compaction the kernels are launched over the live groups only.
+  auto compact = [&]() {
+    if (!allow_compaction || chunks <= 1) return;
+    std::vector<int> order;
+    order.reserve(BP);
+    for (int sl = 0; sl < BP; ++sl) if (!h[sl].done) order.push_back(sl);
+    const int live = (int)order.size();
+    if ((live + 31) / 32 >= chunks) return;
+    for (int sl = 0; sl < BP; ++sl) if (h[sl].done) order.push_back(sl);
+    MIPCU_CK(cudaMemcpyAsync(d_order, order.data(), sizeof(int) * BP, cudaMemcpyHostToDevice, st));
+    double** nvec[] = {const_cast<double**>(&a.l), const_cast<double**>(&a.u), &a.xbar, &a.x0, &a.aty, &a.aty0,
+                       &a.xhat_first, &a.xhat_chk, &a.aty_cand};
+    double** mvec[] = {&a.y, &a.y0, &a.yhat, &a.kx_save};
+    for (double** v : nvec) {
+      if (!nB) break;
+      k_permute_lanes<<<grid_for(nB), kThreads, 0, st>>>(*v, scratch, d_order, nB, BP);
+      std::swap(*v, scratch);
+      ctx->launches++;
+    }
+    for (double** v : mvec) {
+      if (!mB) break;
+      k_permute_lanes<<<grid_for(mB), kThreads, 0, st>>>(*v, scratch, d_order, mB, BP);
+      std::swap(*v, scratch);
+      ctx->launches++;
+    }
+    k_permute_scalars<<<grid_for(BP), kThreads, 0, st>>>(a.sc, sc_scratch, d_order, BP);
+    std::swap(a.sc, sc_scratch);
+    ctx->launches++;
+    std::vector<int> new_node_of(BP);
+    std::vector<Scalars> new_h(BP);
+    for (int sl = 0; sl < BP; ++sl) {
+      new_node_of[sl] = node_of[order[sl]];
+      new_h[sl] = h[order[sl]];
+      slot_of[new_node_of[sl]] = sl;
+    }
+    node_of.swap(new_node_of);
+    h.swap(new_h);
+    MIPCU_CK(cudaMemcpyAsync(d_node_of, node_of.data(), sizeof(int) * BP, cudaMemcpyHostToDevice, st));
+    MIPCU_CK(cudaStreamSynchronize(st));      // `order` / `node_of` are host vectors about to change again
+    chunks = std::max(1, (live + 31) / 32);
   };
 
   cudaEvent_t ev_begin = ctx->ev[0], ev_end = ctx->ev[1];
@@ -799,8 +871,9 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
       row_us += 1e3 * ta; col_us += 1e3 * tb; ++timed_blocks;
     }
     bool all_done = true;
-    for (int b = 0; b < B; ++b) all_done = all_done && h[b].done;
+    for (int b = 0; b < B; ++b) all_done = all_done && h[slot_of[b]].done;
     if (all_done || total >= iter_limit) break;
+    compact();
     if (time_limit > 0.0 &&
         std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > time_limit) {
       timed_out = true;
@@ -810,13 +883,13 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
   MIPCU_CK(cudaEventRecord(ev_end, st));
   if (x_out && nB) {
     double* d_x = buf.get<double>((size_t)B * n);
-    k_unscale_batch<<<grid_for(nB), kThreads, 0, st>>>(a.xhat_chk, ctx->d2, d_x, n, B, BP);
+    k_unscale_batch<<<grid_for(nB), kThreads, 0, st>>>(a.xhat_chk, ctx->d2, d_node_of, d_x, n, B, BP);
     ctx->launches++;
     MIPCU_CK(cudaMemcpyAsync(x_out, d_x, sizeof(double) * (size_t)B * n, cudaMemcpyDeviceToHost, st));
   }
   if (y_out && mB) {
     double* d_y = buf.get<double>((size_t)B * m);
-    k_unscale_duals_batch<<<grid_for(mB), kThreads, 0, st>>>(a.yhat, ctx->row_perm, ctx->d1, sgn, d_y, m, B, BP);
+    k_unscale_duals_batch<<<grid_for(mB), kThreads, 0, st>>>(a.yhat, ctx->row_perm, ctx->d1, sgn, d_node_of, d_y, m, B, BP);
     ctx->launches++;
     MIPCU_CK(cudaMemcpyAsync(y_out, d_y, sizeof(double) * (size_t)B * m, cudaMemcpyDeviceToHost, st));
   }
@@ -825,7 +898,7 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
   MIPCU_CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   for (int b = 0; b < B; ++b) {
-    const Scalars& s = h[b];
+    const Scalars& s = h[slot_of[b]];
     mipcu_stats& o = out[b];
     o = mipcu_stats();
     o.status = s.done ? s.done - 1 : (timed_out ? MIPCU_TIME_LIMIT : MIPCU_ITERATION_LIMIT);
