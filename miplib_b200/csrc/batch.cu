@@ -759,7 +759,8 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
   int* d_order = buf.get<int>(BP);
   int* d_node_of = buf.get<int>(BP);
   MIPCU_CK(cudaMemcpyAsync(d_node_of, node_of.data(), sizeof(int) * BP, cudaMemcpyHostToDevice, st));
-  double* scratch = buf.get<double>(std::max<size_t>(std::max(nB, mB), 1));
+  double* scratch_n = buf.get<double>(std::max<size_t>(nB, 1));   // the arrays rotate through these: one per shape
+  double* scratch_m = buf.get<double>(std::max<size_t>(mB, 1));
   Scalars* sc_scratch = buf.get<Scalars>(BP);
   const bool allow_compaction = !(std::getenv("MIPCU_BATCH_COMPACT") && !std::atoi(std::getenv("MIPCU_BATCH_COMPACT")));
   const int grid_elem = grid_for(std::max(nB, mB));
@@ -828,14 +829,14 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
     double** mvec[] = {&a.y, &a.y0, &a.yhat, &a.kx_save};
     for (double** v : nvec) {
       if (!nB) break;
-      k_permute_lanes<<<grid_for(nB), kThreads, 0, st>>>(*v, scratch, d_order, nB, BP);
-      std::swap(*v, scratch);
+      k_permute_lanes<<<grid_for(nB), kThreads, 0, st>>>(*v, scratch_n, d_order, nB, BP);
+      std::swap(*v, scratch_n);
       ctx->launches++;
     }
     for (double** v : mvec) {
       if (!mB) break;
-      k_permute_lanes<<<grid_for(mB), kThreads, 0, st>>>(*v, scratch, d_order, mB, BP);
-      std::swap(*v, scratch);
+      k_permute_lanes<<<grid_for(mB), kThreads, 0, st>>>(*v, scratch_m, d_order, mB, BP);
+      std::swap(*v, scratch_m);
       ctx->launches++;
     }
     k_permute_scalars<<<grid_for(BP), kThreads, 0, st>>>(a.sc, sc_scratch, d_order, BP);
