@@ -55,19 +55,30 @@ CudaSolver::CudaSolver(bool verbose) : m_verbose(verbose) {}
 // Solver per model - the reference's usage, README.md:24-60 - therefore gets its next context out of
 // this per-device cache, reset to default parameters with no model loaded.
 namespace {
-std::mutex g_ctx_cache_mutex;
-std::vector<std::pair<int, mipcu_ctx*>> g_ctx_cache;     // (device, context)
+// heap-allocated and never destroyed: a Solver with static storage duration may be torn down after
+// this translation unit's own statics
+struct ContextCache
+{
+  std::mutex mutex;
+  std::vector<std::pair<int, mipcu_ctx*>> free;          // (device, context)
+};
+ContextCache& context_cache()
+{
+  static ContextCache* cache = new ContextCache();
+  return *cache;
+}
 constexpr std::size_t kCtxCacheMax = 16;
 
 mipcu_ctx* acquire_context(int device)
 {
   {
-    std::lock_guard<std::mutex> lock(g_ctx_cache_mutex);
-    for (std::size_t i = 0; i < g_ctx_cache.size(); ++i)
-      if (g_ctx_cache[i].first == device)
+    ContextCache& cache = context_cache();
+    std::lock_guard<std::mutex> lock(cache.mutex);
+    for (std::size_t i = 0; i < cache.free.size(); ++i)
+      if (cache.free[i].first == device)
       {
-        mipcu_ctx* ctx = g_ctx_cache[i].second;
-        g_ctx_cache.erase(g_ctx_cache.begin() + static_cast<std::ptrdiff_t>(i));
+        mipcu_ctx* ctx = cache.free[i].second;
+        cache.free.erase(cache.free.begin() + static_cast<std::ptrdiff_t>(i));
         return ctx;
       }
   }
@@ -81,10 +92,11 @@ void release_context(int device, mipcu_ctx* ctx)
   if (!ctx) return;
   if (mipcu_reset(ctx) == 0)
   {
-    std::lock_guard<std::mutex> lock(g_ctx_cache_mutex);
-    if (g_ctx_cache.size() < kCtxCacheMax)
+    ContextCache& cache = context_cache();
+    std::lock_guard<std::mutex> lock(cache.mutex);
+    if (cache.free.size() < kCtxCacheMax)
     {
-      g_ctx_cache.emplace_back(device, ctx);
+      cache.free.emplace_back(device, ctx);
       return;
     }
   }
