@@ -708,7 +708,7 @@ CudaSolver::LpOutcome CudaSolver::solve_lp_on_device(std::vector<double>* x_out,
     y_out->resize(m_device_row_of.size());
     check(m_ctx, mipcu_get_y(m_ctx, y_out->data()));
   }
-  return {st.status, st.primal_obj, st.dual_obj, st.iterations};
+  return {st.status, st.primal_obj, st.dual_obj, st.iterations, st.rel_primal_res};
 }
 
 std::pair<Solver::Result, bool> CudaSolver::solve()
@@ -893,7 +893,19 @@ std::pair<Solver::Result, bool> CudaSolver::solve_continuous()
       case MIPCU_UNBOUNDED: return {R::Unbounded, false};
       case MIPCU_INFEASIBLE_OR_UNBOUNDED: return {R::InfeasibleOrUnbounded, false};
       case MIPCU_ITERATION_LIMIT:
-      case MIPCU_TIME_LIMIT: return {R::Interrupted, false};
+      case MIPCU_TIME_LIMIT:
+        // interrupted with a point in hand: like SCIP (has_solution = a primal solution exists,
+        // reference miplib/scip/solver.cpp:379-410) the last iterate is reported as the incumbent when it
+        // is feasible to ten times the tolerance; lp_solve's timeout row (miplib/lpsolve/solver.cpp:189-192)
+        // has no solution, which is what a still-infeasible iterate maps to
+        if (lp.rel_primal_res <= 10.0 * m_feas_tol && x.size() == m_columns.size())
+        {
+          m_solution = std::move(x);
+          m_has_solution = true;
+          m_objective_value = std::inner_product(m_solution.begin(), m_solution.end(), m_objective.begin(), 0.0);
+          return {R::Interrupted, true};
+        }
+        return {R::Interrupted, false};
       case MIPCU_NUMERICAL_ERROR: return {R::Error, false};
       default: return {R::Other, false};
     }

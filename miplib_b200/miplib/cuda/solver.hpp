@@ -152,6 +152,7 @@ struct CudaSolver : detail::ISolver
     int status;
     double primal_obj, dual_obj;
     std::int64_t iterations;
+    double rel_primal_res = 0;
   };
   LpOutcome solve_lp_on_device(std::vector<double>* x_out, std::vector<double>* y_out);
   std::pair<Solver::Result, bool> solve_continuous();
