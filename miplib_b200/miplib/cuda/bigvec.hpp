@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <mutex>
 #include <new>
+#include <type_traits>
+#include <utility>
 #include <unordered_map>
 #include <vector>
 
@@ -86,6 +88,17 @@ struct RecycleAlloc
   template<class U> RecycleAlloc(RecycleAlloc<U> const&) {}
   T* allocate(std::size_t n) { return static_cast<T*>(BlockCache::get().allocate(n * sizeof(T))); }
   void deallocate(T* p, std::size_t n) noexcept { BlockCache::get().deallocate(p, n * sizeof(T)); }
+  // resize() DEFAULT-initialises (no zero fill for arithmetic types): the bulk ingress grows a vector
+  // by hundreds of megabytes and then fills the new tail from several threads, and a value-initialising
+  // resize would write every byte once more on one core first
+  template<class U> void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value)
+  {
+    ::new (static_cast<void*>(p)) U;
+  }
+  template<class U, class... Args> void construct(U* p, Args&&... args)
+  {
+    ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...);
+  }
   template<class U> bool operator==(RecycleAlloc<U> const&) const { return true; }
   template<class U> bool operator!=(RecycleAlloc<U> const&) const { return false; }
 };

@@ -1,3 +1,4 @@
+#include <cstring>
 #include "capi.hpp"
 
 #include <exception>
@@ -69,8 +70,7 @@ int miplib_cuda_get_values(miplib::Solver* p_solver, double* x, double* objectiv
   return guarded([&] {
     miplib::CudaSolver const& s = miplib::CudaSolver::of(*p_solver);
     if (!s.m_has_solution) throw std::logic_error("Attempt to access values before a solution was found.");
-    if (x)
-      for (std::size_t j = 0; j < s.m_solution.size(); ++j) x[j] = s.m_solution[j];
+    if (x && !s.m_solution.empty()) std::memcpy(x, s.m_solution.data(), sizeof(double) * s.m_solution.size());
     if (objective) *objective = s.m_objective_value;
   });
 }

@@ -250,7 +250,7 @@ void CudaSolver::read_mps(Solver const& solver, std::string const& path)
   }
   load_csr(solver, static_cast<std::int64_t>(rows.size()), static_cast<std::int64_t>(cols.size()), ptr.data(),
            idx.data(), val.data(), c.data(), lb.data(), ub.data(), types.data(), lo.data(), hi.data(), maximize);
-  for (std::size_t j = 0; j < col_names.size(); ++j) m_columns[first_new + j].name = col_names[j];
+  for (std::size_t j = 0; j < col_names.size(); ++j) m_column_names[first_new + j] = col_names[j];
 }
 
 }  // namespace miplib

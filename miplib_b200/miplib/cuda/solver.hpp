@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <limits>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../solver.hpp"
@@ -90,13 +91,22 @@ struct CudaSolver : detail::ISolver
   void read_mps(Solver const& solver, std::string const& path);
 
   // ---- model store (host) --------------------------------------------------------------------
+  // 24 bytes and trivially copyable: loops over the columns of a multi-million-column model stream
+  // 3 doubles per column, and the bulk ingress fills new columns from several threads.  Names are
+  // rare on such models and live in a side map.
   struct Column
   {
     Var::Type type;
     double lb, ub;
-    std::optional<std::string> name;
   };
   BigVec<Column> m_columns;
+  std::unordered_map<std::size_t, std::string> m_column_names;
+  std::optional<std::string> column_name(std::size_t column) const
+  {
+    auto it = m_column_names.find(column);
+    if (it == m_column_names.end()) return std::nullopt;
+    return it->second;
+  }
   // rows in posting order; row r owns entries [m_row_start[r], m_row_start[r+1]) sorted by column
   // (BigVec: the large buffers are recycled between solver objects, bigvec.hpp)
   BigVec<std::int64_t> m_row_start{0};

@@ -19,8 +19,8 @@ double CudaVar::value() const
 }
 
 Var::Type CudaVar::type() const { return backend().m_columns[m_column].type; }
-std::optional<std::string> CudaVar::name() const { return backend().m_columns[m_column].name; }
-void CudaVar::set_name(std::string const& new_name) { backend().m_columns[m_column].name = new_name; }
+std::optional<std::string> CudaVar::name() const { return backend().column_name(m_column); }
+void CudaVar::set_name(std::string const& new_name) { backend().m_column_names[m_column] = new_name; }
 double CudaVar::lb() const { return backend().m_columns[m_column].lb; }
 double CudaVar::ub() const { return backend().m_columns[m_column].ub; }
 
