@@ -3,17 +3,18 @@
 // batched step kernels", section 8e).
 //
 // Layout: every iterate vector is stored [n][BP] / [m][BP] with the batch index fastest
-// (BP = B rounded up to 32).  A warp owns one matrix row and its 32 lanes are 32 LPs: the
-// (val, idx) pair of a nonzero is loaded once (warp-uniform) and used by 32 problems, and the
-// gather `xbar[col][b .. b+32)` is one contiguous 256-byte segment - two full lines per nonzero
-// for 32 problems instead of one line per problem as in the single-LP kernels, which is what
-// makes node LPs cheap.  There is no sub-warp reduction at all: a lane accumulates its own row
-// sum.  Every LP keeps its own control block (restart schedule, primal weight, done flag), the
-// same arithmetic as kernels.cuh / solve.cu, one lane per problem.
+// (BP = B rounded up to 32, 64 or 128).  A warp owns one matrix row and its 32 lanes hold P = 1, 2
+// or 4 adjacent LPs each: the (val, idx) pair of a nonzero is loaded once (warp-uniform) and used by
+// 32 P problems, and the gather `xbar[col][b .. b + 32 P)` is one contiguous segment of 256 P bytes -
+// full lines shared by all problems instead of one line per problem as in the single-LP kernels,
+// which is what makes node LPs cheap.  There is no sub-warp reduction at all: a lane accumulates
+// its own row sums.  Every LP keeps its own control block (restart schedule, primal weight, done
+// flag), the same arithmetic as kernels.cuh / solve.cu.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "internal.h"
@@ -40,383 +41,614 @@ struct BatchArgs {
   double *y, *y0, *yhat;                                              // [m][BP]
   double *kx_save;                          // [m][BP] K xbar of the last iteration of a block (ray test)
   Scalars* sc;                              // [BP]
+  double* hot;                              // [4][BP]: sigma, tau, k_base, done - what the step kernels read
+                                            // of the control blocks, as arrays (k_publish_batch)
   double* partials;                         // [Q_COUNT][nblk_max][BP]
   int m, n, BP, nblk_max;
 };
 
-// One row of the shared matrix times 32 problems' vectors (lane = problem).  val[k] / idx[k] are
-// warp-uniform loads, the gather is one contiguous 256-byte segment per nonzero; two accumulator
-// chains (even / odd entries), fixed summation order.
-//
-// Round 2 tried three ways of putting more loads in flight per warp, all measured on one B200 on
-// configs 4 / 5 with 128 nodes (profiles/r02_batch_engine.md) and all SLOWER than this plain loop:
-//   * row entries fetched one per lane and handed round by warp shuffle, four gathers in flight:
-//     row / column kernel 96 / 112 us against 78 / 102 us on config 4 (removed);
-//   * rows taken in pairs - step vectors of both rows requested before either product, the two
-//     products interleaved (row_dot_batch2), 8 chains in the CTA-per-row kernel: 107 / 146 us against
-//     80 / 115 us (MIPCU_BATCH_PAIRS=1);
-//   * four accumulator chains in the one-row loop: 84 / 119 us against 80 / 115 us (MIPCU_BATCH_PAIRS=2).
-// ncu on the shipped loops: DRAM 22 % (row) / 52 - 56 % (column) busy, L2 29 - 37 %, L1 -> XBAR port
-// 19 - 25 %, 50 - 57 % active warps, no level saturated; every extra register the variants spend costs
-// resident warps (48 registers = 5 CTAs per SM) and the trade has been negative three times.  The
-// throughput that matters for a branch and bound comes from deciding nodes early (MIPCU_BRANCH), not
-// from these loops.
-__device__ int g_batch_pairs = 0;
+// ---- P problems per lane -----------------------------------------------------------------------
+// A warp owns one matrix row and covers 32 P problems: lane l holds problems b .. b + P - 1,
+// b = (32 blockIdx.y + l) P, which are adjacent in memory (batch index fastest), so its part of the
+// gather is one 8 P-byte load.  With P = 4 a warp moves 1 KB per nonzero with the same two warp-uniform
+// (val, idx) loads and the same number of instructions that moved 256 bytes with P = 1: four times the
+// bytes in flight per warp and a quarter of the L1 wavefronts spent on broadcast loads.  (Round 2 had
+// tried more CHAINS per warp three times - shuffle-fed entries, rows in pairs, four accumulators - and
+// lost each time to the registers they cost; wider lanes buy the same memory-level parallelism without
+// more dependent-load chains.)  The layout does not depend on P: every launch picks its own width from
+// the number of problems still running, and a problem's sums are formed in the same order for every P,
+// so results are bit-identical across widths (tests/test_batch_gpu.py).
+template <int P> __device__ __forceinline__ void ldP(double (&o)[P], const double* __restrict__ p);
+template <> __device__ __forceinline__ void ldP<1>(double (&o)[1], const double* __restrict__ p) { o[0] = *p; }
+template <> __device__ __forceinline__ void ldP<2>(double (&o)[2], const double* __restrict__ p) {
+  const double2 t = *reinterpret_cast<const double2*>(p);
+  o[0] = t.x; o[1] = t.y;
+}
+template <> __device__ __forceinline__ void ldP<4>(double (&o)[4], const double* __restrict__ p) {
+  const double2 t0 = reinterpret_cast<const double2*>(p)[0], t1 = reinterpret_cast<const double2*>(p)[1];
+  o[0] = t0.x; o[1] = t0.y; o[2] = t1.x; o[3] = t1.y;
+}
+template <int P> __device__ __forceinline__ void stP(double* __restrict__ p, const double (&v)[P]);
+template <> __device__ __forceinline__ void stP<1>(double* __restrict__ p, const double (&v)[1]) { *p = v[0]; }
+template <> __device__ __forceinline__ void stP<2>(double* __restrict__ p, const double (&v)[2]) {
+  *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+}
+template <> __device__ __forceinline__ void stP<4>(double* __restrict__ p, const double (&v)[4]) {
+  reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]);
+  reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
+}
+// store the values of the problems that still run (one vector store unless the lane is mixed)
+template <int P>
+__device__ __forceinline__ void st_active(double* __restrict__ p, const double (&v)[P], const bool (&act)[P], bool all) {
+  if (all) { stP<P>(p, v); return; }
+#pragma unroll
+  for (int q = 0; q < P; ++q)
+    if (act[q]) p[q] = v[q];
+}
 
-__device__ __forceinline__ double row_dot_batch(const int* __restrict__ ptr, const int* __restrict__ idx,
-                                                const double* __restrict__ val,
-                                                const double* __restrict__ vec, int row, int BP, int b) {
-  const int beg = ptr[row], end = ptr[row + 1];
-  if (g_batch_pairs == 2) {      // four chains: twice the gathers in flight for four more registers
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int k = beg;
-    for (; k + 3 < end; k += 4) {
-      const int c0 = idx[k], c1 = idx[k + 1], c2 = idx[k + 2], c3 = idx[k + 3];
-      const double x0 = vec[(size_t)c0 * BP + b], x1 = vec[(size_t)c1 * BP + b];
-      const double x2 = vec[(size_t)c2 * BP + b], x3 = vec[(size_t)c3 * BP + b];
-      a0 = fma(val[k], x0, a0);
-      a1 = fma(val[k + 1], x1, a1);
-      a2 = fma(val[k + 2], x2, a2);
-      a3 = fma(val[k + 3], x3, a3);
-    }
-    for (; k < end; ++k) a0 = fma(val[k], vec[(size_t)idx[k] * BP + b], a0);
-    return (a0 + a1) + (a2 + a3);
+// the control-block values a lane needs for its P problems
+template <int P> struct LaneState {
+  double step[P];      // sigma (row side) or tau (column side)
+  double w[P];         // Halpern weight (k + 1) / (k + 2)
+  bool act[P];
+  bool any, all;
+};
+template <int P>
+__device__ __forceinline__ LaneState<P> lane_state(const BatchArgs& a, int b, int iter_in_block, bool row_side) {
+  LaneState<P> s;
+  double kb[P], dn[P];
+  ldP<P>(s.step, a.hot + (size_t)(row_side ? 0 : 1) * a.BP + b);
+  ldP<P>(kb, a.hot + (size_t)2 * a.BP + b);
+  ldP<P>(dn, a.hot + (size_t)3 * a.BP + b);
+  s.any = false;
+  s.all = true;
+#pragma unroll
+  for (int q = 0; q < P; ++q) {
+    s.act[q] = dn[q] == 0.0;
+    const double k = kb[q] + (double)iter_in_block;
+    s.w[q] = (k + 1.0) / (k + 2.0);
+    s.any = s.any || s.act[q];
+    s.all = s.all && s.act[q];
   }
-  double a0 = 0.0, a1 = 0.0;
+  return s;
+}
+
+// One row of the shared matrix times the vectors of the lane's P problems.  val[k] / idx[k] are
+// warp-uniform loads; two accumulator chains per problem (even / odd entries), fixed summation order.
+// Called under `if (lane has a running problem)`: a retired lane is masked off and requests nothing
+// (a predicate on the loads instead made ptxas issue every gather right before its use).
+template <int P>
+__device__ __forceinline__ void row_dot_batch(const int* __restrict__ ptr, const int* __restrict__ idx,
+                                              const double* __restrict__ val, const double* __restrict__ vec,
+                                              int row, int BP, int b, double (&s)[P]) {
+  const int beg = ptr[row], end = ptr[row + 1];
+  double a0[P], a1[P];
+#pragma unroll
+  for (int q = 0; q < P; ++q) a0[q] = a1[q] = 0.0;
   int k = beg;
+  // four entries per trip, all four gathers requested before the first product (the two chains still take
+  // the even / the odd entries in order, so the sums are those of the two-entry loop below)
+  for (; k + 3 < end; k += 4) {
+    const double v0 = val[k], v1 = val[k + 1], v2 = val[k + 2], v3 = val[k + 3];
+    const int c0 = idx[k], c1 = idx[k + 1], c2 = idx[k + 2], c3 = idx[k + 3];
+    double x0[P], x1[P], x2[P], x3[P];
+    ldP<P>(x0, vec + (size_t)c0 * BP + b);
+    ldP<P>(x1, vec + (size_t)c1 * BP + b);
+    ldP<P>(x2, vec + (size_t)c2 * BP + b);
+    ldP<P>(x3, vec + (size_t)c3 * BP + b);
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+      a0[q] = fma(v0, x0[q], a0[q]);
+      a1[q] = fma(v1, x1[q], a1[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+      a0[q] = fma(v2, x2[q], a0[q]);
+      a1[q] = fma(v3, x3[q], a1[q]);
+    }
+  }
   for (; k + 1 < end; k += 2) {
     const double v0 = val[k], v1 = val[k + 1];
     const int c0 = idx[k], c1 = idx[k + 1];
-    a0 = fma(v0, vec[(size_t)c0 * BP + b], a0);
-    a1 = fma(v1, vec[(size_t)c1 * BP + b], a1);
-  }
-  if (k < end) a0 = fma(val[k], vec[(size_t)idx[k] * BP + b], a0);
-  return a0 + a1;
-}
-
-// rows `row` and `row + 1` together: the common prefix of the two rows runs as four independent chains,
-// the longer row finishes alone.  Each row's sum is formed exactly as in row_dot_batch.
-__device__ __forceinline__ void row_dot_batch2(const int* __restrict__ ptr, const int* __restrict__ idx,
-                                               const double* __restrict__ val, const double* __restrict__ vec,
-                                               int row, int BP, int b, double& s0, double& s1) {
-  const int b0 = ptr[row], b1 = ptr[row + 1], e1 = ptr[row + 2];
-  const int e0 = b1;
-  const int joint = min(e0 - b0, e1 - b1) & ~1;
-  double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
-  int k = 0;
-  for (; k < joint; k += 2) {
-    const double v00 = val[b0 + k], v01 = val[b0 + k + 1], v10 = val[b1 + k], v11 = val[b1 + k + 1];
-    const int i00 = idx[b0 + k], i01 = idx[b0 + k + 1], i10 = idx[b1 + k], i11 = idx[b1 + k + 1];
-    const double x00 = vec[(size_t)i00 * BP + b], x01 = vec[(size_t)i01 * BP + b];
-    const double x10 = vec[(size_t)i10 * BP + b], x11 = vec[(size_t)i11 * BP + b];
-    a0 = fma(v00, x00, a0);
-    a1 = fma(v01, x01, a1);
-    c0 = fma(v10, x10, c0);
-    c1 = fma(v11, x11, c1);
-  }
-  int p = b0 + k;
-  for (; p + 1 < e0; p += 2) {
-    a0 = fma(val[p], vec[(size_t)idx[p] * BP + b], a0);
-    a1 = fma(val[p + 1], vec[(size_t)idx[p + 1] * BP + b], a1);
-  }
-  if (p < e0) a0 = fma(val[p], vec[(size_t)idx[p] * BP + b], a0);
-  p = b1 + k;
-  for (; p + 1 < e1; p += 2) {
-    c0 = fma(val[p], vec[(size_t)idx[p] * BP + b], c0);
-    c1 = fma(val[p + 1], vec[(size_t)idx[p + 1] * BP + b], c1);
-  }
-  if (p < e1) c0 = fma(val[p], vec[(size_t)idx[p] * BP + b], c0);
-  s0 = a0 + a1;
-  s1 = c0 + c1;
-}
-
-template <int NQ>
-__device__ __forceinline__ void batch_reduce_store(double (&red)[NQ], const int (&q)[NQ], const BatchArgs& a,
-                                                   int b) {
-  __shared__ double s_red[NQ][kWarps][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double x0[P], x1[P];
+    ldP<P>(x0, vec + (size_t)c0 * BP + b);
+    ldP<P>(x1, vec + (size_t)c1 * BP + b);
 #pragma unroll
-  for (int i = 0; i < NQ; ++i) s_red[i][warp][lane] = red[i];
-  __syncthreads();
-  if (warp == 0) {
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) {
-      double t = 0.0;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) t += s_red[i][w][lane];
-      a.partials[((size_t)q[i] * a.nblk_max + blockIdx.x) * a.BP + b] = t;
+    for (int q = 0; q < P; ++q) {
+      a0[q] = fma(v0, x0[q], a0[q]);
+      a1[q] = fma(v1, x1[q], a1[q]);
     }
   }
-}
-
-// the per-row part of the batched row step, given (K xbar)_row for this lane's problem
-template <bool CHECK>
-__device__ __forceinline__ void row_epilogue_batch(const BatchArgs& a, int row, size_t e, double kx, double yi,
-                                                   double y0i, double sigma, double w_new, int keep_kx,
-                                                   double (&red)[5]) {
-  const double lo = a.lo[row], hi = a.hi[row];
-  const double t = kx - yi / sigma;
-  const double yh = sigma * (clampd(t, lo, hi) - t);
-  a.yhat[e] = yh;
-  a.y[e] = w_new * (2.0 * yh - yi) + (1.0 - w_new) * y0i;
-  if (CHECK) {
-    const double dy = yh - yi, d0 = yh - y0i;
-    red[0] += dy * dy;
-    red[1] += d0 * d0;
-    red[2] += (isfinite(lo) ? lo * fmax(yh, 0.0) : 0.0) - (isfinite(hi) ? hi * fmax(-yh, 0.0) : 0.0);
-    const double dp = fmax(dy, 0.0), dm = fmax(-dy, 0.0);
-    red[3] += (isfinite(lo) ? lo * dp : 0.0) - (isfinite(hi) ? hi * dm : 0.0);
-    const double rv = (isfinite(lo) ? 0.0 : dp) + (isfinite(hi) ? 0.0 : dm);
-    red[4] += rv * rv;
-    if (keep_kx) a.kx_save[e] = kx;
+  if (k < end) {
+    const double v0 = val[k];
+    double x0[P];
+    ldP<P>(x0, vec + (size_t)idx[k] * BP + b);
+#pragma unroll
+    for (int q = 0; q < P; ++q) a0[q] = fma(v0, x0[q], a0[q]);
   }
+#pragma unroll
+  for (int q = 0; q < P; ++q) s[q] = a0[q] + a1[q];
 }
 
-template <bool CHECK>
-__global__ void __launch_bounds__(kThreads) k_row_step_batch(const BatchArgs a, int iter_in_block, int keep_kx) {
+// per-CTA sums of NQ quantities for the lane's P problems -> partials[quantity][CTA][problem]; warps are
+// added in a fixed order (0 .. 7) whatever P is
+template <int NQ, int P>
+__device__ __forceinline__ void batch_reduce_store(double (&red)[NQ][P], const int (&q)[NQ], const BatchArgs& a,
+                                                   int b) {
+  __shared__ double s_red[kWarps][32 * P];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.y * 32 + lane;
-  const Scalars* sc = a.sc + b;
-  const bool active = !sc->done;
-  const double sigma = sc->sigma;
-  const double k = (double)(sc->k_base + iter_in_block);
-  const double w_new = (k + 1.0) / (k + 2.0);
-  double red[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  if (__any_sync(0xffffffffu, active)) {
-    constexpr int kPerWarp = kRowsPerCtaB / kWarps;
-    const int first = blockIdx.x * kRowsPerCtaB + warp * kPerWarp;
-    const int last = min(first + kPerWarp, a.m);
-    int row = first;
-    if (g_batch_pairs == 1) {
-      for (; row + 1 < last; row += 2) {
-        // both rows' step vectors are on their way before either product starts
-        const size_t e0 = (size_t)row * a.BP + b, e1 = e0 + a.BP;
-        double y_0 = 0.0, y0_0 = 0.0, y_1 = 0.0, y0_1 = 0.0;
-        if (active) { y_0 = a.y[e0]; y0_0 = a.y0[e0]; y_1 = a.y[e1]; y0_1 = a.y0[e1]; }
-        double kx0, kx1;
-        row_dot_batch2(a.rptr, a.ridx, a.rval, a.xbar, row, a.BP, b, kx0, kx1);
-        if (!active) continue;
-        row_epilogue_batch<CHECK>(a, row, e0, kx0, y_0, y0_0, sigma, w_new, keep_kx, red);
-        row_epilogue_batch<CHECK>(a, row + 1, e1, kx1, y_1, y0_1, sigma, w_new, keep_kx, red);
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) s_red[warp][lane * P + p] = red[i][p];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) t += s_red[w][lane * P + p];
+        a.partials[((size_t)q[i] * a.nblk_max + blockIdx.x) * a.BP + b + p] = t;
       }
     }
-    for (; row < last; ++row) {
+    __syncthreads();
+  }
+}
+
+// The per-row part of the batched row step for one of the lane's problems, given (K xbar)_row.
+// Every product and sum is an explicit IEEE operation (no contraction left to the compiler): a node's
+// iterates must not depend on the lane width its launch happened to get, i.e. on how many other nodes
+// of the round were still running.
+template <bool CHECK>
+__device__ __forceinline__ void row_update(double lo, double hi, double kx, double yi, double y0i, double sigma,
+                                           double w_new, double& yh_out, double& y_out, double (&c)[5]) {
+  const double t = __dsub_rn(kx, __ddiv_rn(yi, sigma));
+  const double yh = __dmul_rn(sigma, __dsub_rn(clampd(t, lo, hi), t));
+  yh_out = yh;
+  y_out = __fma_rn(w_new, __dsub_rn(__dmul_rn(2.0, yh), yi), __dmul_rn(__dsub_rn(1.0, w_new), y0i));
+  if (CHECK) {
+    const double dy = __dsub_rn(yh, yi), d0 = __dsub_rn(yh, y0i);
+    c[0] = __dmul_rn(dy, dy);
+    c[1] = __dmul_rn(d0, d0);
+    c[2] = __dsub_rn(isfinite(lo) ? __dmul_rn(lo, fmax(yh, 0.0)) : 0.0, isfinite(hi) ? __dmul_rn(hi, fmax(-yh, 0.0)) : 0.0);
+    const double dp = fmax(dy, 0.0), dm = fmax(-dy, 0.0);
+    c[3] = __dsub_rn(isfinite(lo) ? __dmul_rn(lo, dp) : 0.0, isfinite(hi) ? __dmul_rn(hi, dm) : 0.0);
+    const double rv = __dadd_rn(isfinite(lo) ? 0.0 : dp, isfinite(hi) ? 0.0 : dm);
+    c[4] = __dmul_rn(rv, rv);
+  }
+}
+
+// rpw = rows per warp: a CTA owns 8 rpw consecutive rows.  Check iterations always run with rpw = 8
+// (kRowsPerCtaB rows per CTA), which fixes the number of partial sums per quantity.
+template <bool CHECK, int P>
+__global__ void __launch_bounds__(kThreads) k_row_step_batch(const BatchArgs a, int iter_in_block, int keep_kx, int rpw) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = (blockIdx.y * 32 + lane) * P;
+  const LaneState<P> ls = lane_state<P>(a, b, iter_in_block, true);
+  double red[5][P];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int p = 0; p < P; ++p) red[i][p] = 0.0;
+  if (ls.any) {     // per lane: a lane whose problems have all finished is masked off for the whole loop
+    const int first = (blockIdx.x * kWarps + warp) * rpw;
+    const int last = min(first + rpw, a.m);
+    for (int row = first; row < last; ++row) {
       const size_t e = (size_t)row * a.BP + b;
-      double yi = 0.0, y0i = 0.0;
-      if (active) { yi = a.y[e]; y0i = a.y0[e]; }
-      const double kx = row_dot_batch(a.rptr, a.ridx, a.rval, a.xbar, row, a.BP, b);
-      if (!active) continue;
-      row_epilogue_batch<CHECK>(a, row, e, kx, yi, y0i, sigma, w_new, keep_kx, red);
+      double yi[P], y0i[P], kx[P];
+      ldP<P>(yi, a.y + e);
+      ldP<P>(y0i, a.y0 + e);
+      row_dot_batch<P>(a.rptr, a.ridx, a.rval, a.xbar, row, a.BP, b, kx);
+      const double lo = a.lo[row], hi = a.hi[row];
+      double yh[P], yn[P];
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        double c[5];
+        row_update<CHECK>(lo, hi, kx[p], yi[p], y0i[p], ls.step[p], ls.w[p], yh[p], yn[p], c);
+        if (CHECK && ls.act[p]) {
+#pragma unroll
+          for (int i = 0; i < 5; ++i) red[i][p] += c[i];
+        }
+      }
+      st_active<P>(a.yhat + e, yh, ls.act, ls.all);
+      st_active<P>(a.y + e, yn, ls.act, ls.all);
+      if (CHECK && keep_kx) st_active<P>(a.kx_save + e, kx, ls.act, ls.all);
     }
   }
   if (CHECK) {
     const int q[5] = {Q_DY2, Q_DY0, Q_DOBJ_ROW, Q_RAYD_ROW, Q_RAYD_ROWV};
-    batch_reduce_store<5>(red, q, a, b);
+    batch_reduce_store<5, P>(red, q, a, b);
   }
 }
 
 // Long rows (config 5: 500 rows of ~1600 nonzeros): one CTA per row, its 8 warps stride over the
 // row's nonzeros and the partial sums meet in shared memory; warp 0 runs the epilogue.  Fixed
 // summation order (warp 0..7), so still bit-reproducible.  MODE 0: row step, MODE 1: KKT residual.
-template <bool CHECK, int MODE>
+template <bool CHECK, int MODE, int P>
 __global__ void __launch_bounds__(kThreads) k_row_batch_long(const BatchArgs a, int iter_in_block, int keep_kx) {
-  __shared__ double s_part[kWarps][32];
+  __shared__ double s_part[kWarps][32 * P];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.y * 32 + lane;
+  const int b = (blockIdx.y * 32 + lane) * P;
   const int row = blockIdx.x;
-  const Scalars* sc = a.sc + b;
-  const bool active = !sc->done;
+  const LaneState<P> ls = lane_state<P>(a, b, iter_in_block, true);
   const double* vec = MODE == 0 ? a.xbar : a.xhat_chk;
-  double acc0 = 0.0, acc1 = 0.0;
-  if (__any_sync(0xffffffffu, active)) {
+  double acc0[P], acc1[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) acc0[p] = acc1[p] = 0.0;
+  if (ls.any) {
     const int beg = a.rptr[row], end = a.rptr[row + 1];
-    if (g_batch_pairs) {
-      // the 8 warps stride over the row's nonzeros; each warp keeps 8 gathers in flight (a row of 1600
-      // entries is 200 per warp: two chains made that a dependent sequence of 100 round trips)
-      double c[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      int k = beg + warp;
-      for (; k + 7 * kWarps < end; k += 8 * kWarps) {
-        double v[8], x[8];
+    int k = beg + warp;
+    for (; k + kWarps < end; k += 2 * kWarps) {
+      const double v0 = a.rval[k], v1 = a.rval[k + kWarps];
+      const int c0 = a.ridx[k], c1 = a.ridx[k + kWarps];
+      double x0[P], x1[P];
+      ldP<P>(x0, vec + (size_t)c0 * a.BP + b);
+      ldP<P>(x1, vec + (size_t)c1 * a.BP + b);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          v[u] = a.rval[k + u * kWarps];
-          x[u] = vec[(size_t)a.ridx[k + u * kWarps] * a.BP + b];
-        }
+      for (int p = 0; p < P; ++p) {
+        acc0[p] = fma(v0, x0[p], acc0[p]);
+        acc1[p] = fma(v1, x1[p], acc1[p]);
+      }
+    }
+    if (k < end) {
+      const double v0 = a.rval[k];
+      double x0[P];
+      ldP<P>(x0, vec + (size_t)a.ridx[k] * a.BP + b);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) c[u] = fma(v[u], x[u], c[u]);
-      }
-      for (; k < end; k += kWarps) c[0] = fma(a.rval[k], vec[(size_t)a.ridx[k] * a.BP + b], c[0]);
-      acc0 = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
-    } else {
-      int k = beg + warp;
-      for (; k + kWarps < end; k += 2 * kWarps) {
-        const double v0 = a.rval[k], v1 = a.rval[k + kWarps];
-        const int c0 = a.ridx[k], c1 = a.ridx[k + kWarps];
-        acc0 = fma(v0, vec[(size_t)c0 * a.BP + b], acc0);
-        acc1 = fma(v1, vec[(size_t)c1 * a.BP + b], acc1);
-      }
-      if (k < end) acc0 = fma(a.rval[k], vec[(size_t)a.ridx[k] * a.BP + b], acc0);
+      for (int p = 0; p < P; ++p) acc0[p] = fma(v0, x0[p], acc0[p]);
     }
   }
-  s_part[warp][lane] = acc0 + acc1;
+#pragma unroll
+  for (int p = 0; p < P; ++p) s_part[warp][lane * P + p] = acc0[p] + acc1[p];
   __syncthreads();
   if (warp != 0) return;
-  double kx = 0.0;
+  double kx[P];
 #pragma unroll
-  for (int w = 0; w < kWarps; ++w) kx += s_part[w][lane];
+  for (int p = 0; p < P; ++p) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) t += s_part[w][lane * P + p];
+    kx[p] = t;
+  }
   const size_t slot = (size_t)row * a.BP + b;       // partial index: one entry per row
+  const double lo = a.lo[row], hi = a.hi[row];
   if (MODE == 1) {
-    const double lo = a.lo[row], hi = a.hi[row];
-    const double v = (kx - clampd(kx, lo, hi)) / a.d1[row];
-    a.partials[((size_t)Q_PRES2 * a.nblk_max + row) * a.BP + b] = v * v;
-    const double kdx = a.kx_save[slot] - kx;
-    const double rv = (isfinite(lo) ? fmax(-kdx, 0.0) : 0.0) + (isfinite(hi) ? fmax(kdx, 0.0) : 0.0);
-    a.partials[((size_t)Q_RAYP_ROWV * a.nblk_max + row) * a.BP + b] = rv * rv;
+    const double d1 = a.d1[row];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const double v = __ddiv_rn(__dsub_rn(kx[p], clampd(kx[p], lo, hi)), d1);
+      a.partials[((size_t)Q_PRES2 * a.nblk_max + row) * a.BP + b + p] = __dmul_rn(v, v);
+      const double kdx = __dsub_rn(a.kx_save[slot + p], kx[p]);
+      const double rv = __dadd_rn(isfinite(lo) ? fmax(-kdx, 0.0) : 0.0, isfinite(hi) ? fmax(kdx, 0.0) : 0.0);
+      a.partials[((size_t)Q_RAYP_ROWV * a.nblk_max + row) * a.BP + b + p] = __dmul_rn(rv, rv);
+    }
     return;
   }
-  double red[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  if (active) {
-    const double sigma = sc->sigma;
-    const double kk = (double)(sc->k_base + iter_in_block);
-    const double w_new = (kk + 1.0) / (kk + 2.0);
-    const double yi = a.y[slot], y0i = a.y0[slot], lo = a.lo[row], hi = a.hi[row];
-    const double t = kx - yi / sigma;
-    const double yh = sigma * (clampd(t, lo, hi) - t);
-    a.yhat[slot] = yh;
-    a.y[slot] = w_new * (2.0 * yh - yi) + (1.0 - w_new) * y0i;
-    if (CHECK) {
-      const double dy = yh - yi, d0 = yh - y0i;
-      red[0] = dy * dy;
-      red[1] = d0 * d0;
-      red[2] = (isfinite(lo) ? lo * fmax(yh, 0.0) : 0.0) - (isfinite(hi) ? hi * fmax(-yh, 0.0) : 0.0);
-      const double dp = fmax(dy, 0.0), dm = fmax(-dy, 0.0);
-      red[3] = (isfinite(lo) ? lo * dp : 0.0) - (isfinite(hi) ? hi * dm : 0.0);
-      const double rv = (isfinite(lo) ? 0.0 : dp) + (isfinite(hi) ? 0.0 : dm);
-      red[4] = rv * rv;
-      if (keep_kx) a.kx_save[slot] = kx;
-    }
-  }
-  if (CHECK) {
-    a.partials[((size_t)Q_DY2 * a.nblk_max + row) * a.BP + b] = red[0];
-    a.partials[((size_t)Q_DY0 * a.nblk_max + row) * a.BP + b] = red[1];
-    a.partials[((size_t)Q_DOBJ_ROW * a.nblk_max + row) * a.BP + b] = red[2];
-    a.partials[((size_t)Q_RAYD_ROW * a.nblk_max + row) * a.BP + b] = red[3];
-    a.partials[((size_t)Q_RAYD_ROWV * a.nblk_max + row) * a.BP + b] = red[4];
-  }
-}
-
-struct ColOperands { double xb, x0, at, at0, lj, uj, xh; };
-
-template <bool CHECK>
-__device__ __forceinline__ ColOperands col_load_batch(const BatchArgs& a, size_t e, const double* xhat_in, bool active) {
-  ColOperands o = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  if (active) {
-    o.xb = a.xbar[e]; o.x0 = a.x0[e]; o.at = a.aty[e]; o.at0 = a.aty0[e]; o.lj = a.l[e]; o.uj = a.u[e];
-    if (CHECK) o.xh = xhat_in[e];
-  }
-  return o;
-}
-
-// the per-column part of the batched column step, given (K' yhat)_j for this lane's problem
-template <bool CHECK, bool STORE>
-__device__ __forceinline__ void col_epilogue_batch(const BatchArgs& a, int j, size_t e, double atyh,
-                                                   const ColOperands& o, double tau, double w_new,
-                                                   double* xhat_out, double (&red)[10]) {
-  const double xb = o.xb, x0 = o.x0, at = o.at, at0 = o.at0, lj = o.lj, uj = o.uj;
-  const double cj = a.c[j];
-  if (CHECK) {
-    const double xh = o.xh;
-    const double dx = xb - xh, dat = atyh - at, d0 = xh - x0;
-    red[0] += dx * dx;
-    red[1] += dx * dat;
-    red[2] += d0 * d0;
-    const double r = cj - atyh;
-    const double rp = fmax(r, 0.0), rm = fmax(-r, 0.0);
-    const double viol = ((isfinite(lj) ? 0.0 : rp) + (isfinite(uj) ? 0.0 : rm)) / a.d2[j];
-    red[3] += viol * viol;
-    red[4] += cj * xh;
-    red[5] += (isfinite(lj) ? lj * rp : 0.0) - (isfinite(uj) ? uj * rm : 0.0);
-    a.aty_cand[e] = atyh;
-    const double qp = fmax(-dat, 0.0), qm = fmax(dat, 0.0);
-    red[6] += (isfinite(lj) ? lj * qp : 0.0) - (isfinite(uj) ? uj * qm : 0.0);
-    const double qv = (isfinite(lj) ? 0.0 : qp) + (isfinite(uj) ? 0.0 : qm);
-    red[7] += qv * qv;
-    red[8] += cj * dx;
-    const double pv = (isfinite(lj) ? fmax(-dx, 0.0) : 0.0) + (isfinite(uj) ? fmax(dx, 0.0) : 0.0);
-    red[9] += pv * pv;
-  }
-  const double xn = w_new * xb + (1.0 - w_new) * x0;
-  const double atn = w_new * (2.0 * atyh - at) + (1.0 - w_new) * at0;
-  const double xh2 = clampd(xn - tau * (cj - atn), lj, uj);
-  a.xbar[e] = 2.0 * xh2 - xn;
-  a.aty[e] = atn;
-  if (STORE) xhat_out[e] = xh2;
-}
-
-template <bool CHECK, bool STORE>
-__global__ void __launch_bounds__(kThreads)
-k_col_step_batch(const BatchArgs a, int iter_in_block, const double* xhat_in, double* xhat_out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.y * 32 + lane;
-  const Scalars* sc = a.sc + b;
-  const bool active = !sc->done;
-  const double tau = sc->tau;
-  const double k = (double)(sc->k_base + iter_in_block);
-  const double w_new = (k + 1.0) / (k + 2.0);
-  double red[10] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  if (__any_sync(0xffffffffu, active)) {
-    constexpr int kPerWarp = kRowsPerCtaB / kWarps;
-    const int first = blockIdx.x * kRowsPerCtaB + warp * kPerWarp;
-    const int last = min(first + kPerWarp, a.n);
-    int j = first;
-    if (g_batch_pairs == 1) {
-      for (; j + 1 < last; j += 2) {
-        // the seven streamed operands of both columns are requested before either product starts
-        const size_t e0 = (size_t)j * a.BP + b, e1 = e0 + a.BP;
-        const ColOperands o0 = col_load_batch<CHECK>(a, e0, xhat_in, active);
-        const ColOperands o1 = col_load_batch<CHECK>(a, e1, xhat_in, active);
-        double s0, s1;
-        row_dot_batch2(a.cptr, a.cidx, a.cval, a.yhat, j, a.BP, b, s0, s1);
-        if (!active) continue;
-        col_epilogue_batch<CHECK, STORE>(a, j, e0, s0, o0, tau, w_new, xhat_out, red);
-        col_epilogue_batch<CHECK, STORE>(a, j + 1, e1, s1, o1, tau, w_new, xhat_out, red);
+  double red[5][P];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int p = 0; p < P; ++p) red[i][p] = 0.0;
+  if (ls.any) {
+    double yi[P], y0i[P], yh[P], yn[P];
+    ldP<P>(yi, a.y + slot);
+    ldP<P>(y0i, a.y0 + slot);
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      double c[5];
+      row_update<CHECK>(lo, hi, kx[p], yi[p], y0i[p], ls.step[p], ls.w[p], yh[p], yn[p], c);
+      if (CHECK && ls.act[p]) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) red[i][p] += c[i];
       }
     }
-    for (; j < last; ++j) {
+    st_active<P>(a.yhat + slot, yh, ls.act, ls.all);
+    st_active<P>(a.y + slot, yn, ls.act, ls.all);
+    if (CHECK && keep_kx) st_active<P>(a.kx_save + slot, kx, ls.act, ls.all);
+  }
+  if (CHECK) {
+    const int q[5] = {Q_DY2, Q_DY0, Q_DOBJ_ROW, Q_RAYD_ROW, Q_RAYD_ROWV};
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int p = 0; p < P; ++p) a.partials[((size_t)q[i] * a.nblk_max + row) * a.BP + b + p] = red[i][p];
+  }
+}
+
+// the per-column part of the batched column step for one problem, given (K' yhat)_j (explicit IEEE
+// operations, see row_update)
+template <bool CHECK>
+__device__ __forceinline__ void col_update(double cj, double d2j, double atyh, double xb, double x0, double at,
+                                           double at0, double lj, double uj, double xh, double tau, double w_new,
+                                           double& xbar_out, double& aty_out, double& xhat_out, double (&c)[10]) {
+  if (CHECK) {
+    const double dx = __dsub_rn(xb, xh), dat = __dsub_rn(atyh, at), d0 = __dsub_rn(xh, x0);
+    c[0] = __dmul_rn(dx, dx);
+    c[1] = __dmul_rn(dx, dat);
+    c[2] = __dmul_rn(d0, d0);
+    const double r = __dsub_rn(cj, atyh);
+    const double rp = fmax(r, 0.0), rm = fmax(-r, 0.0);
+    const double viol = __ddiv_rn(__dadd_rn(isfinite(lj) ? 0.0 : rp, isfinite(uj) ? 0.0 : rm), d2j);
+    c[3] = __dmul_rn(viol, viol);
+    c[4] = __dmul_rn(cj, xh);
+    c[5] = __dsub_rn(isfinite(lj) ? __dmul_rn(lj, rp) : 0.0, isfinite(uj) ? __dmul_rn(uj, rm) : 0.0);
+    const double qp = fmax(-dat, 0.0), qm = fmax(dat, 0.0);
+    c[6] = __dsub_rn(isfinite(lj) ? __dmul_rn(lj, qp) : 0.0, isfinite(uj) ? __dmul_rn(uj, qm) : 0.0);
+    const double qv = __dadd_rn(isfinite(lj) ? 0.0 : qp, isfinite(uj) ? 0.0 : qm);
+    c[7] = __dmul_rn(qv, qv);
+    c[8] = __dmul_rn(cj, dx);
+    const double pv = __dadd_rn(isfinite(lj) ? fmax(-dx, 0.0) : 0.0, isfinite(uj) ? fmax(dx, 0.0) : 0.0);
+    c[9] = __dmul_rn(pv, pv);
+  }
+  const double one_w = __dsub_rn(1.0, w_new);
+  const double xn = __fma_rn(w_new, xb, __dmul_rn(one_w, x0));
+  const double atn = __fma_rn(w_new, __dsub_rn(__dmul_rn(2.0, atyh), at), __dmul_rn(one_w, at0));
+  const double xh2 = clampd(__fma_rn(-tau, __dsub_rn(cj, atn), xn), lj, uj);
+  xbar_out = __dsub_rn(__dmul_rn(2.0, xh2), xn);
+  aty_out = atn;
+  xhat_out = xh2;
+}
+
+template <bool CHECK, bool STORE, int P>
+__global__ void __launch_bounds__(kThreads)
+k_col_step_batch(const BatchArgs a, int iter_in_block, const double* xhat_in, double* xhat_out, int rpw) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = (blockIdx.y * 32 + lane) * P;
+  const LaneState<P> ls = lane_state<P>(a, b, iter_in_block, false);
+  double red[10][P];
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+#pragma unroll
+    for (int p = 0; p < P; ++p) red[i][p] = 0.0;
+  if (ls.any) {
+    const int first = (blockIdx.x * kWarps + warp) * rpw;
+    const int last = min(first + rpw, a.n);
+    for (int j = first; j < last; ++j) {
       const size_t e = (size_t)j * a.BP + b;
-      const ColOperands o = col_load_batch<CHECK>(a, e, xhat_in, active);
-      const double atyh = row_dot_batch(a.cptr, a.cidx, a.cval, a.yhat, j, a.BP, b);
-      if (!active) continue;
-      col_epilogue_batch<CHECK, STORE>(a, j, e, atyh, o, tau, w_new, xhat_out, red);
+      // the streamed operands are requested before the product starts
+      double xb[P], x0[P], at[P], at0[P], lj[P], uj[P], xh[P], atyh[P];
+      ldP<P>(xb, a.xbar + e); ldP<P>(x0, a.x0 + e); ldP<P>(at, a.aty + e); ldP<P>(at0, a.aty0 + e);
+      ldP<P>(lj, a.l + e); ldP<P>(uj, a.u + e);
+      if (CHECK) ldP<P>(xh, xhat_in + e);
+      else {
+#pragma unroll
+        for (int p = 0; p < P; ++p) xh[p] = 0.0;
+      }
+      row_dot_batch<P>(a.cptr, a.cidx, a.cval, a.yhat, j, a.BP, b, atyh);
+      const double cj = a.c[j], d2j = CHECK ? a.d2[j] : 1.0;
+      double xbn[P], atn[P], xhn[P];
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        double c[10];
+        col_update<CHECK>(cj, d2j, atyh[p], xb[p], x0[p], at[p], at0[p], lj[p], uj[p], xh[p], ls.step[p], ls.w[p],
+                          xbn[p], atn[p], xhn[p], c);
+        if (CHECK && ls.act[p]) {
+#pragma unroll
+          for (int i = 0; i < 10; ++i) red[i][p] += c[i];
+        }
+      }
+      if (CHECK) st_active<P>(a.aty_cand + e, atyh, ls.act, ls.all);
+      st_active<P>(a.xbar + e, xbn, ls.act, ls.all);
+      st_active<P>(a.aty + e, atn, ls.act, ls.all);
+      if (STORE) st_active<P>(xhat_out + e, xhn, ls.act, ls.all);
     }
   }
   if (CHECK) {
     const int q[10] = {Q_DX2, Q_DXDATY, Q_DX0, Q_DRES2, Q_POBJ, Q_DOBJ_COL,
                        Q_RAYD_COL, Q_RAYD_COLV, Q_RAYP_C, Q_RAYP_COLV};
-    batch_reduce_store<10>(red, q, a, b);
+    batch_reduce_store<10, P>(red, q, a, b);
   }
 }
 
+
+// ---- entry-fed variants of the two step kernels (non-check iterations) ----------------------------------
+// The loops above reach a nonzero through a dependent chain: warp-uniform idx[k] (an L1 / L2 round trip),
+// then the gather (L2 or HBM round trip), trip after trip, row after row; ncu shows them waiting, not
+// moving bytes.  Here the warp fetches up to 32 (idx, val) entries of a row with ONE coalesced load per
+// array - lane l holds entry l - and hands them round by shuffle, so every gather of the row can be
+// requested as soon as that single load has landed; and the entries of the NEXT row are requested before
+// the current row's products start.  The chain per row is one gather round trip instead of
+// (entries / 4) x (index + gather) round trips.  All 32 lanes stay converged (shuffles need them): a lane
+// whose problems have all finished gathers at the address of a lane that still runs (same sectors, no extra
+// traffic) and stores nothing.  The two accumulator chains take the even / odd entries in order exactly as
+// row_dot_batch does, so both paths produce the same bits.
+constexpr unsigned kFull = 0xffffffffu;
+
+template <int P>
+__device__ __forceinline__ void feed_chunk(int ci, double cv, int cnt, const double* __restrict__ vec, int BP,
+                                           int b, double (&a0)[P], double (&a1)[P]) {
+  int k = 0;
+  for (; k + 3 < cnt; k += 4) {
+    const int c0 = __shfl_sync(kFull, ci, k), c1 = __shfl_sync(kFull, ci, k + 1);
+    const int c2 = __shfl_sync(kFull, ci, k + 2), c3 = __shfl_sync(kFull, ci, k + 3);
+    const double v0 = __shfl_sync(kFull, cv, k), v1 = __shfl_sync(kFull, cv, k + 1);
+    const double v2 = __shfl_sync(kFull, cv, k + 2), v3 = __shfl_sync(kFull, cv, k + 3);
+    double x0[P], x1[P], x2[P], x3[P];
+    ldP<P>(x0, vec + (size_t)c0 * BP + b);
+    ldP<P>(x1, vec + (size_t)c1 * BP + b);
+    ldP<P>(x2, vec + (size_t)c2 * BP + b);
+    ldP<P>(x3, vec + (size_t)c3 * BP + b);
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+      a0[q] = fma(v0, x0[q], a0[q]);
+      a1[q] = fma(v1, x1[q], a1[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+      a0[q] = fma(v2, x2[q], a0[q]);
+      a1[q] = fma(v3, x3[q], a1[q]);
+    }
+  }
+  for (; k + 1 < cnt; k += 2) {
+    const int c0 = __shfl_sync(kFull, ci, k), c1 = __shfl_sync(kFull, ci, k + 1);
+    const double v0 = __shfl_sync(kFull, cv, k), v1 = __shfl_sync(kFull, cv, k + 1);
+    double x0[P], x1[P];
+    ldP<P>(x0, vec + (size_t)c0 * BP + b);
+    ldP<P>(x1, vec + (size_t)c1 * BP + b);
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+      a0[q] = fma(v0, x0[q], a0[q]);
+      a1[q] = fma(v1, x1[q], a1[q]);
+    }
+  }
+  if (k < cnt) {
+    const int c0 = __shfl_sync(kFull, ci, k);
+    const double v0 = __shfl_sync(kFull, cv, k);
+    double x0[P];
+    ldP<P>(x0, vec + (size_t)c0 * BP + b);
+#pragma unroll
+    for (int q = 0; q < P; ++q) a0[q] = fma(v0, x0[q], a0[q]);
+  }
+}
+
+// the warp's rows [first, first + nr): pointers once (lane r holds ptr[first + r]), then per row the
+// product with entries fed by shuffle; `next` prefetches the following row's first 32 entries
+template <int P>
+struct RowFeed {
+  const int* __restrict__ ptr; const int* __restrict__ idx; const double* __restrict__ val;
+  int lane, myptr, beg, end, ci, nbeg, nend, nci;
+  double cv, ncv;
+  __device__ __forceinline__ void start(int first, int nr) {
+    myptr = (nr > 0 && lane <= nr) ? ptr[first + lane] : 0;
+    beg = __shfl_sync(kFull, myptr, 0);
+    end = __shfl_sync(kFull, myptr, 1);
+    fetch(beg, end, ci, cv);
+  }
+  __device__ __forceinline__ void fetch(int from, int to, int& i_out, double& v_out) const {
+    i_out = 0; v_out = 0.0;
+    if (from + lane < to) { i_out = idx[from + lane]; v_out = val[from + lane]; }
+  }
+  __device__ __forceinline__ void prefetch_next(int r, int nr) {
+    nbeg = nend = 0; nci = 0; ncv = 0.0;
+    if (r + 1 < nr) {
+      nbeg = __shfl_sync(kFull, myptr, r + 1);
+      nend = __shfl_sync(kFull, myptr, r + 2);
+      fetch(nbeg, nend, nci, ncv);
+    }
+  }
+  __device__ __forceinline__ void dot(const double* __restrict__ vec, int BP, int b, double (&s)[P]) {
+    double a0[P], a1[P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) a0[q] = a1[q] = 0.0;
+    int base = beg;
+    while (true) {
+      feed_chunk<P>(ci, cv, min(32, end - base), vec, BP, b, a0, a1);
+      base += 32;
+      if (base >= end) break;
+      fetch(base, end, ci, cv);
+    }
+#pragma unroll
+    for (int q = 0; q < P; ++q) s[q] = a0[q] + a1[q];
+  }
+  __device__ __forceinline__ void advance() { beg = nbeg; end = nend; ci = nci; cv = ncv; }
+};
+
+template <int P>
+__global__ void __launch_bounds__(kThreads) k_row_step_batch_fed(const BatchArgs a, int iter_in_block, int rpw) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = (blockIdx.y * 32 + lane) * P;
+  const LaneState<P> ls = lane_state<P>(a, b, iter_in_block, true);
+  const unsigned live = __ballot_sync(kFull, ls.any);
+  if (live == 0) return;
+  const int b_ld = __shfl_sync(kFull, b, ls.any ? lane : __ffs(live) - 1);
+  const int first = (blockIdx.x * kWarps + warp) * rpw;
+  const int nr = min(first + rpw, a.m) - first;
+  RowFeed<P> rf{a.rptr, a.ridx, a.rval, lane};
+  rf.start(first, nr);
+  for (int r = 0; r < nr; ++r) {
+    const int row = first + r;
+    rf.prefetch_next(r, nr);
+    double yi[P], y0i[P], kx[P];
+    ldP<P>(yi, a.y + (size_t)row * a.BP + b_ld);
+    ldP<P>(y0i, a.y0 + (size_t)row * a.BP + b_ld);
+    rf.dot(a.xbar, a.BP, b_ld, kx);
+    const double lo = a.lo[row], hi = a.hi[row];
+    double yh[P], yn[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      double c[5];
+      row_update<false>(lo, hi, kx[p], yi[p], y0i[p], ls.step[p], ls.w[p], yh[p], yn[p], c);
+    }
+    if (ls.any) {
+      const size_t e = (size_t)row * a.BP + b;
+      st_active<P>(a.yhat + e, yh, ls.act, ls.all);
+      st_active<P>(a.y + e, yn, ls.act, ls.all);
+    }
+    rf.advance();
+  }
+}
+
+template <bool STORE, int P>
+__global__ void __launch_bounds__(kThreads)
+k_col_step_batch_fed(const BatchArgs a, int iter_in_block, double* xhat_out, int rpw) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = (blockIdx.y * 32 + lane) * P;
+  const LaneState<P> ls = lane_state<P>(a, b, iter_in_block, false);
+  const unsigned live = __ballot_sync(kFull, ls.any);
+  if (live == 0) return;
+  const int b_ld = __shfl_sync(kFull, b, ls.any ? lane : __ffs(live) - 1);
+  const int first = (blockIdx.x * kWarps + warp) * rpw;
+  const int nr = min(first + rpw, a.n) - first;
+  RowFeed<P> rf{a.cptr, a.cidx, a.cval, lane};
+  rf.start(first, nr);
+  for (int r = 0; r < nr; ++r) {
+    const int j = first + r;
+    rf.prefetch_next(r, nr);
+    const size_t el = (size_t)j * a.BP + b_ld;
+    double xb[P], x0[P], at[P], at0[P], lj[P], uj[P], atyh[P];
+    ldP<P>(xb, a.xbar + el); ldP<P>(x0, a.x0 + el); ldP<P>(at, a.aty + el); ldP<P>(at0, a.aty0 + el);
+    ldP<P>(lj, a.l + el); ldP<P>(uj, a.u + el);
+    rf.dot(a.yhat, a.BP, b_ld, atyh);
+    const double cj = a.c[j];
+    double xbn[P], atn[P], xhn[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      double c[10];
+      col_update<false>(cj, 1.0, atyh[p], xb[p], x0[p], at[p], at0[p], lj[p], uj[p], 0.0, ls.step[p], ls.w[p],
+                        xbn[p], atn[p], xhn[p], c);
+    }
+    if (ls.any) {
+      const size_t e = (size_t)j * a.BP + b;
+      st_active<P>(a.xbar + e, xbn, ls.act, ls.all);
+      st_active<P>(a.aty + e, atn, ls.act, ls.all);
+      if (STORE) st_active<P>(xhat_out + e, xhn, ls.act, ls.all);
+    }
+    rf.advance();
+  }
+}
+
+template <int P>
 __global__ void __launch_bounds__(kThreads) k_kkt_row_batch(const BatchArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.y * 32 + lane;
-  const bool active = !a.sc[b].done;
-  double red[2] = {0.0, 0.0};
-  if (__any_sync(0xffffffffu, active)) {
+  const int b = (blockIdx.y * 32 + lane) * P;
+  double dn[P];
+  ldP<P>(dn, a.hot + (size_t)3 * a.BP + b);
+  bool any = false;
+#pragma unroll
+  for (int p = 0; p < P; ++p) any = any || dn[p] == 0.0;
+  double red[2][P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) red[0][p] = red[1][p] = 0.0;
+  if (any) {
     for (int i = 0; i < kRowsPerCtaB / kWarps; ++i) {
       const int row = blockIdx.x * kRowsPerCtaB + warp * (kRowsPerCtaB / kWarps) + i;
       if (row >= a.m) break;
-      const double kx = row_dot_batch(a.rptr, a.ridx, a.rval, a.xhat_chk, row, a.BP, b);
-      const double lo = a.lo[row], hi = a.hi[row];
-      const double v = (kx - clampd(kx, lo, hi)) / a.d1[row];
-      red[0] += v * v;
-      const double kdx = a.kx_save[(size_t)row * a.BP + b] - kx;      // K (xbar - xhat) = K dx
-      const double rv = (isfinite(lo) ? fmax(-kdx, 0.0) : 0.0) + (isfinite(hi) ? fmax(kdx, 0.0) : 0.0);
-      red[1] += rv * rv;
+      double kx[P], ks[P];
+      row_dot_batch<P>(a.rptr, a.ridx, a.rval, a.xhat_chk, row, a.BP, b, kx);
+      ldP<P>(ks, a.kx_save + (size_t)row * a.BP + b);
+      const double lo = a.lo[row], hi = a.hi[row], d1 = a.d1[row];
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const double v = __ddiv_rn(__dsub_rn(kx[p], clampd(kx[p], lo, hi)), d1);
+        red[0][p] += __dmul_rn(v, v);
+        const double kdx = __dsub_rn(ks[p], kx[p]);      // K (xbar - xhat) = K dx
+        const double rv = __dadd_rn(isfinite(lo) ? fmax(-kdx, 0.0) : 0.0, isfinite(hi) ? fmax(kdx, 0.0) : 0.0);
+        red[1][p] += __dmul_rn(rv, rv);
+      }
     }
   }
   const int q[2] = {Q_PRES2, Q_RAYP_ROWV};
-  batch_reduce_store<2>(red, q, a, b);
+  batch_reduce_store<2, P>(red, q, a, b);
 }
 
 // sum over CTAs of one quantity for the 32 problems of this chunk (lane = problem)
@@ -515,6 +747,19 @@ __global__ void __launch_bounds__(kThreads) k_ctrl_check_batch(const BatchArgs a
   }
 }
 
+// The four control-block fields the step kernels read, as arrays [4][BP] (sigma, tau, k_base, done): a
+// lane picks up the state of its P problems with three vector loads instead of 3 P loads strided by
+// sizeof(Scalars).  Runs after everything that changes them (start, controller, lane compaction).
+__global__ void k_publish_batch(const BatchArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.BP) return;
+  const Scalars* sc = a.sc + b;
+  a.hot[b] = sc->sigma;
+  a.hot[(size_t)a.BP + b] = sc->tau;
+  a.hot[(size_t)2 * a.BP + b] = (double)sc->k_base;
+  a.hot[(size_t)3 * a.BP + b] = sc->done ? 1.0 : 0.0;
+}
+
 __global__ void k_restart_apply_batch(const BatchArgs a) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int b = (int)(e % a.BP);
@@ -569,13 +814,16 @@ __global__ void k_load_duals(const double* __restrict__ y0, const int* __restric
 }
 
 // aty_cand = K' yhat for every problem (seeds the warm start; a cold start has K'0 = 0)
+template <int P>
 __global__ void __launch_bounds__(kThreads) k_aty_batch(const BatchArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.y * 32 + lane;
+  const int b = (blockIdx.y * 32 + lane) * P;
   for (int i = 0; i < kRowsPerCtaB / kWarps; ++i) {
     const int j = blockIdx.x * kRowsPerCtaB + warp * (kRowsPerCtaB / kWarps) + i;
     if (j >= a.n) break;
-    a.aty_cand[(size_t)j * a.BP + b] = row_dot_batch(a.cptr, a.cidx, a.cval, a.yhat, j, a.BP, b);
+    double s[P];
+    row_dot_batch<P>(a.cptr, a.cidx, a.cval, a.yhat, j, a.BP, b, s);
+    stP<P>(a.aty_cand + (size_t)j * a.BP + b, s);
   }
 }
 
@@ -612,6 +860,14 @@ __global__ void k_unscale_duals_batch(const double* __restrict__ yhat, const int
   if (b < B) y_out[(size_t)b * m + (row_perm ? row_perm[i] : i)] = sgn * yhat[e] * d1[i];
 }
 
+// f(std::integral_constant<int, P>) for P = 1, 2, 4: picks the kernel instance of a lane width
+template <class F>
+void with_width(int P, F&& f) {
+  if (P == 4) f(std::integral_constant<int, 4>{});
+  else if (P == 2) f(std::integral_constant<int, 2>{});
+  else f(std::integral_constant<int, 1>{});
+}
+
 struct DeviceBuffers {
   std::vector<void*> owned;
   template <class T>
@@ -629,18 +885,16 @@ struct DeviceBuffers {
 }  // namespace
 
 // Algorithmic bytes of one launch of the batched kernels with B problems in flight:
-// the matrix is streamed once per 32-problem chunk (12 bytes per nonzero + 4 per row pointer; it
-// stays in L2 after the first chunk), the gathered vector is counted once per problem (8 n or 8 m),
-// the step vectors as in the single-LP kernels (row: y, y0 read, y, yhat written, row sides shared;
-// column: xbar, x0, aty, aty0, l, u read, xbar, aty written, c shared).
+// the shared matrix once (12 bytes per nonzero + 4 per row pointer; round 2 counted it once per
+// 32-problem chunk, which is what the kernels did then), the shared row sides / objective once, the
+// gathered vector once per problem (8 n or 8 m), the step vectors as in the single-LP kernels
+// (row: y, y0 read, y, yhat written; column: xbar, x0, aty, aty0, l, u read, xbar, aty written).
 int64_t batch_row_bytes(const mipcu_ctx* ctx, int BP) {
-  const int64_t chunks = BP / 32;
-  return chunks * (12 * ctx->nnz + 4 * ((int64_t)ctx->m + 1) + 16 * (int64_t)ctx->m) +
+  return 12 * ctx->nnz + 4 * ((int64_t)ctx->m + 1) + 16 * (int64_t)ctx->m +
          (int64_t)BP * (8 * (int64_t)ctx->n + 32 * (int64_t)ctx->m);
 }
 int64_t batch_col_bytes(const mipcu_ctx* ctx, int BP) {
-  const int64_t chunks = BP / 32;
-  return chunks * (12 * ctx->nnz + 4 * ((int64_t)ctx->n + 1) + 8 * (int64_t)ctx->n) +
+  return 12 * ctx->nnz + 4 * ((int64_t)ctx->n + 1) + 8 * (int64_t)ctx->n +
          (int64_t)BP * (8 * (int64_t)ctx->m + 64 * (int64_t)ctx->n);
 }
 
@@ -655,11 +909,6 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
   auto t0 = std::chrono::steady_clock::now();
   cudaStream_t st = ctx->stream;
   ctx->launches = 0;
-  {
-    const char* v = std::getenv("MIPCU_BATCH_PAIRS");     // laboratory switch: 0 round-1 loops, 1 row pairs, 2 four chains
-    const int pairs = v ? std::atoi(v) : 0;
-    MIPCU_CK(cudaMemcpyToSymbolAsync(g_batch_pairs, &pairs, sizeof(int), 0, cudaMemcpyHostToDevice, st));
-  }
   if (!ctx->d_sc) MIPCU_CK(cudaMalloc(&ctx->d_sc, sizeof(Scalars)));
   if (!ctx->h_sc) MIPCU_CK(cudaMallocHost(&ctx->h_sc, sizeof(Scalars) * 2));
   for (auto& e : ctx->ev)
@@ -668,7 +917,18 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
   refresh_vectors(ctx);
 
   const int n = ctx->n, m = ctx->m;
-  const int BP = (B + 31) / 32 * 32;
+  // lanes hold up to max_width problems (laboratory switch MIPCU_BATCH_WIDTH = 1 | 2 | 4; default 4)
+  int max_width = 4;
+  if (const char* v = std::getenv("MIPCU_BATCH_WIDTH")) max_width = std::atoi(v) >= 4 ? 4 : std::atoi(v) >= 2 ? 2 : 1;
+  // laboratory switches: MIPCU_BATCH_FEED (row step; default 1) / MIPCU_BATCH_FEED_COL (column step; default 0):
+  // 1 = entries fetched one per lane and fed by shuffle, 0 = warp-uniform entry loads.  Measured on configs 4 / 5
+  // (profiles/r02_batch_engine.md): the entry-fed row kernel with 4 problems per lane and the uniform-load
+  // column kernel with 2 are the fastest pair; the CTA-per-row kernel of long-row models is best with 2.
+  const bool fed = !(std::getenv("MIPCU_BATCH_FEED") && !std::atoi(std::getenv("MIPCU_BATCH_FEED")));
+  const bool fed_col = std::getenv("MIPCU_BATCH_FEED_COL") && std::atoi(std::getenv("MIPCU_BATCH_FEED_COL"));
+  const int fixed_rpw = std::getenv("MIPCU_BATCH_RPW") ? std::max(1, std::min(8, std::atoi(std::getenv("MIPCU_BATCH_RPW")))) : 0;
+  const int pad_to = B > 64 ? 32 * max_width : B > 32 ? 32 * std::min(max_width, 2) : 32;
+  const int BP = (B + pad_to - 1) / pad_to * pad_to;
   const size_t nB = (size_t)n * BP, mB = (size_t)m * BP;
   // rows far longer than a warp can stream serially get a CTA each (config 5)
   const bool long_rows = m > 0 && ctx->nnz / std::max(m, 1) > 128;
@@ -693,6 +953,7 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
   a.y = buf.get<double>(mB); a.y0 = buf.get<double>(mB); a.yhat = buf.get<double>(mB);
   a.kx_save = buf.get<double>(mB);
   a.sc = buf.get<Scalars>(BP);
+  a.hot = buf.get<double>((size_t)4 * BP);
   a.partials = buf.get<double>((size_t)Q_COUNT * nblk_max * BP);
   a.m = m; a.n = n; a.BP = BP; a.nblk_max = nblk_max;
   MIPCU_CK(cudaMemsetAsync(a.partials, 0, sizeof(double) * Q_COUNT * nblk_max * BP, st));
@@ -719,8 +980,9 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
       k_load_duals<<<grid_for(mB), kThreads, 0, st>>>(h_y, ctx->row_perm, ctx->d1, sgn, a.yhat, m, B, BP);
       ctx->launches++;
       if (nB) {
-        const dim3 g(std::max(grid_for(n, kRowsPerCtaB), 1), BP / 32);
-        k_aty_batch<<<g, kThreads, 0, st>>>(a);
+        const int P0 = (BP % 128 == 0 && max_width >= 4) ? 4 : (BP % 64 == 0 && max_width >= 2) ? 2 : 1;
+        const dim3 g(std::max(grid_for(n, kRowsPerCtaB), 1), BP / (32 * P0));
+        with_width(P0, [&](auto w) { k_aty_batch<decltype(w)::value><<<g, kThreads, 0, st>>>(a); });
         ctx->launches++;
       }
     } else {
@@ -751,6 +1013,8 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
     s.done = b < B ? 0 : 1 + MIPCU_OPTIMAL;     // pad lanes never run
   }
   MIPCU_CK(cudaMemcpyAsync(a.sc, h.data(), sizeof(Scalars) * BP, cudaMemcpyHostToDevice, st));
+  k_publish_batch<<<grid_for(BP), kThreads, 0, st>>>(a);
+  ctx->launches++;
   // Lanes are re-packed as nodes finish (compact, below): `chunks` 32-lane groups hold every problem that
   // still runs, and only those are launched.
   int chunks = BP / 32;
@@ -773,41 +1037,99 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
   cudaEvent_t ev_t[3] = {ctx->ev[4], ctx->ev[5], ctx->ev[6]};
   double row_us = 0.0, col_us = 0.0;
   int64_t timed_blocks = 0;
+  // Lane width and rows per warp of a launch.  Width: the widest lanes the running problems fill more than
+  // half of (check iterations: at most 2 - their 5 / 10 running sums per problem are registers).  Rows per
+  // warp (non-check launches only; check launches keep 8 so that the partial sums have a fixed shape): as
+  // many as leave about two waves of warps - with wide lanes a launch has few, long warps otherwise.
+  auto width_for = [&](int cap) {
+    const int live_lanes = chunks * 32;
+    for (int P : {4, 2})
+      if (P <= cap && P <= max_width && live_lanes > 16 * P && (live_lanes + 32 * P - 1) / (32 * P) * (32 * P) <= BP)
+        return P;
+    return 1;
+  };
+  auto rpw_for = [&](int rows, int gy) {
+    if (fixed_rpw) return fixed_rpw;
+    int r = kRowsPerCtaB / kWarps;
+    while (r > 1 && (long long)rows * gy / r < 8192) r >>= 1;
+    return r;
+  };
   auto enqueue_block = [&]() {
+    const int live_lanes = chunks * 32;
+    const int Pr = width_for(long_rows ? 2 : fed ? 4 : 2), Pj = width_for(fed_col ? 4 : 2), Pc = width_for(2);
+    auto groups = [&](int P) { return (live_lanes + 32 * P - 1) / (32 * P); };
+    const int gyr = groups(Pr), gyj = groups(Pj), gyc = groups(Pc);
+    const int rpw_row = rpw_for(m, gyr), rpw_col = rpw_for(n, gyj);
     for (int i = 0; i < period; ++i) {
       const bool first = i == 0, last = i == period - 1;
       const bool timed = i == (period > 2 ? 1 : 0);
+      const bool chk = first || last;
       if (timed) MIPCU_CK(cudaEventRecord(ev_t[0], st));
       if (m && long_rows) {
-        const dim3 g(m, chunks);
-        if (first || last) k_row_batch_long<true, 0><<<g, kThreads, 0, st>>>(a, i, last ? 1 : 0);
-        else k_row_batch_long<false, 0><<<g, kThreads, 0, st>>>(a, i, 0);
+        if (chk) {
+          const dim3 g(m, gyc);
+          const int keep = last ? 1 : 0;
+          with_width(Pc, [&](auto w) { k_row_batch_long<true, 0, decltype(w)::value><<<g, kThreads, 0, st>>>(a, i, keep); });
+        } else {
+          const dim3 g(m, gyr);
+          with_width(Pr, [&](auto w) { k_row_batch_long<false, 0, decltype(w)::value><<<g, kThreads, 0, st>>>(a, i, 0); });
+        }
         ctx->launches++;
-        if (last) { k_row_batch_long<false, 1><<<g, kThreads, 0, st>>>(a, i, 0); ctx->launches++; }
+        if (last) {
+          const dim3 g(m, gyc);
+          with_width(Pc, [&](auto w) { k_row_batch_long<false, 1, decltype(w)::value><<<g, kThreads, 0, st>>>(a, i, 0); });
+          ctx->launches++;
+        }
       } else if (m) {
-        const dim3 grid_rows(std::max(nblk_row, 1), chunks);
-        if (first || last) k_row_step_batch<true><<<grid_rows, kThreads, 0, st>>>(a, i, last ? 1 : 0);
-        else k_row_step_batch<false><<<grid_rows, kThreads, 0, st>>>(a, i, 0);
+        if (chk) {
+          const dim3 g(std::max(nblk_row, 1), gyc);
+          const int keep = last ? 1 : 0;
+          with_width(Pc, [&](auto w) {
+            k_row_step_batch<true, decltype(w)::value><<<g, kThreads, 0, st>>>(a, i, keep, kRowsPerCtaB / kWarps);
+          });
+        } else {
+          const dim3 g(std::max(grid_for(m, kWarps * rpw_row), 1), gyr);
+          with_width(Pr, [&](auto w) {
+            if (fed) k_row_step_batch_fed<decltype(w)::value><<<g, kThreads, 0, st>>>(a, i, rpw_row);
+            else k_row_step_batch<false, decltype(w)::value><<<g, kThreads, 0, st>>>(a, i, 0, rpw_row);
+          });
+        }
         ctx->launches++;
-        if (last) { k_kkt_row_batch<<<grid_rows, kThreads, 0, st>>>(a); ctx->launches++; }
+        if (last) {
+          const dim3 g(std::max(nblk_row, 1), gyc);
+          with_width(Pc, [&](auto w) { k_kkt_row_batch<decltype(w)::value><<<g, kThreads, 0, st>>>(a); });
+          ctx->launches++;
+        }
       }
       if (timed) MIPCU_CK(cudaEventRecord(ev_t[1], st));
       const double* xin = first ? a.xhat_first : a.xhat_chk;
       double* xo = last ? a.xhat_first : (i == period - 2 ? a.xhat_chk : nullptr);
       if (n) {
-        const bool chk = first || last;
-        const dim3 grid_cols(std::max(nblk_col, 1), chunks);
-        if (chk && xo) k_col_step_batch<true, true><<<grid_cols, kThreads, 0, st>>>(a, i, xin, xo);
-        else if (chk) k_col_step_batch<true, false><<<grid_cols, kThreads, 0, st>>>(a, i, xin, xo);
-        else if (xo) k_col_step_batch<false, true><<<grid_cols, kThreads, 0, st>>>(a, i, xin, xo);
-        else k_col_step_batch<false, false><<<grid_cols, kThreads, 0, st>>>(a, i, xin, xo);
+        if (chk) {
+          const dim3 g(std::max(nblk_col, 1), gyc);
+          with_width(Pc, [&](auto w) {
+            constexpr int P = decltype(w)::value;
+            if (xo) k_col_step_batch<true, true, P><<<g, kThreads, 0, st>>>(a, i, xin, xo, kRowsPerCtaB / kWarps);
+            else k_col_step_batch<true, false, P><<<g, kThreads, 0, st>>>(a, i, xin, xo, kRowsPerCtaB / kWarps);
+          });
+        } else {
+          const dim3 g(std::max(grid_for(n, kWarps * rpw_col), 1), gyj);
+          with_width(Pj, [&](auto w) {
+            constexpr int P = decltype(w)::value;
+            if (fed_col && xo) k_col_step_batch_fed<true, P><<<g, kThreads, 0, st>>>(a, i, xo, rpw_col);
+            else if (fed_col) k_col_step_batch_fed<false, P><<<g, kThreads, 0, st>>>(a, i, xo, rpw_col);
+            else if (xo) k_col_step_batch<false, true, P><<<g, kThreads, 0, st>>>(a, i, xin, xo, rpw_col);
+            else k_col_step_batch<false, false, P><<<g, kThreads, 0, st>>>(a, i, xin, xo, rpw_col);
+          });
+        }
         ctx->launches++;
       }
       if (timed) MIPCU_CK(cudaEventRecord(ev_t[2], st));
       if (first) { k_ctrl_first_batch<<<chunks, kThreads, 0, st>>>(a, nblk_row, nblk_col); ctx->launches++; }
     }
     k_ctrl_check_batch<<<chunks, kThreads, 0, st>>>(a, nblk_row, nblk_col);
-    ctx->launches++;
+    k_publish_batch<<<grid_for(BP), kThreads, 0, st>>>(a);
+    ctx->launches += 2;
     if (grid_elem) { k_restart_apply_batch<<<grid_elem, kThreads, 0, st>>>(a); ctx->launches++; }
   };
 
@@ -841,7 +1163,8 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
     }
     k_permute_scalars<<<grid_for(BP), kThreads, 0, st>>>(a.sc, sc_scratch, d_order, BP);
     std::swap(a.sc, sc_scratch);
-    ctx->launches++;
+    k_publish_batch<<<grid_for(BP), kThreads, 0, st>>>(a);
+    ctx->launches += 2;
     std::vector<int> new_node_of(BP);
     std::vector<Scalars> new_h(BP);
     for (int sl = 0; sl < BP; ++sl) {

@@ -212,3 +212,42 @@ def test_batch_early_branch_stop(built):
     saved = 1 - sum(s.iterations for s in early) / sum(s.iterations for s in exact)
     print(f"iterations saved by the early stop: {100 * saved:.0f} %")
     assert saved > 0.3
+
+
+@pytest.mark.parametrize("case", ["setcover", "mkp_long_rows"])
+def test_batch_result_does_not_depend_on_lane_width_or_entry_feed(built, case, monkeypatch):
+    """A node's iterates must not depend on how its launch was shaped - problems per lane (1 / 2 / 4, picked
+    from the number of nodes still running), rows per warp, warp-uniform or shuffle-fed matrix entries:
+    bit-identical x, duals and iteration counts for every node across all of them (batch.cu pins every
+    rounding of the step and forms the row sums in one order)."""
+    from miplib_b200 import Engine
+    rng = np.random.default_rng(11)
+    if case == "setcover":
+        L = gen.set_cover(300, 700, 8, 20264); B, nfix = 130, 6     # 130 nodes: 4-wide lanes with a ragged tail
+    else:
+        L = gen.mkp(5, 2000, 4, 10, 20265); B, nfix = 70, 40
+    lb, ub = node_boxes(L, B, rng, nfix)
+    settings = [dict(MIPCU_BATCH_WIDTH="1", MIPCU_BATCH_FEED="0", MIPCU_BATCH_FEED_COL="0", MIPCU_BATCH_RPW="8"),
+                dict(),                                                                   # shipped defaults
+                dict(MIPCU_BATCH_WIDTH="4", MIPCU_BATCH_FEED="1", MIPCU_BATCH_FEED_COL="1", MIPCU_BATCH_RPW="1"),
+                dict(MIPCU_BATCH_WIDTH="2", MIPCU_BATCH_FEED="0", MIPCU_BATCH_FEED_COL="1"),
+                dict(MIPCU_BATCH_WIDTH="4", MIPCU_BATCH_FEED="0", MIPCU_BATCH_FEED_COL="0", MIPCU_BATCH_RPW="3")]
+    outs = []
+    with Engine(0) as e:
+        e.load_lp(L)
+        e.set_param("iter_limit", 20000)
+        for env in settings:
+            for k in ("MIPCU_BATCH_WIDTH", "MIPCU_BATCH_FEED", "MIPCU_BATCH_FEED_COL", "MIPCU_BATCH_RPW"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            st, x, y = e.solve_batch(lb, ub, want_y=True)
+            outs.append((st, x, y))
+    st0, x0, y0 = outs[0]
+    assert sum(s.status == "optimal" for s in st0) >= B // 2
+    for env, (st, x, y) in zip(settings[1:], outs[1:]):
+        assert [s.iterations for s in st] == [s.iterations for s in st0], env
+        assert [s.status for s in st] == [s.status for s in st0], env
+        assert np.array_equal(x, x0), (env, float(np.abs(x - x0).max()))
+        assert np.array_equal(y, y0), (env, float(np.abs(y - y0).max()))
+        assert [s.primal_obj for s in st] == [s.primal_obj for s in st0], env
