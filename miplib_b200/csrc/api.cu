@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "internal.h"
 
@@ -65,7 +66,7 @@ void set_default_params(mipcu_ctx* ctx) {
   ctx->params[MIPCU_PARAM_SHARD_EXCHANGE] = 2;
   ctx->params[MIPCU_PARAM_USE_PDL] = 0;
   ctx->params[MIPCU_PARAM_MULTICAST] = 1;
-  ctx->params[MIPCU_PARAM_ROW_SORT] = 1;
+  ctx->params[MIPCU_PARAM_ROW_SORT] = 2;
   ctx->params[MIPCU_PARAM_PEER_TIMEOUT] = 120.0;
   ctx->params[MIPCU_PARAM_VALIDATE] = 0;
 }
@@ -258,8 +259,13 @@ int mipcu_set_objective(mipcu_ctx* ctx, const double* c, int maximize) {
     MIPCU_REQUIRE(ctx->loaded, "mipcu_set_objective: no model loaded");
     MIPCU_REQUIRE(ctx->n == 0 || c, "mipcu_set_objective: null array");
     MIPCU_CK(cudaSetDevice(ctx->device));
-    if (ctx->n)
+    if (ctx->n && ctx->col_perm) {       // the objective follows its columns (binned at load)
+      std::vector<double> staged(c, c + ctx->n);
+      cols_to_internal_order(ctx, staged.data());
+      MIPCU_CK(cudaMemcpy(ctx->c, staged.data(), sizeof(double) * ctx->n, cudaMemcpyHostToDevice));
+    } else if (ctx->n) {
       MIPCU_CK(cudaMemcpyAsync(ctx->c, c, sizeof(double) * ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+    }
     MIPCU_CK(cudaStreamSynchronize(ctx->stream));
     ctx->maximize = maximize != 0;
     ctx->vectors_dirty = true;
@@ -372,7 +378,10 @@ int mipcu_get_scaling(mipcu_ctx* ctx, double* d1, double* d2) {
       MIPCU_CK(cudaMemcpy(d1, ctx->d1, sizeof(double) * ctx->m, cudaMemcpyDeviceToHost));
       rows_to_caller_order(ctx, d1);
     }
-    if (d2 && ctx->n) MIPCU_CK(cudaMemcpy(d2, ctx->d2, sizeof(double) * ctx->n, cudaMemcpyDeviceToHost));
+    if (d2 && ctx->n) {
+      MIPCU_CK(cudaMemcpy(d2, ctx->d2, sizeof(double) * ctx->n, cudaMemcpyDeviceToHost));
+      cols_to_caller_order(ctx, d2);
+    }
   });
 }
 

@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(kThreads) k_row_batch_long(const BatchArgs a, 
   }
   const size_t slot = (size_t)row * a.BP + b;       // partial index: one entry per row
   const double lo = a.lo[row], hi = a.hi[row];
-  if (MODE == 1) {
+  if constexpr (MODE == 1) {
     const double d1 = a.d1[row];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
@@ -322,8 +322,7 @@ __global__ void __launch_bounds__(kThreads) k_row_batch_long(const BatchArgs a, 
       const double rv = __dadd_rn(isfinite(lo) ? fmax(-kdx, 0.0) : 0.0, isfinite(hi) ? fmax(kdx, 0.0) : 0.0);
       a.partials[((size_t)Q_RAYP_ROWV * a.nblk_max + row) * a.BP + b + p] = __dmul_rn(rv, rv);
     }
-    return;
-  }
+  } else {
   double red[5][P];
 #pragma unroll
   for (int i = 0; i < 5; ++i)
@@ -352,6 +351,7 @@ __global__ void __launch_bounds__(kThreads) k_row_batch_long(const BatchArgs a, 
     for (int i = 0; i < 5; ++i)
 #pragma unroll
       for (int p = 0; p < P; ++p) a.partials[((size_t)q[i] * a.nblk_max + row) * a.BP + b + p] = red[i][p];
+  }
   }
 }
 
@@ -785,21 +785,22 @@ __global__ void k_restart_apply_batch(const BatchArgs a) {
 // boxes arrive [B][n] from the host; store them scaled and batch-fastest, pad lanes copy LP 0.
 // x0 ([B][n], caller's terms, or null): the start point, clamped into the node's box.
 __global__ void k_load_boxes(const double* __restrict__ lb, const double* __restrict__ ub,
-                             const double* __restrict__ x0,
+                             const double* __restrict__ x0, const int* __restrict__ col_perm,
                              const double* __restrict__ d2, double* __restrict__ l, double* __restrict__ u,
                              double* __restrict__ xcand, int n, int B, int BP) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (size_t)n * BP) return;
   const int b = (int)(e % BP), j = (int)(e / BP);
   const int src = b < B ? b : 0;
-  double lo = lb[(size_t)src * n + j], hi = ub[(size_t)src * n + j];
+  const int jc = col_perm ? col_perm[j] : j;      // the caller's column
+  double lo = lb[(size_t)src * n + jc], hi = ub[(size_t)src * n + jc];
   if (lo <= -INF_THRESHOLD) lo = -INFINITY;
   if (hi >= INF_THRESHOLD) hi = INFINITY;
   lo /= d2[j];
   hi /= d2[j];
   l[e] = lo;
   u[e] = hi;
-  xcand[e] = clampd(x0 ? x0[(size_t)src * n + j] / d2[j] : 0.0, lo, hi);
+  xcand[e] = clampd(x0 ? x0[(size_t)src * n + jc] / d2[j] : 0.0, lo, hi);
 }
 
 // y0 ([B][m], caller's terms and row order) -> yhat [m][BP] in the engine's (scaled, sorted-row) terms
@@ -829,11 +830,12 @@ __global__ void __launch_bounds__(kThreads) k_aty_batch(const BatchArgs a) {
 
 // node_of[slot]: the caller's node whose problem lives in lane `slot` (lanes are re-packed as nodes finish)
 __global__ void k_unscale_batch(const double* __restrict__ xhat, const double* __restrict__ d2,
-                                const int* __restrict__ node_of, double* __restrict__ x_out, int n, int B, int BP) {
+                                const int* __restrict__ node_of, const int* __restrict__ col_perm,
+                                double* __restrict__ x_out, int n, int B, int BP) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (size_t)n * BP) return;
   const int b = node_of[(int)(e % BP)], j = (int)(e / BP);
-  if (b < B) x_out[(size_t)b * n + j] = xhat[e] * d2[j];
+  if (b < B) x_out[(size_t)b * n + (col_perm ? col_perm[j] : j)] = xhat[e] * d2[j];
 }
 
 // Lane compaction: dst[r][s] = src[r][order[s]] for every row r of a [rows][BP] array.
@@ -971,7 +973,7 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
       MIPCU_CK(cudaMemcpyAsync(h_x, x0, sizeof(double) * (size_t)B * n, cudaMemcpyHostToDevice, st));
     }
     if (nB) {
-      k_load_boxes<<<grid_for(nB), kThreads, 0, st>>>(h_l, h_u, h_x, ctx->d2, l, u, a.xhat_chk, n, B, BP);
+      k_load_boxes<<<grid_for(nB), kThreads, 0, st>>>(h_l, h_u, h_x, ctx->col_perm, ctx->d2, l, u, a.xhat_chk, n, B, BP);
       ctx->launches++;
     }
     if (y0 && mB) {
@@ -1207,7 +1209,7 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
   MIPCU_CK(cudaEventRecord(ev_end, st));
   if (x_out && nB) {
     double* d_x = buf.get<double>((size_t)B * n);
-    k_unscale_batch<<<grid_for(nB), kThreads, 0, st>>>(a.xhat_chk, ctx->d2, d_node_of, d_x, n, B, BP);
+    k_unscale_batch<<<grid_for(nB), kThreads, 0, st>>>(a.xhat_chk, ctx->d2, d_node_of, ctx->col_perm, d_x, n, B, BP);
     ctx->launches++;
     MIPCU_CK(cudaMemcpyAsync(x_out, d_x, sizeof(double) * (size_t)B * n, cudaMemcpyDeviceToHost, st));
   }

@@ -191,6 +191,11 @@ struct mipcu_ctx {
   // (row sides, warm-start / solution duals, the test hooks) is permuted at the boundary.
   int* row_perm = nullptr;
   std::vector<int> h_row_perm;   // host copy, fetched on first use by the test hooks
+  // columns binned at load (setup.cu:bin_columns, single-GPU contexts): internal column j is the caller's
+  // column col_perm[j], col_inv is the inverse.  Null = identity.  Every n-vector that crosses the ABI
+  // (objective, boxes, start point, solution, the test hooks) is permuted at the boundary.
+  int *col_perm = nullptr, *col_inv = nullptr;
+  std::vector<int> h_col_perm;
   double *c = nullptr, *lb = nullptr, *ub = nullptr, *lo = nullptr, *hi = nullptr;
   // scaled copies + diagonal scalings
   double *cs = nullptr, *ls = nullptr, *us = nullptr, *los = nullptr, *his = nullptr;
@@ -248,6 +253,8 @@ void set_bounds(mipcu_ctx* ctx, int64_t n_changed, const int64_t* cols, const do
 void spmv_host(mipcu_ctx* ctx, int transpose, const double* v, double* out);
 void build_col_block(mipcu_ctx* ctx);   // collective: the column block of the block-owner exchange
 const std::vector<int>& host_row_perm(mipcu_ctx* ctx);   // empty = identity
+void cols_to_caller_order(mipcu_ctx* ctx, double* v);    // host n-vector, internal -> caller's column order
+void cols_to_internal_order(mipcu_ctx* ctx, double* v);  // host n-vector, caller's -> internal column order
 void rows_to_caller_order(mipcu_ctx* ctx, double* v);    // host m-vector, internal -> caller's row order
 void rows_to_internal_order(mipcu_ctx* ctx, double* v);  // host m-vector, caller's -> internal row order
 

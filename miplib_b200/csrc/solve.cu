@@ -178,24 +178,24 @@ __global__ void k_restart_apply(const Scalars* sc, int j_begin, int n, int m, co
   }
 }
 
-// xs / ys: warm start in the caller's (unscaled) terms; row_perm: internal row -> caller's row
+// xs / ys: warm start in the caller's (unscaled) terms; row_perm / col_perm: internal row / column -> caller's
 __global__ void k_start_point(int n, int m, const double* __restrict__ xs, const double* __restrict__ ys,
-                              const int* __restrict__ row_perm,
+                              const int* __restrict__ row_perm, const int* __restrict__ col_perm,
                               const double* __restrict__ d1, const double* __restrict__ d2,
                               const double* __restrict__ l, const double* __restrict__ u, double sgn,
                               double* __restrict__ xcand, double* __restrict__ yhat) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) xcand[i] = clampd(xs ? xs[i] / d2[i] : 0.0, l[i], u[i]);
+  if (i < n) xcand[i] = clampd(xs ? xs[col_perm ? col_perm[i] : i] / d2[i] : 0.0, l[i], u[i]);
   if (i < m) yhat[i] = ys ? sgn * ys[row_perm ? row_perm[i] : i] / d1[i] : 0.0;
 }
 
 // solution in the caller's terms: unscaled, duals back in the caller's row order
 __global__ void k_unscale(int n, int m, const double* __restrict__ xh, const double* __restrict__ yh,
-                          const int* __restrict__ row_perm,
+                          const int* __restrict__ row_perm, const int* __restrict__ col_perm,
                           const double* __restrict__ d1, const double* __restrict__ d2, double sgn,
                           double* __restrict__ x, double* __restrict__ y) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) x[i] = xh[i] * d2[i];
+  if (i < n) x[col_perm ? col_perm[i] : i] = xh[i] * d2[i];
   if (i < m) y[row_perm ? row_perm[i] : i] = sgn * yh[i] * d1[i];
 }
 
@@ -531,7 +531,7 @@ void init_iterate(mipcu_ctx* ctx, Scalars& h) {
   MIPCU_CK(cudaMemsetAsync(ctx->partials, 0, sizeof(double) * Q_COUNT * ctx->max_blocks, st));
   MIPCU_CK(cudaMemcpyAsync(ctx->d_sc, &h, sizeof(Scalars), cudaMemcpyHostToDevice, st));
   if (nm) {
-    k_start_point<<<grid_for(nm), kThreads, 0, st>>>(n, m, ctx->x_start, ctx->y_start, ctx->row_perm, ctx->d1,
+    k_start_point<<<grid_for(nm), kThreads, 0, st>>>(n, m, ctx->x_start, ctx->y_start, ctx->row_perm, ctx->col_perm, ctx->d1,
                                                      ctx->d2, ctx->ls, ctx->us, sgn, ctx->xhat_chk,
                                                      ctx->yhat);
     ctx->launches++;
@@ -702,7 +702,7 @@ void solve_lp(mipcu_ctx* ctx, mipcu_stats* out) {
   const int nm = std::max(ctx->n, ctx->m);
   const double sgn = ctx->maximize ? -1.0 : 1.0;
   if (nm) {
-    k_unscale<<<grid_for(nm), kThreads, 0, st>>>(ctx->n, ctx->m, ctx->xhat_chk, ctx->yhat, ctx->row_perm, ctx->d1,
+    k_unscale<<<grid_for(nm), kThreads, 0, st>>>(ctx->n, ctx->m, ctx->xhat_chk, ctx->yhat, ctx->row_perm, ctx->col_perm, ctx->d1,
                                                  ctx->d2, sgn, ctx->x_sol, ctx->y_sol);
     ctx->launches++;
   }
@@ -754,6 +754,7 @@ void debug_iterate(mipcu_ctx* ctx, int64_t iters, double* xbar_out, double* y_ou
     MIPCU_CK(cudaMemcpyAsync(y_out, ctx->y, sizeof(double) * ctx->m, cudaMemcpyDeviceToHost, ctx->stream));
   MIPCU_CK(cudaStreamSynchronize(ctx->stream));
   if (y_out) rows_to_caller_order(ctx, y_out);
+  if (xbar_out) cols_to_caller_order(ctx, xbar_out);
 }
 
 void time_kernel(mipcu_ctx* ctx, int which, int reps, int flush_l2, double* mean_us, int64_t* bytes) {

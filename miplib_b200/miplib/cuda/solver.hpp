@@ -153,6 +153,7 @@ struct CudaSolver : detail::ISolver
   void ensure_context();
   std::vector<mipcu_ctx*> node_contexts();   // primary + one loaded copy per extra GPU (B&B rounds)
   void upload_model();
+  void device_holds_row_store();   // bookkeeping after a device load made straight from the row store's content
   // B&B: load the model with extra valid rows appended (cuts); the next plain solve re-uploads
   void upload_rows(std::vector<std::int64_t> const& ptr, std::vector<std::int32_t> const& idx,
                    std::vector<double> const& val, std::vector<double> const& lo,

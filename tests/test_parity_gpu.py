@@ -263,6 +263,52 @@ def test_row_permutation_invariance(engine):
     assert rel(a, b) <= 2e-6
 
 
+def test_load_time_ordering_is_invisible(engine):
+    """MIPCU_PARAM_ROW_SORT: 0 = caller's order, 1 = rows by length, 2 (default) = rows by length + columns binned
+    by (length, first row).  Every vector that crosses the ABI is permuted at the boundary: products, scalings,
+    solutions, duals, bound updates, warm starts and node boxes must come back in the caller's numbering."""
+    L = gen.lp(400, 900, 5, 12)
+    rng = np.random.default_rng(3)
+    v, w = rng.standard_normal(L.n), rng.standard_normal(L.m)
+    out = {}
+    for mode in (0, 1, 2):
+        engine.set_param("row_sort", mode)
+        engine.load_lp(L)
+        assert np.abs(engine.spmv(v) - L.A @ v).max() <= 1e-12
+        assert np.abs(engine.spmv(w, transpose=True) - L.A.T @ w).max() <= 1e-12
+        engine.prepare()
+        d1, d2 = engine.scaling()
+        st = engine.solve(); assert_optimal(st)
+        x, y = engine.x(), engine.y()
+        cert = kkt_verify.certificate(L, x, y)
+        assert max(cert["rel_primal_res"], cert["rel_dual_res"], cert["rel_gap"]) <= 1.05e-6, (mode, cert)
+        # a bound update on a few columns addresses the caller's columns
+        cols = np.array([3, 17, 250, 899]); lbn = L.lb[cols].copy(); ubn = np.minimum(L.ub[cols], 0.25)
+        engine.set_bounds(cols, lbn, ubn)
+        st2 = engine.solve(); assert_optimal(st2)
+        x2 = engine.x()
+        assert np.all(x2[cols] <= 0.25 + 1e-9)
+        # the solution as a warm start (caller's numbering) leads back to the same optimum
+        # (test_warm_start_from_solution_converges_immediately pins the "at once" under the default ordering)
+        engine.warm_start(x2, engine.y())
+        st3 = engine.solve(); assert_optimal(st3)
+        assert rel(st3.primal_obj, st2.primal_obj) <= 2e-6
+        engine.warm_start(None, None)
+        # node boxes [B][n] and their solutions
+        lb = np.tile(L.lb, (3, 1)); ub = np.tile(L.ub, (3, 1)); ub[1, cols] = 0.25; lb[2, 5] = ub[2, 5] = 1.0
+        stb, xb = engine.solve_batch(lb, ub)
+        assert all(s.status == "optimal" for s in stb)
+        assert np.all(xb[1][cols] <= 0.25 + 1e-9) and abs(xb[2][5] - 1.0) <= 1e-12
+        out[mode] = (st.primal_obj, st2.primal_obj, [s.primal_obj for s in stb], d1, d2, x)
+    engine.set_param("row_sort", 2)
+    for mode in (1, 2):
+        assert rel(out[mode][0], out[0][0]) <= 2e-6 and rel(out[mode][1], out[0][1]) <= 2e-6
+        assert max(rel(a, b) for a, b in zip(out[mode][2], out[0][2])) <= 4e-6
+        assert np.abs(out[mode][3] - out[0][3]).max() <= 1e-12 * np.abs(out[0][3]).max()      # same scalings,
+        assert np.abs(out[mode][4] - out[0][4]).max() <= 1e-12 * np.abs(out[0][4]).max()      # caller's order
+        assert rel(float(L.c @ out[mode][5]), out[mode][0]) <= 1e-9
+
+
 def test_resolve_is_deterministic(engine):
     L = gen.lp(300, 500, 6, 9)
     engine.load_lp(L)
