@@ -1,6 +1,9 @@
 // api.cu - the extern "C" surface declared in include/mipcu.h.  Every entry point converts
 // C++ exceptions into rc = 1 + a message retrievable with mipcu_last_error(), the convention of
 // the reference's own C API (reference miplib/capi.cpp:7-28).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -227,8 +230,16 @@ int mipcu_load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64
                         ctx->params[MIPCU_PARAM_MULTICAST] == ctx->multicast_at_setup;
       keep = dist_sum_scalar(ctx, same ? 1.0 : 0.0) > ctx->world - 0.5;
     }
+    const bool timing = std::getenv("MIPCU_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+      if (timing)
+        std::fprintf(stderr, "[mipcu_load_lp rank %d] %s %.1f ms\n", ctx->rank, what,
+                     1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    };
     if (!keep) p2p_teardown(ctx);
     ctx->keep_exchange = keep;
+    lap(keep ? "exchange mappings kept" : "exchange torn down");
     try {
       load_lp(ctx, m, n, nnz, row_ptr, col_idx, val, c, lb, ub, row_lo, row_hi, maximize);
     } catch (...) {
@@ -236,8 +247,10 @@ int mipcu_load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64
       throw;
     }
     ctx->keep_exchange = false;
+    lap("load_lp");
     if (keep) {
       own_rebuild(ctx);   // only the column block of the block-owner exchange depends on the matrix
+      lap("column block rebuilt");
     } else {
       p2p_setup(ctx);   // collective on sharded contexts: maps the peers' exchange buffers
       own_setup(ctx);   // block-owner exchange (MIPCU_PARAM_SHARD_EXCHANGE = 2): column block of the whole matrix
