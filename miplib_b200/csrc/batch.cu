@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 #include <vector>
@@ -870,17 +871,28 @@ void with_width(int P, F&& f) {
   else f(std::integral_constant<int, 1>{});
 }
 
+// Scratch of one batch call.  From the context's stream-ordered pool when it has one (a branch and bound
+// issues a round every few hundred milliseconds: ~25 arrays of up to 50 MB each through cudaMalloc /
+// cudaFree were 15 - 25 ms of every round, and cudaFree synchronises the device); the pool keeps the
+// memory between rounds.  Freed in stream order when the call returns.
 struct DeviceBuffers {
+  mipcu_ctx* ctx;
   std::vector<void*> owned;
+  explicit DeviceBuffers(mipcu_ctx* c) : ctx(c) {}
   template <class T>
   T* get(size_t count) {
     T* p = nullptr;
-    MIPCU_CK(cudaMalloc(&p, sizeof(T) * std::max<size_t>(count, 1)));
+    const size_t bytes = sizeof(T) * std::max<size_t>(count, 1);
+    if (ctx->pool_alloc) MIPCU_CK(cudaMallocFromPoolAsync(&p, bytes, (cudaMemPool_t)ctx->pool, ctx->stream));
+    else MIPCU_CK(cudaMalloc(&p, bytes));
     owned.push_back(p);
     return p;
   }
   ~DeviceBuffers() {
-    for (void* p : owned) cudaFree(p);
+    for (void* p : owned) {
+      if (ctx->pool_alloc) cudaFreeAsync(p, ctx->stream);
+      else cudaFree(p);
+    }
   }
 };
 
@@ -911,6 +923,13 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
   auto t0 = std::chrono::steady_clock::now();
   cudaStream_t st = ctx->stream;
   ctx->launches = 0;
+  const bool timing = std::getenv("MIPCU_TIMING") != nullptr;      // wall-clock laps of the call on stderr
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(st);
+    std::fprintf(stderr, "[mipcu_solve_lp_batch] %s %.1f ms\n", what,
+                 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  };
   if (!ctx->d_sc) MIPCU_CK(cudaMalloc(&ctx->d_sc, sizeof(Scalars)));
   if (!ctx->h_sc) MIPCU_CK(cudaMallocHost(&ctx->h_sc, sizeof(Scalars) * 2));
   for (auto& e : ctx->ev)
@@ -941,7 +960,7 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
   const double time_limit = ctx->params[MIPCU_PARAM_TIME_LIMIT];
   const double sgn = ctx->maximize ? -1.0 : 1.0;
 
-  DeviceBuffers buf;
+  DeviceBuffers buf(ctx);
   BatchArgs a{};
   a.rptr = ctx->rows.ptr; a.ridx = ctx->rows.idx; a.rval = ctx->rows.val;
   a.cptr = ctx->cols.ptr; a.cidx = ctx->cols.idx; a.cval = ctx->cols.val;
@@ -992,6 +1011,7 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
       MIPCU_CK(cudaMemsetAsync(a.yhat, 0, sizeof(double) * std::max<size_t>(mB, 1), st));
     }
   }
+  lap("scratch allocated, boxes and start points on the device");
   std::vector<Scalars> h(BP);
   for (int b = 0; b < BP; ++b) {
     Scalars& s = h[b];
@@ -1207,6 +1227,7 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
     }
   }
   MIPCU_CK(cudaEventRecord(ev_end, st));
+  lap("iterations");
   if (x_out && nB) {
     double* d_x = buf.get<double>((size_t)B * n);
     k_unscale_batch<<<grid_for(nB), kThreads, 0, st>>>(a.xhat_chk, ctx->d2, d_node_of, ctx->col_perm, d_x, n, B, BP);
@@ -1220,6 +1241,7 @@ void solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const double* u
     MIPCU_CK(cudaMemcpyAsync(y_out, d_y, sizeof(double) * (size_t)B * m, cudaMemcpyDeviceToHost, st));
   }
   MIPCU_CK(cudaStreamSynchronize(st));
+  lap("solutions read back");
   float ms = 0.f;
   MIPCU_CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
