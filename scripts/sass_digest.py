@@ -9,7 +9,9 @@ WANT = ["k_row_step<0, false>", "k_row_step<0, true>", "k_col_step<0, false, fal
         "k_kkt_row<0>", "k_spmv<0>", "k_row_step<8, false>", "k_col_step<8, false, false>",
         "k_row_step_own<0, false, false>", "k_row_step_own<0, false, true>", "k_col_step_own<0, false, false, false>",
         "k_col_step_own<0, false, false, true>", "k_primal_step_p2p<false, false>",
-        "k_row_step_batch<false>", "k_col_step_batch<false, false>", "k_row_batch_long<false, 0>",
+        "k_row_step_batch_fed<4>", "k_row_step_batch_fed<1>", "k_col_step_batch<false, false, 2>",
+        "k_col_step_batch<false, false, 1>", "k_row_step_batch<true, 2>", "k_col_step_batch<true, true, 2>",
+        "k_row_batch_long<false, 0, 2>", "k_publish_batch",
         "k_ctrl_check", "k_ctrl_check_batch", "k_restart_apply"]
 
 
