@@ -322,7 +322,51 @@ bool CudaBranchAndBound::absorb_lazy_rows()
   return true;
 }
 
-// nearest / up / down rounding of the integer columns of an LP point, clipped to the node box
+// 1-opt on a feasible point (SCIP's "oneopt" idea): every integer column with a cost is moved as far
+// towards its cheaper side as the root box and the slack of its rows allow, the most expensive columns
+// first, row activities kept up to date; repeated while something moves.  A rounded-up LP point of a
+// covering model carries many redundant columns (config 4: 87 585 after rounding, 40 212 is the LP bound);
+// this is what removes them.  x must be row-feasible on entry and stays so.
+bool CudaBranchAndBound::one_opt(std::vector<double>& x) const
+{
+  if (opt_order.empty() || cptr.size() != n + 1) return false;
+  std::vector<double> act(m, 0.0);
+  for (std::size_t r = 0; r < m; ++r)
+  {
+    double a = 0;
+    for (std::int64_t k = rptr[r]; k < rptr[r + 1]; ++k) a += rval[k] * x[ridx[k]];
+    act[r] = a;
+  }
+  bool moved_any = false;
+  for (int pass = 0; pass < 4; ++pass)
+  {
+    bool moved = false;
+    for (std::int32_t j : opt_order)
+    {
+      double const dir = cost[j] > 0 ? -1.0 : 1.0;                 // the direction that lowers the objective
+      double room = dir < 0 ? x[j] - root_lb[j] : root_ub[j] - x[j];
+      if (!(room >= 1.0 - 1e-9)) continue;
+      for (std::int64_t k = cptr[j]; k < cptr[j + 1] && room >= 1.0 - 1e-9; ++k)
+      {
+        std::int32_t const r = cidx[k];
+        double const d = cval[k] * dir;                            // change of the row's activity per unit step
+        if (d > 0 && !std::isinf(rhi[r])) room = std::min(room, (rhi[r] - act[r]) / d);
+        else if (d < 0 && !std::isinf(rlo[r])) room = std::min(room, (act[r] - rlo[r]) / -d);
+      }
+      double const step = std::floor(room + 1e-9);
+      if (!(step >= 1.0) || std::isinf(step)) continue;
+      x[j] += dir * step;
+      for (std::int64_t k = cptr[j]; k < cptr[j + 1]; ++k) act[cidx[k]] += cval[k] * dir * step;
+      moved = true;
+    }
+    if (!moved) break;
+    moved_any = true;
+  }
+  return moved_any;
+}
+
+// nearest / up / down rounding of the integer columns of an LP point, clipped to the node box; a rounding
+// that is feasible and not far above the incumbent is also handed to one_opt
 void CudaBranchAndBound::try_roundings(std::vector<double> const& x, std::vector<double> const& lb,
                                        std::vector<double> const& ub)
 {
@@ -339,7 +383,13 @@ void CudaBranchAndBound::try_roundings(std::vector<double> const& x, std::vector
       }
       cand[j] = v;
     }
-    try_incumbent(cand);
+    bool const had = have_incumbent;
+    double const before = best;
+    if (!try_incumbent(cand)) continue;                     // infeasible, or rejected by a lazy handler
+    // worth polishing: the first feasible point, a new incumbent, or a point within 25 % of the incumbent
+    double const v = objective(cand);
+    bool const promising = !had || best < before || v <= best + 0.25 * std::abs(best);
+    if (pure_integer && promising && one_opt(cand)) try_incumbent(cand);
   }
 }
 
@@ -351,7 +401,8 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   };
   double const inf = S.infinity();
-  std::vector<double> root_lb(n), root_ub(n);
+  root_lb.assign(n, 0.0);
+  root_ub.assign(n, 0.0);
   for (std::size_t j = 0; j < n; ++j)
   {
     root_lb[j] = S.m_columns[j].lb <= -inf ? -kInf : S.m_columns[j].lb;
@@ -363,6 +414,11 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
     }
   }
   if (!propagate(root_lb, root_ub)) return {R::Infeasible, false};
+  opt_order.clear();
+  for (std::size_t j = 0; j < n; ++j)
+    if (is_int[j] && cost[j] != 0) opt_order.push_back(static_cast<std::int32_t>(j));
+  std::stable_sort(opt_order.begin(), opt_order.end(),
+                   [&](std::int32_t a, std::int32_t b) { return std::abs(cost[a]) > std::abs(cost[b]); });
 
   auto finish = [&](bool complete) -> std::pair<R, bool> {
     S.m_info.proven_optimal = complete && have_incumbent;
@@ -453,6 +509,7 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
   std::priority_queue<Node, std::vector<Node>, decltype(by_bound)> open(by_bound);
   open.push(Node{{}, -kInf, 0, nullptr, nullptr, 0.0, false});
   bool complete = true;
+  double lost_bound = kInf;      // smallest bound among the nodes given up undecided (they leave no open node)
   bool unbounded_relaxation = false;
   std::int64_t const node_limit = 4000000;
   std::size_t const per_gpu = 128;                       // node LPs per GPU per round
@@ -588,10 +645,15 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
       {
         unbounded_relaxation = true;                 // an unbounded node LP: no finite optimum to prove
         complete = false;
+        lost_bound = -kInf;
         continue;
       }
-      if (lp.status == MIPCU_NUMERICAL_ERROR) { complete = false; continue; }
-      if (lp.status == MIPCU_TIME_LIMIT) { complete = false; continue; }
+      if (lp.status == MIPCU_NUMERICAL_ERROR || lp.status == MIPCU_TIME_LIMIT)
+      {
+        complete = false;
+        lost_bound = std::min(lost_bound, node.bound);
+        continue;
+      }
       double node_bound = node.bound;
       bool const early = lp.status == MIPCU_BRANCH;      // cannot be pruned by bound: branch on the 1e-4 point
       if (early)
@@ -672,11 +734,17 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
               open.push(std::move(again));
             }
             else
+            {
               complete = false;                        // an integral LP point that rounding broke
+              lost_bound = std::min(lost_bound, node_bound);
+            }
           }
         }
         else
+        {
           complete = false;                            // undecided node with nothing to branch on
+          lost_bound = std::min(lost_bound, node_bound);
+        }
         continue;
       }
       double const split = std::floor(x[pick]);
@@ -709,7 +777,19 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
       }
     }
   }
-  S.m_info.best_bound = have_incumbent ? sgn * best : 0;
+  // Global dual bound.  A finished tree proves the incumbent; an interrupted one (time or node limit) is
+  // bounded by its best undecided node: rounds are processed whole, so every such node is either in
+  // `open` here - ordered by bound, its top carries the smallest one - or was given up undecided
+  // (numerical error, time limit inside its LP, nothing left to branch on), which lost_bound remembers.
+  if (complete)
+    S.m_info.best_bound = have_incumbent ? sgn * best : 0;
+  else
+  {
+    double lower = std::min(lost_bound, open.empty() ? kInf : open.top().bound);
+    if (have_incumbent) lower = std::min(lower, best);
+    S.m_info.best_bound = sgn * lower;             // +-1e300-like values mean "nothing proven"
+    S.m_info.bound_is_open_node = true;
+  }
   if (unbounded_relaxation && !have_incumbent) return {R::InfeasibleOrUnbounded, false};
   return finish(complete);
 }

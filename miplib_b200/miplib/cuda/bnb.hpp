@@ -56,6 +56,7 @@ struct CudaBranchAndBound
   bool absorb_lazy_rows();         // rows posted by lazy handlers -> this tree's row set; true if any
   void try_roundings(std::vector<double> const& x, std::vector<double> const& lb,
                      std::vector<double> const& ub);
+  bool one_opt(std::vector<double>& x) const;   // true: an integer column was moved to a cheaper value
   double cutoff() const;           // nodes whose bound reaches this cannot improve the incumbent
 
   CudaSolver& S;
@@ -70,6 +71,8 @@ struct CudaBranchAndBound
   bool have_incumbent = false;
   bool lazy_rejected = false, lazy_added = false;   // outcome of the last try_incumbent
   std::vector<double> best_x;
+  std::vector<double> root_lb, root_ub;   // the root box after propagation (what an incumbent must respect)
+  std::vector<std::int32_t> opt_order;    // integer columns with a cost, most expensive first (one_opt)
   double cost_norm = 0;            // ||c||_2: turns the engine's relative dual residual back into an absolute one
 };
 

@@ -92,6 +92,28 @@ int miplib_cuda_set_verbose(miplib::Solver* p_solver, int verbose)
   return guarded([&] { miplib::CudaSolver::of(*p_solver).set_verbose(verbose != 0); });
 }
 
+int miplib_cuda_set_time_limit(miplib::Solver* p_solver, double seconds)
+{
+  return guarded([&] { p_solver->set_time_limit(seconds); });
+}
+
+int miplib_cuda_set_nr_threads(miplib::Solver* p_solver, std::int64_t gpus)
+{
+  return guarded([&] {
+    if (gpus < 1) throw std::logic_error("miplib_cuda_set_nr_threads: at least one GPU");
+    p_solver->set_nr_threads(static_cast<std::size_t>(gpus));
+  });
+}
+
+int miplib_cuda_get_bound(miplib::Solver* p_solver, double* best_bound, int* proven_optimal)
+{
+  return guarded([&] {
+    miplib::CudaSolver const& s = miplib::CudaSolver::of(*p_solver);
+    if (best_bound) *best_bound = s.m_info.best_bound;
+    if (proven_optimal) *proven_optimal = s.m_info.proven_optimal ? 1 : 0;
+  });
+}
+
 int miplib_cuda_get_shape(miplib::Solver* p_solver, std::int64_t* n, std::int64_t* m)
 {
   return guarded([&] {

@@ -45,6 +45,14 @@ int miplib_cuda_get_info(miplib::Solver* p_solver, std::int64_t* lp_iterations, 
 // second argument, miplib/solver.hpp:34); this turns the backend's iteration log on / off.
 int miplib_cuda_set_verbose(miplib::Solver* p_solver, int verbose);
 
+// Solver::set_time_limit / set_nr_threads (= GPUs the branch and bound deals its node LPs to) for hosts
+// that only hold the C handle, and the dual side of the last solve: *best_bound is the proven bound on the
+// optimum (the incumbent's objective once the tree is finished; the smallest bound among the open nodes
+// of an interrupted tree; the dual objective of a continuous model), *proven_optimal 0 / 1.
+int miplib_cuda_set_time_limit(miplib::Solver* p_solver, double seconds);
+int miplib_cuda_set_nr_threads(miplib::Solver* p_solver, std::int64_t gpus);
+int miplib_cuda_get_bound(miplib::Solver* p_solver, double* best_bound, int* proven_optimal);
+
 // Number of columns / alive rows of the lowered model.
 int miplib_cuda_get_shape(miplib::Solver* p_solver, std::int64_t* n, std::int64_t* m);
 

@@ -129,6 +129,7 @@ struct CudaSolver : detail::ISolver
     bool polished = false;   // the continuous optimum was snapped to an exact vertex (polish_vertex)
     double seconds = 0, best_bound = 0;
     bool proven_optimal = false;
+    bool bound_is_open_node = false;   // interrupted tree: best_bound is the smallest bound among the open nodes
   };
   SolveInfo m_info;
 

@@ -477,3 +477,39 @@ def test_dumped_instances_are_pinned_by_checksum_and_solve_to_the_golden(built, 
     M["h"].run()
     obj = M["h"].getInfo().objective_function_value
     assert abs(obj - golden["C1_lp"]["objective"]) <= 1e-9 * (1 + abs(obj))
+
+
+@pytest.mark.gpu
+def test_full_size_mip_configs_under_a_time_limit(built):
+    """BASELINE configs 4 / 5 as MIPs at FULL size (20k x 50k set cover, 600 x 100 100 knapsack with switch rows):
+    nobody here can prove their optima (HiGHS has no bound for config 4 and no incumbent for config 5 after a
+    minute), so the branch and bound runs under a time limit and what it returns is checked size-independently:
+    Interrupted with an incumbent that is integral and feasible for every row and bound (recomputed in FP64), the
+    reported objective is c'x, the dual bound is on the right side of the incumbent and not below the root LP
+    bound, and the gap is what rounding + 1-opt + a few thousand nodes give (measured: 6.3 % / 0.24 %)."""
+    lib, C = _front(built)
+    lib.miplib_cuda_set_time_limit.argtypes = [C.c_void_p, C.c_double]
+    for cfg, root_bound, max_gap in ((4, 40211.9658, 0.10), (5, 2305927.33, 0.01)):
+        L = gen.config(cfg)
+        solver = C.c_void_p()
+        assert lib.miplib_create_solver(C.byref(solver), 5) == 0
+        lib.miplib_cuda_set_verbose(solver, 0)
+        rc, keep = _load_csr(lib, C, solver, L, np.ones(L.n, np.int32))       # every column Binary
+        assert rc == 0, lib.miplib_get_last_error()
+        assert lib.miplib_cuda_set_time_limit(solver, 12.0) == 0
+        result, has = C.c_int(-1), C.c_int(-1)
+        assert lib.miplib_cuda_solve(solver, C.byref(result), C.byref(has)) == 0, lib.miplib_get_last_error()
+        assert (result.value, has.value) == (4, 1)                            # Solver::Result::Interrupted, incumbent
+        x = np.empty(L.n); obj = C.c_double(); bound = C.c_double(); proven = C.c_int(-1)
+        assert lib.miplib_cuda_get_values(solver, x.ctypes.data_as(C.c_void_p), C.byref(obj)) == 0
+        assert lib.miplib_cuda_get_bound(solver, C.byref(bound), C.byref(proven)) == 0
+        assert proven.value == 0
+        assert np.abs(x - np.round(x)).max() == 0.0 and x.min() >= 0.0 and x.max() <= 1.0
+        ax = L.A @ x
+        assert np.all(ax <= L.row_hi + 1e-9) and np.all(ax >= L.row_lo - 1e-9)
+        assert abs(float(L.c @ x) - obj.value) <= 1e-9 * (1 + abs(obj.value))
+        sgn = -1.0 if L.maximize else 1.0
+        assert sgn * bound.value <= sgn * obj.value                            # bound on the right side
+        assert sgn * bound.value >= sgn * root_bound - 2e-6 * (1 + abs(root_bound))   # no worse than the root LP
+        assert abs(obj.value - bound.value) <= max_gap * abs(obj.value), (cfg, obj.value, bound.value)
+        assert lib.miplib_destroy_solver(solver) == 0
