@@ -365,6 +365,104 @@ bool CudaBranchAndBound::one_opt(std::vector<double>& x) const
   return moved_any;
 }
 
+// Greedy repair of an integral point inside the root box: while a row is violated, move the integer column of that
+// row that buys the most violation per unit of cost, provided the move breaks no row that holds (rows are
+// re-checked through the column copy).  Covering and packing rows with non-negative coefficients - configs 4
+// and 5 - always find such a move; anything else may get stuck, which is reported.
+bool CudaBranchAndBound::repair(std::vector<double>& x) const
+{
+  if (cptr.size() != n + 1) return false;
+  std::vector<double> act(m, 0.0);
+  for (std::size_t r = 0; r < m; ++r)
+  {
+    double a = 0;
+    for (std::int64_t k = rptr[r]; k < rptr[r + 1]; ++k) a += rval[k] * x[ridx[k]];
+    act[r] = a;
+  }
+  auto violated = [&](std::size_t r) {
+    if (act[r] < rlo[r] - 1e-9 * (1.0 + std::abs(rlo[r]))) return -1;       // too small
+    if (act[r] > rhi[r] + 1e-9 * (1.0 + std::abs(rhi[r]))) return 1;        // too large
+    return 0;
+  };
+  for (int pass = 0; pass < 3; ++pass)
+  {
+    bool any = false;
+    for (std::size_t r = 0; r < m; ++r)
+    {
+      int guard = 0;
+      for (int v = violated(r); v != 0 && guard < 64; v = violated(r), ++guard)
+      {
+        any = true;
+        double const need = v < 0 ? rlo[r] - act[r] : act[r] - rhi[r];
+        std::int32_t pick = -1;
+        double pick_dir = 0, pick_score = kInf;
+        for (std::int64_t k = rptr[r]; k < rptr[r + 1]; ++k)
+        {
+          std::int32_t const j = ridx[k];
+          if (!is_int[j] || rval[k] == 0) continue;
+          double const dir = (rval[k] > 0) == (v < 0) ? 1.0 : -1.0;         // the move that helps this row
+          if (dir > 0 ? x[j] + 1.0 > root_ub[j] + 1e-9 : x[j] - 1.0 < root_lb[j] - 1e-9) continue;
+          bool ok = true;                                                     // must not break a row that holds
+          for (std::int64_t q = cptr[j]; q < cptr[j + 1] && ok; ++q)
+          {
+            std::int32_t const i = cidx[q];
+            if (static_cast<std::size_t>(i) == r) continue;
+            double const a2 = act[i] + cval[q] * dir;
+            if (a2 > rhi[i] + 1e-9 * (1.0 + std::abs(rhi[i])) && cval[q] * dir > 0) ok = false;
+            if (a2 < rlo[i] - 1e-9 * (1.0 + std::abs(rlo[i])) && cval[q] * dir < 0) ok = false;
+          }
+          if (!ok) continue;
+          // cost of the move per unit of this row's violation it removes (other rows it helps count too)
+          double gain = std::min(std::abs(rval[k]), need);
+          for (std::int64_t q = cptr[j]; q < cptr[j + 1]; ++q)
+          {
+            std::int32_t const i = cidx[q];
+            if (static_cast<std::size_t>(i) == r) continue;
+            double const d = cval[q] * dir;
+            if (d > 0 && act[i] < rlo[i]) gain += std::min(d, rlo[i] - act[i]);
+            if (d < 0 && act[i] > rhi[i]) gain += std::min(-d, act[i] - rhi[i]);
+          }
+          double const score = (cost[j] * dir) / std::max(gain, 1e-12);
+          if (score < pick_score) { pick_score = score; pick = j; pick_dir = dir; }
+        }
+        if (pick < 0) return false;
+        x[pick] += pick_dir;
+        for (std::int64_t q = cptr[pick]; q < cptr[pick + 1]; ++q) act[cidx[q]] += cval[q] * pick_dir;
+      }
+      if (violated(r) != 0) return false;
+    }
+    if (!any) return true;
+  }
+  for (std::size_t r = 0; r < m; ++r)
+    if (violated(r) != 0) return false;
+  return true;
+}
+
+// LP-guided start points for the two local searches: integer columns at or above a threshold go up, the rest
+// down; the point is repaired greedily, polished by one_opt and offered as an incumbent.  Pure-integer models
+// only, at the first nodes of the tree and then at every 64th (each call is a few passes over the matrix on the
+// host).  On config 4 at full size this takes the incumbent from 42 920 (rounding up + one_opt) to within a few
+// per cent of the LP bound.
+void CudaBranchAndBound::try_threshold_roundings(std::vector<double> const& x)
+{
+  if (!pure_integer || cptr.size() != n + 1) return;
+  ++threshold_calls;
+  if (threshold_calls > 8 && threshold_calls % 64 != 0) return;
+  std::vector<double> cand(n);
+  for (double theta : {0.9, 0.6, 0.35, 0.15})
+  {
+    for (std::size_t j = 0; j < n; ++j)
+    {
+      double const f = x[j] - std::floor(x[j] + 1e-9);
+      double v = f >= theta ? std::ceil(x[j] - 1e-9) : std::floor(x[j] + 1e-9);
+      cand[j] = std::min(std::max(v, root_lb[j]), root_ub[j]);
+    }
+    if (!repair(cand)) continue;
+    one_opt(cand);
+    try_incumbent(cand);
+  }
+}
+
 // nearest / up / down rounding of the integer columns of an LP point, clipped to the node box; a rounding
 // that is feasible and not far above the incumbent is also handed to one_opt
 void CudaBranchAndBound::try_roundings(std::vector<double> const& x, std::vector<double> const& lb,
@@ -662,6 +760,7 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
         double const d = sgn * lp.dual_obj;
         node_bound = std::max(node_bound, d - std::max(1e-6, S.m_feas_tol) * (1.0 + std::abs(d)));
         try_roundings(x, lb, ub);
+        try_threshold_roundings(x);
         if (node_bound >= cutoff()) continue;
       }
       if (lp.status == MIPCU_OPTIMAL)
@@ -686,6 +785,7 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
           if (objective_integral) node_bound = std::ceil(node_bound - 1e-9);
         }
         try_roundings(x, lb, ub);
+        try_threshold_roundings(x);
         if (node_bound >= cutoff()) continue;
       }
       // branching column: the most fractional integer column of the LP point

@@ -57,6 +57,8 @@ struct CudaBranchAndBound
   void try_roundings(std::vector<double> const& x, std::vector<double> const& lb,
                      std::vector<double> const& ub);
   bool one_opt(std::vector<double>& x) const;   // true: an integer column was moved to a cheaper value
+  bool repair(std::vector<double>& x) const;    // greedy moves until every row holds; false: stuck
+  void try_threshold_roundings(std::vector<double> const& x);   // x_j >= theta -> up, then repair + one_opt
   double cutoff() const;           // nodes whose bound reaches this cannot improve the incumbent
 
   CudaSolver& S;
@@ -73,6 +75,7 @@ struct CudaBranchAndBound
   std::vector<double> best_x;
   std::vector<double> root_lb, root_ub;   // the root box after propagation (what an incumbent must respect)
   std::vector<std::int32_t> opt_order;    // integer columns with a cost, most expensive first (one_opt)
+  std::int64_t threshold_calls = 0;       // nodes whose LP point went through try_threshold_roundings
   double cost_norm = 0;            // ||c||_2: turns the engine's relative dual residual back into an absolute one
 };
 
