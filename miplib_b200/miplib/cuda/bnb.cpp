@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <deque>
 #include <iostream>
@@ -166,7 +167,7 @@ std::size_t CudaBranchAndBound::add_implied_bound_rows(std::vector<double> const
       }
     }
   }
-  if (added) rebuild_columns();
+  if (added) { rebuild_columns(); ++rows_epoch; }
   return added;
 }
 
@@ -186,11 +187,15 @@ double CudaBranchAndBound::cutoff() const
 
 // Activity-based bound tightening to a fixpoint (bounded work).  Returns false when some row can
 // no longer be satisfied inside the box.
-bool CudaBranchAndBound::propagate(std::vector<double>& lb, std::vector<double>& ub) const
+bool CudaBranchAndBound::propagate(std::vector<double>& lb, std::vector<double>& ub, std::int32_t seed_col) const
 {
   std::deque<std::int32_t> work;
-  std::vector<char> queued(m, 1);
-  for (std::size_t r = 0; r < m; ++r) work.push_back(static_cast<std::int32_t>(r));
+  std::vector<char> queued(m, seed_col < 0 ? 1 : 0);
+  if (seed_col < 0)
+    for (std::size_t r = 0; r < m; ++r) work.push_back(static_cast<std::int32_t>(r));
+  else      // the box was at a fixpoint before seed_col's bounds changed: only its rows can tighten anything
+    for (std::int64_t k = cptr[seed_col]; k < cptr[seed_col + 1]; ++k)
+      if (!queued[cidx[k]]) { queued[cidx[k]] = 1; work.push_back(cidx[k]); }
   std::int64_t budget = 30 * static_cast<std::int64_t>(m) + 2000;
   auto touch = [&](std::int32_t col) {
     for (std::int64_t k = cptr[col]; k < cptr[col + 1]; ++k)
@@ -319,6 +324,7 @@ bool CudaBranchAndBound::absorb_lazy_rows()
   S.m_info.lazy_rows += static_cast<std::int64_t>(S.m_lazy_new_rows.size());
   S.m_lazy_new_rows.clear();
   rebuild_columns();
+  ++rows_epoch;
   return true;
 }
 
@@ -468,26 +474,37 @@ void CudaBranchAndBound::try_threshold_roundings(std::vector<double> const& x)
 void CudaBranchAndBound::try_roundings(std::vector<double> const& x, std::vector<double> const& lb,
                                        std::vector<double> const& ub)
 {
-  std::vector<double> cand(n);
+  auto rounded = [&](std::size_t j, int mode) {
+    double v = x[j];
+    if (is_int[j])
+    {
+      v = mode == 0 ? std::round(v) : mode == 1 ? std::ceil(v - 1e-6) : std::floor(v + 1e-6);
+      v = std::min(std::max(v, std::ceil(lb[j] - 1e-9)), std::floor(ub[j] + 1e-9));
+    }
+    return v;
+  };
+  // the three objectives in one pass over the columns, before anything proportional to the matrix: a point
+  // more than 25 % above the incumbent is neither an incumbent nor worth polishing
+  double value[3] = {0, 0, 0};
+  for (std::size_t j = 0; j < n; ++j)
+  {
+    if (cost[j] == 0) continue;
+    for (int mode = 0; mode < 3; ++mode) value[mode] += cost[j] * rounded(j, mode);
+  }
+  std::vector<double> cand;
   for (int mode = 0; mode < 3; ++mode)
   {
-    for (std::size_t j = 0; j < n; ++j)
-    {
-      double v = x[j];
-      if (is_int[j])
-      {
-        v = mode == 0 ? std::round(v) : mode == 1 ? std::ceil(v - 1e-6) : std::floor(v + 1e-6);
-        v = std::min(std::max(v, std::ceil(lb[j] - 1e-9)), std::floor(ub[j] + 1e-9));
-      }
-      cand[j] = v;
-    }
     bool const had = have_incumbent;
     double const before = best;
+    if (had && value[mode] > best + 0.25 * std::abs(best)) continue;
+    cand.resize(n);
+    for (std::size_t j = 0; j < n; ++j) cand[j] = rounded(j, mode);
     if (!try_incumbent(cand)) continue;                     // infeasible, or rejected by a lazy handler
-    // worth polishing: the first feasible point, a new incumbent, or a point within 25 % of the incumbent
-    double const v = objective(cand);
-    bool const promising = !had || best < before || v <= best + 0.25 * std::abs(best);
-    if (pure_integer && promising && one_opt(cand)) try_incumbent(cand);
+    // worth polishing: the first feasible point, a new incumbent, and - every few nodes, it is a pass or
+    // four over the matrix - a point within 25 % of the incumbent
+    bool const improved = !had || best < before;
+    bool const turn = ++polish_candidates <= 32 || polish_candidates % 8 == 0;
+    if (pure_integer && (improved || turn) && one_opt(cand)) try_incumbent(cand);
   }
 }
 
@@ -625,6 +642,11 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
   // parents' solutions ride on the open nodes only while that stays cheap on the host
   std::size_t const warm_budget_bytes = std::size_t(2) << 30;
   std::vector<mipcu_stats> stats;
+  // MIPLIB_CUDA_TIMING: where the wall time of the tree goes (printed once at the end)
+  bool const timing = std::getenv("MIPLIB_CUDA_TIMING") != nullptr;
+  double t_assemble = 0, t_pack = 0, t_gpu = 0, t_post = 0;
+  std::int64_t rounds = 0;
+  auto lap_from = [&](double since) { return elapsed() - since; };
   while (!open.empty())
   {
     if ((S.m_time_limit > 0 && elapsed() > S.m_time_limit) || S.m_info.nodes >= node_limit)
@@ -640,6 +662,7 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
       upload();
     }
     // ---- a round: the best open nodes, tightened on the host, the survivors solved together ----
+    double t_mark = elapsed();
     round.clear();
     while (!open.empty() && round.size() < round_cap)
     {
@@ -650,7 +673,7 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
       S.m_info.nodes += 1;
       Pending p{std::move(node), root_lb, root_ub, kInf, true};
       for (Change const& c : p.node.changes) { p.lb[c.col] = c.lb; p.ub[c.col] = c.ub; }
-      if (!propagate(p.lb, p.ub)) continue;
+      if (!propagate(p.lb, p.ub, p.node.epoch == rows_epoch ? p.node.branched : -1)) continue;
       if (all_fixed(p.lb, p.ub))
       {
         try_incumbent(p.lb);
@@ -658,7 +681,10 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
       }
       round.push_back(std::move(p));
     }
+    t_assemble += lap_from(t_mark);
+    t_mark = elapsed();
     if (round.empty()) continue;
+    ++rounds;
     std::size_t const B = round.size();
     box_lb.resize(B * n);
     box_ub.resize(B * n);
@@ -698,6 +724,8 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
         w0s[b] = p.node.weight;
       }
     }
+    t_pack += lap_from(t_mark);
+    t_mark = elapsed();
     // deal the round to the GPUs: nodes are independent, no device-side exchange
     {
       std::size_t const G = std::min(gpus.size(), B);
@@ -722,6 +750,8 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
       for (std::string const& e : errors)
         if (!e.empty()) throw std::logic_error("Cuda backend: " + e);
     }
+    t_gpu += lap_from(t_mark);
+    t_mark = elapsed();
     S.m_info.lp_solves += static_cast<std::int64_t>(B);
     S.m_info.kernel_launches += stats[0].kernel_launches;
     if (user_verbose)
@@ -854,16 +884,18 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
         px = std::make_shared<std::vector<double> const>(x);
         py = std::make_shared<std::vector<double> const>(ys.begin() + b * m, ys.begin() + (b + 1) * m);
       }
+      // carry every bound propagation found, so the children start from the tightened box
+      std::vector<Change> inherited;
+      for (std::size_t j = 0; j < n; ++j)
+        if (lb[j] != root_lb[j] || ub[j] != root_ub[j])
+          inherited.push_back({static_cast<std::int32_t>(j), lb[j], ub[j]});
       for (int side = 0; side < 2; ++side)
       {
         Node child;
         child.x = px;
         child.y = py;
         child.weight = px ? lp.primal_weight : 0.0;
-        // carry every bound propagation found, so the child starts from the tightened box
-        for (std::size_t j = 0; j < n; ++j)
-          if (lb[j] != root_lb[j] || ub[j] != root_ub[j])
-            child.changes.push_back({static_cast<std::int32_t>(j), lb[j], ub[j]});
+        child.changes = inherited;
         double cl = lb[pick], cu = ub[pick];
         if (side == 0) cu = split; else cl = split + 1;
         if (cl > cu) continue;
@@ -873,10 +905,17 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
         if (!found) child.changes.push_back({pick, cl, cu});
         child.bound = node_bound;
         child.depth = node.depth + 1;
+        child.branched = pick;
+        child.epoch = rows_epoch;
         open.push(std::move(child));
       }
     }
+    t_post += lap_from(t_mark);
   }
+  if (timing)
+    std::fprintf(stderr, "[miplib cuda b&b] %lld rounds, %lld nodes: assemble (pop + propagate) %.2f s, pack boxes %.2f s, "
+                 "node LPs on the device %.2f s, decide / round / branch %.2f s\n",
+                 static_cast<long long>(rounds), static_cast<long long>(S.m_info.nodes), t_assemble, t_pack, t_gpu, t_post);
   // Global dual bound.  A finished tree proves the incumbent; an interrupted one (time or node limit) is
   // bounded by its best undecided node: rounds are processed whole, so every such node is either in
   // `open` here - ordered by bound, its top carries the smallest one - or was given up undecided

@@ -45,9 +45,14 @@ struct CudaBranchAndBound
     std::shared_ptr<std::vector<double> const> x, y;
     double weight = 0;
     bool exact = false;            // solve this node's LP to full accuracy (no early MIPCU_BRANCH stop)
+    // The parent's box was propagated to a fixpoint before it was split, so only the rows of the branched
+    // column can tighten anything in the child: propagate() starts from them (-1: from every row).  Valid
+    // while the row set is the one the parent saw (rows_epoch).
+    std::int32_t branched = -1;
+    std::int64_t epoch = -1;
   };
 
-  bool propagate(std::vector<double>& lb, std::vector<double>& ub) const;
+  bool propagate(std::vector<double>& lb, std::vector<double>& ub, std::int32_t seed_col = -1) const;
   std::size_t add_implied_bound_rows(std::vector<double> const& lb, std::vector<double> const& ub);
   void rebuild_columns();
   bool row_feasible(std::vector<double> const& x, double tol_scale) const;
@@ -75,6 +80,8 @@ struct CudaBranchAndBound
   std::vector<double> best_x;
   std::vector<double> root_lb, root_ub;   // the root box after propagation (what an incumbent must respect)
   std::vector<std::int32_t> opt_order;    // integer columns with a cost, most expensive first (one_opt)
+  std::int64_t rows_epoch = 0;            // bumped whenever rows join the tree (lazy handlers, implied bounds)
+  std::int64_t polish_candidates = 0;     // feasible roundings seen (one_opt runs on the first 32, then every 8th)
   std::int64_t threshold_calls = 0;       // nodes whose LP point went through try_threshold_roundings
   double cost_norm = 0;            // ||c||_2: turns the engine's relative dual residual back into an absolute one
 };
