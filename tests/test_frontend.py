@@ -38,6 +38,13 @@ def test_libmiplib_exports_reference_capi(built):
                 "miplib_shallow_copy_solver", "miplib_create_var", "miplib_destroy_var",
                 "miplib_shallow_copy_var"]:                     # reference miplib/capi.hpp:16-23
         assert f" T {sym}" in out, sym
+    # and every entry point the Cuda backend adds (miplib_b200/miplib/cuda/capi.hpp) is exported
+    import re
+    header = (built.ROOT / "miplib_b200" / "miplib" / "cuda" / "capi.hpp").read_text()
+    declared = re.findall(r"^int\s+(miplib_cuda_\w+)\s*\(", header, flags=re.M)
+    assert len(declared) >= 11 and "miplib_cuda_get_bound" in declared
+    for sym in declared:
+        assert f" T {sym}" in out, sym
 
 
 def write_models(path, models, indicator_rows=None):
