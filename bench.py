@@ -11,11 +11,13 @@ A "step" is ONE COMPLETE SOLVE of that LP from a zero start to 1e-6 relative KKT
   metric / value : PDHG iterations per second with the model resident in HBM
                    (total iterations of the K timed solves / their wall time)
   time_to_tol_s  : seconds per solve to 1e-6 relative KKT (resident)
-  e2e            : the same metric through the C ABI with HOST buffers: mipcu_load_lp (H2D of the
-                   CSR + vectors from pinned memory, CSC build) + mipcu_solve_lp (scaling, step
-                   size, iterations) + mipcu_get_x / get_y (D2H), all inside the timed region
-  roofline       : the dominant kernel (fused K.xbar + dual step, k_row_step), timed in situ by
-                   CUDA events on the solver's stream during the timed solves
+  e2e            : the same metric from HOST buffers, everything inside the timed region.  N = 1: through the
+                   reference-facing plugin call - miplib_create_solver(Cuda) + miplib_cuda_load_csr +
+                   Solver::solve() + values, a fresh solver every step - with the C-ABI figure beside it
+                   (e2e.c_abi: mipcu_load_lp, H2D from pinned memory + transposes, + mipcu_solve_lp +
+                   mipcu_get_x / get_y); N > 1: the C ABI on every rank
+  roofline       : the slower of the two fused kernels (k_row_step / k_col_step), timed in situ by
+                   CUDA events on the solver's stream during the timed solves; both are listed
   cpu_baseline   : the multi-core C/OpenMP port of the same iteration (oracle/pdhg_port.c) on the
                    same LP, a bounded number of iterations, on this box's host cores
 
@@ -24,12 +26,16 @@ A "step" is ONE COMPLETE SOLVE of that LP from a zero start to 1e-6 relative KKT
                    the golden objective; a failed check makes the run exit non-zero
   nodes          : bounded secondary block (config 4): rounds of 128 branch-and-bound node LPs per
                    GPU, dealt to the ranks with no collective; root LP certificate-checked
+  mip            : N = 1 only, informative (never changes the exit code): config 4 as a MIP at FULL size
+                   for 12 s through the plugin C API; incumbent recomputed integral and row-feasible,
+                   dual bound of the interrupted tree, gap
   cpu_baseline_highs : N = 1 only - SciPy-HiGHS (the stand-in for the reference's SCIP / lp_solve
                    backends) on config 1 to optimality and on the bench config under a time cap
 
 N > 1 (torchrun, one process per GPU): the same LP row-sharded across the ranks (strong scaling):
-every rank owns m/N rows of A; the K'y partial sums are combined by one NCCL all-reduce per
-iteration.  --impl reference: rank 0 times the CPU port; other ranks exit 0.
+every rank owns m/N rows of A and n/N columns of A' (block-owner exchange: the slices of the iterates are
+pushed into peer memory over NVLink from the kernels' epilogues; --shard-exchange 0 = one NCCL all-reduce of
+the K'y partial sums per iteration).  --impl reference: rank 0 times the CPU port; other ranks exit 0.
 """
 from __future__ import annotations
 
@@ -445,6 +451,8 @@ def run_cuda(args, rank, world, local_rank):
         line["spmv"] = spmv
     if nodes is not None:
         line["nodes"] = nodes
+    if world == 1 and not args.no_nodes:
+        line["mip"] = mip_block(4, 12.0)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(L)
         line["cpu_baseline_highs"] = cpu_baseline_highs(args.config, args.highs_cap)
@@ -505,6 +513,69 @@ def plugin_e2e(args, L, A, host) -> dict:
             "seconds_per_solve": secs / args.steps, "result": outs[-1][0], "objective": outs[-1][1],
             "through": "plugin: miplib_create_solver(Cuda) + miplib_cuda_load_csr + Solver::solve() + values "
                        "(libmiplib.so; host buffers, a fresh solver every step)"}
+
+
+def mip_block(cfg: int, seconds: float) -> dict:
+    """Bounded secondary block (N = 1): BASELINE config 4 as a MIP at FULL size through the plugin C API
+    (miplib_create_solver(Cuda) + miplib_cuda_load_csr with Binary columns + Solver::solve() under a time
+    limit).  Nobody here can prove its optimum, so the outcome is checked size-independently: the incumbent
+    is integral and feasible for every row (recomputed in FP64), its objective is c'x, the dual bound is on
+    the right side of it.  Informative only: never changes the exit code."""
+    import ctypes as C
+    from miplib_b200 import build
+    from oracle import gen
+    try:
+        L = gen.config(cfg)
+        A = L.A.tocsr(); A.sort_indices()
+        lib = C.CDLL(str(build.FRONT_LIB))
+        lib.miplib_get_last_error.restype = C.c_char_p
+        lib.miplib_cuda_load_csr.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 9 + [C.c_int]
+        lib.miplib_cuda_set_time_limit.argtypes = [C.c_void_p, C.c_double]
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        arrs = [A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data.astype(np.float64),
+                np.ascontiguousarray(L.c, dtype=np.float64), np.ascontiguousarray(L.lb, dtype=np.float64),
+                np.ascontiguousarray(L.ub, dtype=np.float64), np.ones(L.n, np.int32),
+                np.maximum(L.row_lo, -1e30), np.minimum(L.row_hi, 1e30)]
+        s = C.c_void_p()
+        if lib.miplib_create_solver(C.byref(s), 5):
+            raise RuntimeError(lib.miplib_get_last_error().decode())
+        try:
+            lib.miplib_cuda_set_verbose(s, 0)
+            rc = lib.miplib_cuda_load_csr(s, L.m, L.n, *[vp(a) for a in arrs], int(L.maximize))
+            rc = rc or lib.miplib_cuda_set_time_limit(s, float(seconds))
+            res, has = C.c_int(), C.c_int()
+            t0 = time.perf_counter()
+            rc = rc or lib.miplib_cuda_solve(s, C.byref(res), C.byref(has))
+            secs = time.perf_counter() - t0
+            if rc:
+                raise RuntimeError(lib.miplib_get_last_error().decode())
+            it, nodes, bound, proven = C.c_int64(), C.c_int64(), C.c_double(), C.c_int()
+            lib.miplib_cuda_get_info(s, C.byref(it), None, C.byref(nodes), None)
+            lib.miplib_cuda_get_bound(s, C.byref(bound), C.byref(proven))
+            out = {"workload": f"C{cfg} as a MIP at full size ({L.m} x {L.n} binaries), {seconds:g} s time limit, "
+                               "branch and bound with batched node LPs on one GPU (plugin C API)",
+                   "seconds": secs, "result": res.value, "has_incumbent": bool(has.value), "nodes": nodes.value,
+                   "lp_iterations": it.value, "dual_bound": bound.value, "proven_optimal": bool(proven.value)}
+            if has.value:
+                x = np.empty(L.n); obj = C.c_double()
+                lib.miplib_cuda_get_values(s, vp(x), C.byref(obj))
+                ax = L.A @ x
+                sgn = -1.0 if L.maximize else 1.0
+                out.update(incumbent=obj.value, relative_gap=abs(obj.value - bound.value) / max(1e-9, abs(obj.value)),
+                           max_integrality_violation=float(np.abs(x - np.round(x)).max()),
+                           max_row_violation=float(max((L.row_lo - ax)[np.isfinite(L.row_lo)].max(initial=0.0),
+                                                       (ax - L.row_hi)[np.isfinite(L.row_hi)].max(initial=0.0), 0.0)),
+                           objective_recomputed=float(L.c @ x))
+                out["ok"] = bool(out["max_integrality_violation"] == 0.0 and out["max_row_violation"] <= 1e-9 and
+                                 abs(out["objective_recomputed"] - obj.value) <= 1e-9 * (1 + abs(obj.value)) and
+                                 sgn * bound.value <= sgn * obj.value)
+            else:
+                out["ok"] = False
+            return out
+        finally:
+            lib.miplib_destroy_solver(s)
+    except Exception as e:       # informative block: report, never fail the bench
+        return {"error": str(e)[:200], "ok": False}
 
 
 def nodes_block(cfg, per_gpu, steps, warmup, rank, world, local_rank, dist) -> dict | None:
