@@ -635,32 +635,30 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
   // costs on the infinite side are counted into the dual residual instead (solve.cu: Q_DRES2), so the
   // dual objective may overshoot the node optimum by about that residual times |x|.
   struct Pending { Node node; std::vector<double> lb, ub; double cut; bool finite_box; };
-  std::vector<Pending> round;
-  std::vector<double> box_lb, box_ub, cuts, xs, ys, x0s, y0s, w0s, btol;
+  // Everything one round owns.  Two of them: while the device solves the node LPs of one round, the host
+  // decides the previous one (incumbents, branching) and assembles the next (see the loop below).
+  struct RoundData
+  {
+    std::vector<Pending> round;
+    std::vector<double> box_lb, box_ub, cuts, xs, ys, x0s, y0s, w0s, btol;
+    std::vector<mipcu_stats> stats;
+    std::string error;
+  };
+  RoundData bufs[2];
   // accuracy at which a node that cannot be pruned by bound is handed back for branching
   double const branch_tol = std::max(1e-4, S.m_feas_tol);
   // parents' solutions ride on the open nodes only while that stays cheap on the host
   std::size_t const warm_budget_bytes = std::size_t(2) << 30;
-  std::vector<mipcu_stats> stats;
   // MIPLIB_CUDA_TIMING: where the wall time of the tree goes (printed once at the end)
   bool const timing = std::getenv("MIPLIB_CUDA_TIMING") != nullptr;
   double t_assemble = 0, t_pack = 0, t_gpu = 0, t_post = 0;
   std::int64_t rounds = 0;
   auto lap_from = [&](double since) { return elapsed() - since; };
-  while (!open.empty())
-  {
-    if ((S.m_time_limit > 0 && elapsed() > S.m_time_limit) || S.m_info.nodes >= node_limit)
-    {
-      complete = false;
-      break;
-    }
-    // rows posted by lazy handlers during the last round join the tree and the device model
-    if (absorb_lazy_rows())
-    {
-      custom_rows = true;
-      if (!propagate(root_lb, root_ub)) break;      // nothing left inside the root box
-      upload();
-    }
+  // ---- a round: the best open nodes, tightened on the host, packed for the device; false: nothing to solve ----
+  auto assemble = [&](RoundData& R) -> bool {
+    auto& round = R.round; auto& box_lb = R.box_lb; auto& box_ub = R.box_ub; auto& cuts = R.cuts; auto& xs = R.xs;
+    auto& ys = R.ys; auto& x0s = R.x0s; auto& y0s = R.y0s; auto& w0s = R.w0s; auto& btol = R.btol; auto& stats = R.stats;
+    R.error.clear();
     // ---- a round: the best open nodes, tightened on the host, the survivors solved together ----
     double t_mark = elapsed();
     round.clear();
@@ -683,7 +681,7 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
     }
     t_assemble += lap_from(t_mark);
     t_mark = elapsed();
-    if (round.empty()) continue;
+    if (round.empty()) return false;
     ++rounds;
     std::size_t const B = round.size();
     box_lb.resize(B * n);
@@ -725,8 +723,14 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
       }
     }
     t_pack += lap_from(t_mark);
-    t_mark = elapsed();
-    // deal the round to the GPUs: nodes are independent, no device-side exchange
+    return true;
+  };
+
+  // ---- deal the round to the GPUs: nodes are independent, no device-side exchange (runs on its own thread) ----
+  auto run_gpu = [&](RoundData& R) {
+    auto& box_lb = R.box_lb; auto& box_ub = R.box_ub; auto& cuts = R.cuts; auto& xs = R.xs; auto& ys = R.ys;
+    auto& x0s = R.x0s; auto& y0s = R.y0s; auto& w0s = R.w0s; auto& btol = R.btol; auto& stats = R.stats;
+    std::size_t const B = R.round.size();
     {
       std::size_t const G = std::min(gpus.size(), B);
       std::vector<std::thread> workers;
@@ -748,10 +752,15 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
       }
       for (std::thread& t : workers) t.join();
       for (std::string const& e : errors)
-        if (!e.empty()) throw std::logic_error("Cuda backend: " + e);
+        if (!e.empty()) R.error = e;
     }
-    t_gpu += lap_from(t_mark);
-    t_mark = elapsed();
+  };
+
+  // ---- decide the nodes of a solved round: incumbents, pruning, branching ----
+  auto decide = [&](RoundData& R) {
+    auto& round = R.round; auto& xs = R.xs; auto& ys = R.ys; auto& stats = R.stats;
+    std::size_t const B = round.size();
+    double const t_mark = elapsed();
     S.m_info.lp_solves += static_cast<std::int64_t>(B);
     S.m_info.kernel_launches += stats[0].kernel_launches;
     if (user_verbose)
@@ -911,10 +920,73 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
       }
     }
     t_post += lap_from(t_mark);
+  };
+
+  // ---- the loop.  With no lazy-constraint handler attached the rounds are PIPELINED: the host assembles
+  // round k + 1 from the open list as it stands, hands it to the device as soon as round k comes back, and
+  // decides round k (roundings, local searches, branching: half of the wall time of a big tree) while the
+  // device works.  Round k + 1 therefore does not see the children of round k - they join the list one round
+  // later, which a best-first tree with thousands of open nodes does not notice; while the tree is small the
+  // open list is empty at that point and the loop simply waits (no overlap, same order as before).  Handlers
+  // may post rows while a round is decided, and rows mean a new device model: then one round at a time.
+  bool const pipelined = S.m_lazy_handlers.empty() && !(std::getenv("MIPLIB_CUDA_BNB_SYNC") != nullptr);
+  auto limits_hit = [&]() {
+    return (S.m_time_limit > 0 && elapsed() > S.m_time_limit) || S.m_info.nodes >= node_limit;
+  };
+  int cur = 0;
+  std::thread device;
+  RoundData* in_flight = nullptr;
+  auto wait_device = [&]() -> RoundData* {
+    if (!in_flight) return nullptr;
+    double const t_mark = elapsed();
+    device.join();
+    t_gpu += lap_from(t_mark);
+    RoundData* done = in_flight;
+    in_flight = nullptr;
+    if (!done->error.empty()) throw std::logic_error("Cuda backend: " + done->error);
+    return done;
+  };
+  try
+  {
+    while (true)
+    {
+      if (limits_hit())
+      {
+        if (!open.empty()) complete = false;
+        if (RoundData* done = wait_device()) decide(*done);
+        if (!open.empty()) complete = false;
+        break;
+      }
+      // rows posted by lazy handlers during the last round join the tree and the device model
+      if (!in_flight && absorb_lazy_rows())
+      {
+        custom_rows = true;
+        if (!propagate(root_lb, root_ub)) break;      // nothing left inside the root box
+        upload();
+      }
+      RoundData& next = bufs[cur];
+      bool const have_next = assemble(next);
+      RoundData* done = wait_device();
+      if (have_next)
+      {
+        in_flight = &next;
+        device = std::thread(run_gpu, std::ref(next));
+        cur ^= 1;
+        if (!pipelined) done = wait_device();          // one round at a time
+      }
+      if (done) decide(*done);
+      if (!in_flight && !have_next && !done && open.empty()) break;
+    }
   }
+  catch (...)
+  {
+    if (device.joinable()) device.join();
+    throw;
+  }
+  if (device.joinable()) device.join();
   if (timing)
     std::fprintf(stderr, "[miplib cuda b&b] %lld rounds, %lld nodes: assemble (pop + propagate) %.2f s, pack boxes %.2f s, "
-                 "node LPs on the device %.2f s, decide / round / branch %.2f s\n",
+                 "waiting for the device %.2f s, decide / round / branch %.2f s\n",
                  static_cast<long long>(rounds), static_cast<long long>(S.m_info.nodes), t_assemble, t_pack, t_gpu, t_post);
   // Global dual bound.  A finished tree proves the incumbent; an interrupted one (time or node limit) is
   // bounded by its best undecided node: rounds are processed whole, so every such node is either in
