@@ -372,7 +372,10 @@ void CudaSolver::load_csr(Solver const&, std::int64_t m, std::int64_t n, std::in
   // time as the host threads fill the row store: on config 3 the device load (30 - 50 ms) and the host
   // copy (15 - 35 ms) used to run one after the other, the upload reading the copy.  Best effort: without
   // a usable device the model simply stays dirty and solve() reports the missing GPU as before.
-  bool const eager = first == 0 && m_row_lo.empty() && nnz_new >= (std::int64_t(1) << 22) && mipcu_device_count() > 0;
+  // (MIPLIB_CUDA_EAGER_NNZ overrides the size threshold: the tests run this path on small models)
+  char const* eager_env = std::getenv("MIPLIB_CUDA_EAGER_NNZ");
+  std::int64_t const eager_from = eager_env ? std::atoll(eager_env) : (std::int64_t(1) << 22);
+  bool const eager = first == 0 && m_row_lo.empty() && nnz_new >= eager_from && mipcu_device_count() > 0;
   std::thread device_load;
   struct JoinOnExit
   {

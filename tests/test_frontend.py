@@ -520,3 +520,45 @@ def test_full_size_mip_configs_under_a_time_limit(built):
         assert sgn * bound.value >= sgn * root_bound - 2e-6 * (1 + abs(root_bound))   # no worse than the root LP
         assert abs(obj.value - bound.value) <= max_gap * abs(obj.value), (cfg, obj.value, bound.value)
         assert lib.miplib_destroy_solver(solver) == 0
+
+
+@pytest.mark.gpu
+def test_bulk_ingress_eager_device_load_then_append(built, golden, monkeypatch):
+    """miplib_cuda_load_csr on an empty solver of a big model loads the device at once, out of the caller's arrays,
+    while host threads fill the row store (threshold lowered here so that config 1 takes that path).  The solve
+    must then find the model on the device (same optimum), and a later structural change - a second block of
+    columns and rows appended by another load_csr - must reach the device too: the optimum of the block-diagonal
+    model is the sum of the two."""
+    monkeypatch.setenv("MIPLIB_CUDA_EAGER_NNZ", "0")
+    lib, C = _front(built)
+    L1, L2 = gen.config(1), gen.lp(300, 500, 6, 7)
+    solver = C.c_void_p()
+    assert lib.miplib_create_solver(C.byref(solver), 5) == 0
+    lib.miplib_cuda_set_verbose(solver, 0)
+    rc, keep1 = _load_csr(lib, C, solver, L1)
+    assert rc == 0, lib.miplib_get_last_error()
+    result, has, obj = C.c_int(-1), C.c_int(-1), C.c_double()
+    assert lib.miplib_cuda_solve(solver, C.byref(result), C.byref(has)) == 0, lib.miplib_get_last_error()
+    assert (result.value, has.value) == (0, 1)
+    x = np.empty(L1.n)
+    assert lib.miplib_cuda_get_values(solver, x.ctypes.data_as(C.c_void_p), C.byref(obj)) == 0
+    e1 = golden["C1_lp"]["objective"]
+    assert abs(obj.value - e1) <= 1e-6 * (1 + abs(e1))
+    assert abs(float(L1.c @ x) - obj.value) <= 1e-9 * (1 + abs(e1))
+    # append a second, independent block: load_csr REPLACES the objective, so the first block's columns cost 0 now
+    rc, keep2 = _load_csr(lib, C, solver, L2)
+    assert rc == 0, lib.miplib_get_last_error()
+    n, m = C.c_int64(), C.c_int64()
+    assert lib.miplib_cuda_get_shape(solver, C.byref(n), C.byref(m)) == 0
+    assert (n.value, m.value) == (L1.n + L2.n, L1.m + L2.m)
+    assert lib.miplib_cuda_solve(solver, C.byref(result), C.byref(has)) == 0, lib.miplib_get_last_error()
+    assert (result.value, has.value) == (0, 1)
+    xx = np.empty(L1.n + L2.n)
+    assert lib.miplib_cuda_get_values(solver, xx.ctypes.data_as(C.c_void_p), C.byref(obj)) == 0
+    e2 = golden["lp_300x500_s7"]["objective"]
+    assert abs(obj.value - e2) <= 2e-6 * (1 + abs(e2))
+    # the first block is still constrained by its own rows
+    ax = L1.A @ xx[:L1.n]
+    assert np.all(ax <= L1.row_hi + 1e-4 * (1 + np.abs(L1.row_hi))) and np.all(ax >= L1.row_lo - 1e-4 * (1 + np.abs(L1.row_lo)))
+    assert abs(float(L2.c @ xx[L1.n:]) - obj.value) <= 1e-9 * (1 + abs(e2))
+    assert lib.miplib_destroy_solver(solver) == 0
