@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdint>
 #include <cstdlib>
 #include <cstdio>
 #include <deque>
@@ -506,6 +507,60 @@ void CudaBranchAndBound::try_roundings(std::vector<double> const& x, std::vector
     bool const turn = ++polish_candidates <= 32 || polish_candidates % 8 == 0;
     if (pure_integer && (improved || turn) && one_opt(cand)) try_incumbent(cand);
   }
+}
+
+int CudaBranchAndBound::selftest_local_search(std::vector<double> const& x_lp, int trials, std::vector<double>& x_out,
+                                              bool* feasible)
+{
+  double const inf = S.infinity();
+  root_lb.assign(n, 0.0);
+  root_ub.assign(n, 0.0);
+  for (std::size_t j = 0; j < n; ++j)
+  {
+    root_lb[j] = S.m_columns[j].lb <= -inf ? -kInf : S.m_columns[j].lb;
+    root_ub[j] = S.m_columns[j].ub >= inf ? kInf : S.m_columns[j].ub;
+    if (is_int[j]) { root_lb[j] = std::ceil(root_lb[j] - 1e-9); root_ub[j] = std::floor(root_ub[j] + 1e-9); }
+  }
+  if (feasible) *feasible = false;
+  if (!propagate(root_lb, root_ub)) return -1;
+  opt_order.clear();
+  for (std::size_t j = 0; j < n; ++j)
+    if (is_int[j] && cost[j] != 0) opt_order.push_back(static_cast<std::int32_t>(j));
+  std::stable_sort(opt_order.begin(), opt_order.end(),
+                   [&](std::int32_t a, std::int32_t b) { return std::abs(cost[a]) > std::abs(cost[b]); });
+  // incremental against full propagation of single-column branchings (a deterministic walk over the columns)
+  int mismatches = 0;
+  std::uint64_t state = 88172645463325252ull;
+  for (int t = 0; t < trials && n > 0; ++t)
+  {
+    state ^= state << 13; state ^= state >> 7; state ^= state << 17;
+    std::size_t const j = static_cast<std::size_t>(state % n);
+    if (!is_int[j] || root_lb[j] >= root_ub[j]) continue;
+    for (int side = 0; side < 2; ++side)
+    {
+      std::vector<double> la(root_lb), ua(root_ub), lb2(root_lb), ub2(root_ub);
+      if (side == 0) { ua[j] = root_lb[j]; ub2[j] = root_lb[j]; }
+      else { la[j] = root_lb[j] + 1; lb2[j] = root_lb[j] + 1; }
+      bool const full = propagate(la, ua), seeded = propagate(lb2, ub2, static_cast<std::int32_t>(j));
+      if (full != seeded || (full && (la != lb2 || ua != ub2))) ++mismatches;
+    }
+  }
+  x_out.assign(n, 0.0);
+  if (x_lp.size() == n && pure_integer)
+  {
+    for (std::size_t j = 0; j < n; ++j)
+    {
+      double const f = x_lp[j] - std::floor(x_lp[j] + 1e-9);
+      double const v = f >= 0.5 ? std::ceil(x_lp[j] - 1e-9) : std::floor(x_lp[j] + 1e-9);
+      x_out[j] = std::min(std::max(v, root_lb[j]), root_ub[j]);
+    }
+    if (repair(x_out))
+    {
+      one_opt(x_out);
+      if (feasible) *feasible = row_feasible(x_out, 1e-9);
+    }
+  }
+  return mismatches;
 }
 
 std::pair<Solver::Result, bool> CudaBranchAndBound::run()

@@ -33,6 +33,13 @@ struct CudaBranchAndBound
   explicit CudaBranchAndBound(CudaSolver& solver);
   std::pair<Solver::Result, bool> run();
 
+  // Host-only self test of the tree's local machinery (no device needed; miplib_cuda_selftest_local_search):
+  // the root box is propagated, `trials` random single-column branchings are propagated twice - from every
+  // row and from the rows of the branched column only - and must give the same verdict and the same box;
+  // then x_lp is threshold-rounded (0.5), repaired and polished by one_opt.  Returns the number of
+  // propagation mismatches; *feasible says whether the returned point satisfies every row and bound.
+  int selftest_local_search(std::vector<double> const& x_lp, int trials, std::vector<double>& x_out, bool* feasible);
+
   private:
   struct Change { std::int32_t col; double lb, ub; };
   struct Node

@@ -4,7 +4,9 @@
 #include <exception>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
+#include "bnb.hpp"
 #include "solver.hpp"
 
 extern void miplib_store_error(char const* what);   // capi.cpp
@@ -111,6 +113,23 @@ int miplib_cuda_get_bound(miplib::Solver* p_solver, double* best_bound, int* pro
     miplib::CudaSolver const& s = miplib::CudaSolver::of(*p_solver);
     if (best_bound) *best_bound = s.m_info.best_bound;
     if (proven_optimal) *proven_optimal = s.m_info.proven_optimal ? 1 : 0;
+  });
+}
+
+int miplib_cuda_selftest_local_search(miplib::Solver* p_solver, double const* x_lp, int trials, double* x_out,
+                                      int* feasible, int* propagate_mismatches)
+{
+  return guarded([&] {
+    miplib::CudaSolver& s = miplib::CudaSolver::of(*p_solver);
+    std::size_t const n = s.m_columns.size();
+    s.m_objective.resize(n, 0.0);
+    miplib::CudaBranchAndBound bnb(s);
+    std::vector<double> in(x_lp ? std::vector<double>(x_lp, x_lp + n) : std::vector<double>()), out;
+    bool ok = false;
+    int const mism = bnb.selftest_local_search(in, trials, out, &ok);
+    if (x_out && out.size() == n) std::memcpy(x_out, out.data(), sizeof(double) * n);
+    if (feasible) *feasible = ok ? 1 : 0;
+    if (propagate_mismatches) *propagate_mismatches = mism;
   });
 }
 

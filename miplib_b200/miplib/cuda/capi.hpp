@@ -53,6 +53,13 @@ int miplib_cuda_set_time_limit(miplib::Solver* p_solver, double seconds);
 int miplib_cuda_set_nr_threads(miplib::Solver* p_solver, std::int64_t gpus);
 int miplib_cuda_get_bound(miplib::Solver* p_solver, double* best_bound, int* proven_optimal);
 
+// Host-only self test of the branch and bound's local machinery on the loaded (pure-integer) model - no device
+// involved: propagation from the rows of a branched column only must equal propagation from every row (`trials`
+// random branchings; *propagate_mismatches), and x_lp, threshold-rounded, must come back from the greedy repair and
+// the 1-opt pass as a point (x_out, n doubles) that satisfies every row (*feasible).
+int miplib_cuda_selftest_local_search(miplib::Solver* p_solver, double const* x_lp, int trials, double* x_out,
+                                      int* feasible, int* propagate_mismatches);
+
 // Number of columns / alive rows of the lowered model.
 int miplib_cuda_get_shape(miplib::Solver* p_solver, std::int64_t* n, std::int64_t* m);
 

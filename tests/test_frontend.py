@@ -562,3 +562,56 @@ def test_bulk_ingress_eager_device_load_then_append(built, golden, monkeypatch):
     assert np.all(ax <= L1.row_hi + 1e-4 * (1 + np.abs(L1.row_hi))) and np.all(ax >= L1.row_lo - 1e-4 * (1 + np.abs(L1.row_lo)))
     assert abs(float(L2.c @ xx[L1.n:]) - obj.value) <= 1e-9 * (1 + abs(e2))
     assert lib.miplib_destroy_solver(solver) == 0
+
+
+@pytest.mark.parametrize("case", ["setcover", "mkp"])
+def test_branch_and_bound_local_machinery_on_cpu(built, case):
+    """Host side of the tree, no GPU involved (miplib_cuda_selftest_local_search): (i) propagating a child's box
+    from the rows of its branched column only gives the same verdict and the same box as propagating from every
+    row; (ii) an LP point (HiGHS on the CPU), threshold-rounded, comes back from the greedy repair and the 1-opt
+    pass integral and feasible for every row, cheaper than plain rounding-up / rounding-down, and 1-opt: no single
+    column can be moved to its cheaper side without breaking a row."""
+    from oracle import highs_ref
+    lib, C = _front(built)
+    L = gen.set_cover(300, 700, 8, 20264) if case == "setcover" else gen.mkp(12, 300, 4, 6, 20265)
+    lp = highs_ref.solve_lp(L)
+    assert lp["status"] == 0
+    x_lp = np.ascontiguousarray(lp["x"], dtype=np.float64)
+    solver = C.c_void_p()
+    assert lib.miplib_create_solver(C.byref(solver), 5) == 0
+    rc, keep = _load_csr(lib, C, solver, L, np.ones(L.n, np.int32))          # every column Binary
+    assert rc == 0, lib.miplib_get_last_error()
+    x = np.empty(L.n); feas = C.c_int(-1); mism = C.c_int(-1)
+    lib.miplib_cuda_selftest_local_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert lib.miplib_cuda_selftest_local_search(solver, x_lp.ctypes.data_as(C.c_void_p), 200,
+                                                 x.ctypes.data_as(C.c_void_p), C.byref(feas), C.byref(mism)) == 0, \
+        lib.miplib_get_last_error()
+    assert mism.value == 0
+    assert feas.value == 1
+    assert np.array_equal(x, np.round(x)) and x.min() >= 0 and x.max() <= 1
+    A = L.A.tocsc()
+    ax = L.A @ x
+    assert np.all(ax <= L.row_hi + 1e-9) and np.all(ax >= L.row_lo - 1e-9)
+    sgn = -1.0 if L.maximize else 1.0
+    cost = sgn * L.c
+    # no worse than the plain rounding of this model class when that is feasible (covering: up), and than the
+    # trivial point otherwise (the switch rows of the knapsack make rounding down infeasible; all-zero is feasible)
+    plain = np.ceil(x_lp - 1e-9) if case == "setcover" else np.floor(x_lp + 1e-9)
+    ap = L.A @ plain
+    if not (np.all(ap <= L.row_hi + 1e-9) and np.all(ap >= L.row_lo - 1e-9)):
+        plain = np.zeros(L.n)
+        assert np.all(L.row_lo <= 1e-9) and np.all(L.row_hi >= -1e-9)
+    assert cost @ x <= cost @ plain + 1e-9
+    # 1-opt: no column can take one step towards its cheaper side
+    for j in range(L.n):
+        if cost[j] == 0:
+            continue
+        d = -1.0 if cost[j] > 0 else 1.0
+        if not (0 <= x[j] + d <= 1):
+            continue
+        col = A[:, j]
+        a2 = ax.copy(); a2[col.indices] += col.data * d
+        assert np.any(a2 > L.row_hi + 1e-9) or np.any(a2 < L.row_lo - 1e-9), j
+    # within reach of the LP bound (measured: a few per cent on these sizes)
+    assert abs(cost @ x - sgn * lp["obj"]) <= 0.15 * abs(lp["obj"])
+    assert lib.miplib_destroy_solver(solver) == 0
