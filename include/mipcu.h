@@ -77,11 +77,12 @@ enum {
                                      when the box supports it; 0: unicast stores into every peer.  Set before load;
                                      after load it reads back 1 only if the window is in use on every rank */
   MIPCU_PARAM_ROW_SORT = 14,      /* load-time ordering of the device copies, invisible through this ABI (every vector is
-                                     permuted at the boundary).  2 (default): rows stored sorted by decreasing length (no
-                                     padding in the sliced-ELL copy) AND columns binned by (length, first row), so that the
-                                     32 columns of a slice start in neighbouring lines of the gathered vector (row-sharded
-                                     contexts keep the caller's column numbering, i.e. behave as 1); 1: rows by length
-                                     only; 0: the caller's order.  Set before load */
+                                     permuted at the boundary).  3 (default): rows stored sorted by decreasing length (no
+                                     padding in the sliced-ELL copy), columns binned by (length, first row), so that the
+                                     32 columns of a slice start in neighbouring lines of the gathered vector, and the rows
+                                     of equal length re-sorted by their first (new) column for the same reason (row-sharded
+                                     contexts keep the caller's column numbering, i.e. behave as 1); 2: without the second
+                                     row sort; 1: rows by length only; 0: the caller's order.  Set before load */
   MIPCU_PARAM_PEER_TIMEOUT = 15,  /* row-sharded contexts: seconds a kernel waits at a cross-GPU barrier for its peers
                                      (default 120; 0 = forever).  On expiry the solve returns rc = 1 with a message
                                      instead of hanging or trapping: sharded load / solve are collective and fail-stop */

@@ -428,6 +428,12 @@ __global__ void k_len_first_keys(const int* __restrict__ ptr, const int* __restr
   }
 }
 
+// out[i] = in[perm[i]] (composition of two row permutations)
+__global__ void k_gather_ints(const int* __restrict__ in, const int* __restrict__ perm, int* __restrict__ out, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = in[perm[i]];
+}
+
 __global__ void k_invert_perm(const int* __restrict__ perm, int* __restrict__ inv, int count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) inv[perm[i]] = i;
@@ -569,8 +575,8 @@ int* sort_rows_by_length(mipcu_ctx* ctx, Csr& A, bool by_first = false) {
 // column of the model).  Its rows are sorted by (decreasing length, first row index) - columns of a
 // 32-column slice then start in neighbouring lines of yhat - and A is rebuilt from the permuted T, so the
 // column indices inside a row of A are the NEW ones, increasing.  Leaves ctx->col_perm / col_inv.
-// Measured on config 3 (profiles/r02_locality.md): requests per gathered double 0.999 -> 0.939 on the
-// column step (0.990 on the row step), column kernel -5 %, row kernel -3 %.
+// Measured on config 3 (profiles/r02_locality.md): requests per gathered double 0.999 -> 0.935 on the
+// column step, 0.978 on the row step after the second row sort below; column kernel -5 %, row kernel -4 %.
 void bin_columns(mipcu_ctx* ctx, Csr& A, Csr& T) {
   int* cperm = sort_rows_by_length(ctx, T, true);
   if (!cperm) return;
@@ -583,6 +589,29 @@ void bin_columns(mipcu_ctx* ctx, Csr& A, Csr& T) {
   free_csr(A);
   build_transpose(ctx, T, A);       // entries of a row come out sorted by the new column index
   A.tpr = tpr;
+  // and the rows once more, by (length, first NEW column): the first entries of a slice's rows then sit in
+  // neighbouring lines of xbar as well (config 3: requests per gathered double on the row side 0.990 -> 0.978,
+  // column side 0.939 -> 0.935; scripts/locality_lab.py).  The rows get new numbers, so K' is rebuilt from the
+  // re-sorted rows (same column order), and the row permutation is the composition of the two sorts.
+  if (ctx->params[MIPCU_PARAM_ROW_SORT] < 3.0) return;
+  if (int* again = sort_rows_by_length(ctx, A, true)) {
+    const int m = A.nrows;
+    if (ctx->row_perm) {
+      int* composed = dalloc<int>(m);
+      k_gather_ints<<<grid_for(m), kThreads, 0, ctx->stream>>>(ctx->row_perm, again, composed, m);
+      ctx->launches++;
+      MIPCU_CK(cudaStreamSynchronize(ctx->stream));
+      dfree(ctx->row_perm);
+      dfree(again);
+      ctx->row_perm = composed;
+    } else {
+      ctx->row_perm = again;
+    }
+    const int ttpr = T.tpr;
+    free_csr(T);
+    build_transpose(ctx, A, T);
+    T.tpr = ttpr;
+  }
 }
 
 }  // namespace
