@@ -77,7 +77,8 @@ enum {
                                      when the box supports it; 0: unicast stores into every peer.  Set before load;
                                      after load it reads back 1 only if the window is in use on every rank */
   MIPCU_PARAM_ROW_SORT = 14,      /* load-time ordering of the device copies, invisible through this ABI (every vector is
-                                     permuted at the boundary).  3 (default): rows stored sorted by decreasing length (no
+                                     permuted at the boundary).  4 (default): as 3, with a second (columns, rows) round.
+                                     3: rows stored sorted by decreasing length (no
                                      padding in the sliced-ELL copy), columns binned by (length, first row), so that the
                                      32 columns of a slice start in neighbouring lines of the gathered vector, and the rows
                                      of equal length re-sorted by their first (new) column for the same reason (row-sharded

@@ -69,7 +69,7 @@ void set_default_params(mipcu_ctx* ctx) {
   ctx->params[MIPCU_PARAM_SHARD_EXCHANGE] = 2;
   ctx->params[MIPCU_PARAM_USE_PDL] = 0;
   ctx->params[MIPCU_PARAM_MULTICAST] = 1;
-  ctx->params[MIPCU_PARAM_ROW_SORT] = 3;
+  ctx->params[MIPCU_PARAM_ROW_SORT] = 4;
   ctx->params[MIPCU_PARAM_PEER_TIMEOUT] = 120.0;
   ctx->params[MIPCU_PARAM_VALIDATE] = 0;
 }

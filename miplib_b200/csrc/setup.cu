@@ -578,39 +578,48 @@ int* sort_rows_by_length(mipcu_ctx* ctx, Csr& A, bool by_first = false) {
 // Measured on config 3 (profiles/r02_locality.md): requests per gathered double 0.999 -> 0.935 on the
 // column step, 0.978 on the row step after the second row sort below; column kernel -5 %, row kernel -4 %.
 void bin_columns(mipcu_ctx* ctx, Csr& A, Csr& T) {
-  int* cperm = sort_rows_by_length(ctx, T, true);
-  if (!cperm) return;
-  const int n = T.nrows;
-  ctx->col_perm = cperm;
-  ctx->col_inv = dalloc<int>(n);
-  k_invert_perm<<<grid_for(n), kThreads, 0, ctx->stream>>>(cperm, ctx->col_inv, n);
-  ctx->launches++;
-  const int tpr = A.tpr;
-  free_csr(A);
-  build_transpose(ctx, T, A);       // entries of a row come out sorted by the new column index
-  A.tpr = tpr;
-  // and the rows once more, by (length, first NEW column): the first entries of a slice's rows then sit in
-  // neighbouring lines of xbar as well (config 3: requests per gathered double on the row side 0.990 -> 0.978,
-  // column side 0.939 -> 0.935; scripts/locality_lab.py).  The rows get new numbers, so K' is rebuilt from the
-  // re-sorted rows (same column order), and the row permutation is the composition of the two sorts.
-  if (ctx->params[MIPCU_PARAM_ROW_SORT] < 3.0) return;
-  if (int* again = sort_rows_by_length(ctx, A, true)) {
-    const int m = A.nrows;
-    if (ctx->row_perm) {
-      int* composed = dalloc<int>(m);
-      k_gather_ints<<<grid_for(m), kThreads, 0, ctx->stream>>>(ctx->row_perm, again, composed, m);
-      ctx->launches++;
-      MIPCU_CK(cudaStreamSynchronize(ctx->stream));
-      dfree(ctx->row_perm);
-      dfree(again);
-      ctx->row_perm = composed;
-    } else {
-      ctx->row_perm = again;
-    }
+  const int n = T.nrows, m = A.nrows;
+  // perm (new -> previous numbering) applied on top of *total (previous -> caller's); takes ownership of perm
+  auto compose = [&](int*& total, int* perm, int count) {
+    if (!total) { total = perm; return; }
+    int* composed = dalloc<int>(count);
+    k_gather_ints<<<grid_for(count), kThreads, 0, ctx->stream>>>(total, perm, composed, count);
+    ctx->launches++;
+    MIPCU_CK(cudaStreamSynchronize(ctx->stream));
+    dfree(total);
+    dfree(perm);
+    total = composed;
+  };
+  // MIPCU_PARAM_ROW_SORT: 2 = columns once; 3 = columns, then rows; 4 = two (columns, rows) rounds.  Every
+  // round re-sorts one side by (length, first index in the OTHER side's current numbering) and rebuilds the
+  // other copy; requests per gathered double on config 3 (scripts/locality_lab.py), row / column side:
+  // 0.990 / 0.939 (2), 0.978 / 0.935 (3), 0.971 / 0.929 (4), 0.970 / 0.927 (a third round: not worth its 6 ms).
+  const int mode = (int)ctx->params[MIPCU_PARAM_ROW_SORT];
+  const int rounds = mode >= 4 ? 2 : 1;
+  for (int r = 0; r < rounds; ++r) {
+    int* cperm = sort_rows_by_length(ctx, T, true);
+    if (!cperm) break;
+    compose(ctx->col_perm, cperm, n);
+    const int tpr = A.tpr;
+    free_csr(A);
+    build_transpose(ctx, T, A);       // entries of a row come out sorted by the new column index
+    A.tpr = tpr;
+    if (mode < 3) break;
+    // the rows, by (length, first NEW column): the first entries of a slice's rows then sit in neighbouring
+    // lines of xbar as well.  The rows get new numbers, so K' is rebuilt from the re-sorted rows (same column
+    // order), and the row permutation is the composition of the sorts.
+    int* again = sort_rows_by_length(ctx, A, true);
+    if (!again) break;
+    compose(ctx->row_perm, again, m);
     const int ttpr = T.tpr;
     free_csr(T);
     build_transpose(ctx, A, T);
     T.tpr = ttpr;
+  }
+  if (ctx->col_perm) {
+    ctx->col_inv = dalloc<int>(n);
+    k_invert_perm<<<grid_for(n), kThreads, 0, ctx->stream>>>(ctx->col_perm, ctx->col_inv, n);
+    ctx->launches++;
   }
 }
 

@@ -1,4 +1,4 @@
-"""A/B of MIPCU_PARAM_ROW_SORT = 1 / 2 / 3 on one box: isolated launch times of the two fused kernels (config 3)."""
+"""A/B of MIPCU_PARAM_ROW_SORT = 1 / 2 / 3 / 4 on one box: isolated launch times of the two fused kernels (config 3)."""
 import json, sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -6,7 +6,7 @@ from miplib_b200 import Engine
 from oracle import gen
 L = gen.config(int(sys.argv[1]) if len(sys.argv) > 1 else 3)
 for rep in range(2):
-    for mode in (1, 2, 3):
+    for mode in (1, 2, 3, 4):
         with Engine(0) as e:
             e.set_param("row_sort", mode)
             e.load_lp(L)

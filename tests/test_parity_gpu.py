@@ -271,7 +271,7 @@ def test_load_time_ordering_is_invisible(engine):
     rng = np.random.default_rng(3)
     v, w = rng.standard_normal(L.n), rng.standard_normal(L.m)
     out = {}
-    for mode in (0, 1, 2, 3):
+    for mode in (0, 1, 2, 3, 4):
         engine.set_param("row_sort", mode)
         engine.load_lp(L)
         assert np.abs(engine.spmv(v) - L.A @ v).max() <= 1e-12
@@ -300,8 +300,8 @@ def test_load_time_ordering_is_invisible(engine):
         assert all(s.status == "optimal" for s in stb)
         assert np.all(xb[1][cols] <= 0.25 + 1e-9) and abs(xb[2][5] - 1.0) <= 1e-12
         out[mode] = (st.primal_obj, st2.primal_obj, [s.primal_obj for s in stb], d1, d2, x)
-    engine.set_param("row_sort", 3)
-    for mode in (1, 2, 3):
+    engine.set_param("row_sort", 4)
+    for mode in (1, 2, 3, 4):
         assert rel(out[mode][0], out[0][0]) <= 2e-6 and rel(out[mode][1], out[0][1]) <= 2e-6
         assert max(rel(a, b) for a, b in zip(out[mode][2], out[0][2])) <= 4e-6
         assert np.abs(out[mode][3] - out[0][3]).max() <= 1e-12 * np.abs(out[0][3]).max()      # same scalings,
