@@ -415,7 +415,8 @@ def run_cuda(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": config_dict(args.config, m, n, int(A.nnz)),
-        "layout": {"matrix_format": "SELL-32-256, one lane per row (CSR lanes-per-row kernels for long-row models)",
+        "layout": {"matrix_format": "SELL-32-256, one lane per row (CSR lanes-per-row kernels for long-row models); rows sorted by "
+                                    "length, columns and rows binned by their first index at load (single-GPU contexts)",
                    "parallelism": "single GPU" if world == 1 else
                    f"row-sharded x{world}, " + {
                        2: "block-owner exchange: each rank streams its row block of K and its column block of K', "
