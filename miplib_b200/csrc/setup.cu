@@ -868,7 +868,10 @@ void load_lp(mipcu_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* r
     }
   }
   lap("matrix on the device, validated");
-  if (ctx->params[MIPCU_PARAM_ROW_SORT] != 0.0) ctx->row_perm = sort_rows_by_length(ctx, A);
+  // (rows of equal length by their first column from ROW_SORT = 3 on: on row-sharded contexts, which keep the
+  // caller's column numbering, this is the part of the load-time ordering that is purely local to a rank)
+  if (ctx->params[MIPCU_PARAM_ROW_SORT] != 0.0)
+    ctx->row_perm = sort_rows_by_length(ctx, A, ctx->params[MIPCU_PARAM_ROW_SORT] >= 3.0);
   lap("rows sorted by length");
   build_transpose(ctx, A, ctx->cols);
   lap("transpose");
