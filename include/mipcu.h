@@ -175,7 +175,10 @@ int  mipcu_solve_lp_batch(mipcu_ctx* ctx, int32_t B, const double* lb, const dou
  * than the node's cutoff by more than 2 branch_tol (1 + |pobj| + |dobj|) - such a node cannot be pruned
  * by bound however accurately it is solved, so a branch and bound need not wait for 1e-6 (no cutoff:
  * any branch_tol-accurate point qualifies).  y_out ([B][m]) may be NULL.  stats[b].row/col_kernel_us
- * and _bytes describe the batched kernels with all B problems in flight. */
+ * and _bytes describe the batched kernels with all B problems in flight.
+ * A node's result (x, duals, iterations, status) does not depend on B or on which other nodes share
+ * the call: the kernels pick their launch shape from the number of nodes still running, but every
+ * node's sums are formed in one order and every rounding of its step is pinned (bit-identical). */
 int  mipcu_solve_lp_batch_warm(mipcu_ctx* ctx, int32_t B, const double* lb, const double* ub,
                                const double* cutoff, const double* x0, const double* y0,
                                const double* primal_weight0, const double* branch_tol,
