@@ -271,6 +271,28 @@ def _load_csr(lib, C, solver, L, types=None):
     return lib.miplib_cuda_load_csr(solver, L.m, L.n, *ptrs, int(L.maximize)), arrs
 
 
+def test_bulk_ingress_without_a_device_stays_host_only(built, monkeypatch):
+    """The eager device load of miplib_cuda_load_csr is best effort: with no usable GPU (this container) the call
+    must still build the row store and succeed, even when the size threshold says "load the device now"."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    monkeypatch.setenv("MIPLIB_CUDA_EAGER_NNZ", "0")
+    lib, C = _front(built)
+    solver = C.c_void_p()
+    assert lib.miplib_create_solver(C.byref(solver), 5) == 0
+    L = gen.config(1)
+    rc, _ = _load_csr(lib, C, solver, L)
+    assert rc == 0, lib.miplib_get_last_error()
+    n, m = C.c_int64(), C.c_int64()
+    assert lib.miplib_cuda_get_shape(solver, C.byref(n), C.byref(m)) == 0
+    assert (n.value, m.value) == (L.n, L.m)
+    result, has = C.c_int(-1), C.c_int(-1)
+    assert lib.miplib_cuda_solve(solver, C.byref(result), C.byref(has)) == 1       # no device: an error, not a fallback
+    assert b"no CUDA device" in lib.miplib_get_last_error() or b"Cuda backend" in lib.miplib_get_last_error()
+    assert lib.miplib_destroy_solver(solver) == 0
+
+
 def test_bulk_ingress_builds_the_same_row_store(built):
     lib, C = _front(built)
     solver = C.c_void_p()
