@@ -159,3 +159,38 @@ def test_golden_trace_reproduces():
     r = pdhg_ref.solve(L, period=64, max_iter=64, trace_at=(10, 64))
     assert np.allclose(r["trace"][10][0], z["xbar10"], rtol=0, atol=1e-13)
     assert np.allclose(r["trace"][64][1], z["y64"], rtol=0, atol=1e-12)
+
+
+def test_requests_per_gathered_double_and_the_load_time_ordering():
+    """scripts/locality_lab.py counts, on the host, the unit that binds the fused SpMV kernels: distinct 128-byte
+    lines per (32-row slice, gather step).  Pinned here on configs 1 and 2: a uniformly random pattern has (almost)
+    one request per gathered double; sorting the columns of equal length by their first row, and then the rows by
+    their first new column - what setup.cu: bin_columns does on the device - removes the share profiles/r02_locality.md
+    reports, and a second round removes a little more."""
+    from scripts.locality_lab import requests_per_nnz
+    L = gen.config(2)
+    A = L.A.tocsr(); A.sort_indices()
+    AT = A.T.tocsr(); AT.sort_indices()
+    row0, col0 = requests_per_nnz(A), requests_per_nnz(AT)
+    assert 0.99 <= row0 <= 1.0 and 0.99 <= col0 <= 1.0
+
+    def first_len(M):
+        lens = np.diff(M.indptr)
+        return M.indices[np.minimum(M.indptr[:-1], M.nnz - 1)], lens
+
+    lens = np.diff(A.indptr)
+    M = A[np.argsort(-lens, kind="stable")].tocsr()
+    seen = []
+    for _ in range(2):                                   # two (columns, rows) rounds, as shipped
+        T = M.T.tocsr(); T.sort_indices()
+        f, l = first_len(T)
+        M = M[:, np.lexsort((f, -l))].tocsr(); M.sort_indices()
+        f, l = first_len(M)
+        M = M[np.lexsort((f, -l))].tocsr()
+        T = M.T.tocsr(); T.sort_indices()
+        seen.append((requests_per_nnz(M), requests_per_nnz(T)))
+    (r1, c1), (r2, c2) = seen
+    assert r1 <= 0.96 and c1 <= 0.875                  # config 2: 0.957 / 0.870 after one round
+    assert r2 < r1 and c2 < c1 and r2 <= 0.94 and c2 <= 0.86      # 0.935 / 0.853 after two
+    # the permutations only relabel: same multiset of row lengths and of values
+    assert np.array_equal(np.sort(np.diff(M.indptr)), np.sort(lens)) and abs(M.data.sum() - A.data.sum()) <= 1e-9 * A.nnz
