@@ -492,7 +492,7 @@ void CudaBranchAndBound::try_roundings(std::vector<double> const& x, std::vector
     if (cost[j] == 0) continue;
     for (int mode = 0; mode < 3; ++mode) value[mode] += cost[j] * rounded(j, mode);
   }
-  std::vector<double> cand;
+  std::vector<double>& cand = rounding_scratch;
   for (int mode = 0; mode < 3; ++mode)
   {
     bool const had = have_incumbent;
@@ -823,6 +823,8 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
                    B, static_cast<long long>(S.m_info.nodes), open.size(),
                    have_incumbent ? sgn * best : std::nan(""));
 
+    std::vector<double> x;                 // one buffer for the whole round (a fresh 8 n-byte vector per node
+    std::vector<Change> inherited;         // goes through mmap / munmap on big models)
     for (std::size_t b = 0; b < B; ++b)
     {
       Node const& node = round[b].node;
@@ -830,7 +832,7 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
       std::vector<double> const& ub = round[b].ub;
       mipcu_stats const& lp = stats[b];
       S.m_info.lp_iterations += lp.iterations;
-      std::vector<double> x(xs.begin() + b * n, xs.begin() + (b + 1) * n);
+      x.assign(xs.begin() + b * n, xs.begin() + (b + 1) * n);
       if (lp.status == MIPCU_CUTOFF) continue;       // bound (or infeasibility) proven by the dual
       if (lp.status == MIPCU_INFEASIBLE) continue;   // Farkas certificate from the engine
       if (lp.status == MIPCU_UNBOUNDED || lp.status == MIPCU_INFEASIBLE_OR_UNBOUNDED)
@@ -949,7 +951,7 @@ std::pair<Solver::Result, bool> CudaBranchAndBound::run()
         py = std::make_shared<std::vector<double> const>(ys.begin() + b * m, ys.begin() + (b + 1) * m);
       }
       // carry every bound propagation found, so the children start from the tightened box
-      std::vector<Change> inherited;
+      inherited.clear();
       for (std::size_t j = 0; j < n; ++j)
         if (lb[j] != root_lb[j] || ub[j] != root_ub[j])
           inherited.push_back({static_cast<std::int32_t>(j), lb[j], ub[j]});

@@ -85,6 +85,7 @@ struct CudaBranchAndBound
   bool have_incumbent = false;
   bool lazy_rejected = false, lazy_added = false;   // outcome of the last try_incumbent
   std::vector<double> best_x;
+  std::vector<double> rounding_scratch;   // try_roundings' candidate (kept between calls)
   std::vector<double> root_lb, root_ub;   // the root box after propagation (what an incumbent must respect)
   std::vector<std::int32_t> opt_order;    // integer columns with a cost, most expensive first (one_opt)
   std::int64_t rows_epoch = 0;            // bumped whenever rows join the tree (lazy handlers, implied bounds)
